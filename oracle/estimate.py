@@ -155,24 +155,17 @@ def locate(forest, dofs, X):
     ijk = np.clip(np.floor(fpos).astype(np.int64), 0, forest.reps - 1)
     lev = np.zeros(n, dtype=np.int64)
     idx = forest.lookup(0, ijk)
-    while True:
-        go = np.zeros(n, dtype=bool)
-        for l in range(forest.n_levels):
-            m = lev == l
-            if m.any():
-                go[m] = forest.child0[l][idx[m]] >= 0
-        if not go.any():
-            break
-        for l in range(forest.n_levels - 1):
-            m = go & (lev == l)
-            if not m.any():
-                continue
-            h = forest.h(l + 1)
-            nn = forest.cells_per_axis(l + 1)
-            cijk = np.clip(np.floor((X[m] - forest.lo) / h).astype(np.int64), 2 * forest.ijk[l][idx[m]],
-                           2 * forest.ijk[l][idx[m]] + 1)
-            idx[m] = forest.lookup(l + 1, cijk)
-            lev[m] = l + 1
+    for l in range(forest.n_levels - 1):
+        m = lev == l
+        if m.any():
+            m[m] = forest.child0[l][idx[m]] >= 0
+        if not m.any():
+            continue
+        h = forest.h(l + 1)
+        cijk = np.clip(np.floor((X[m] - forest.lo) / h).astype(np.int64), 2 * forest.ijk[l][idx[m]],
+                       2 * forest.ijk[l][idx[m]] + 1)
+        idx[m] = forest.lookup(l + 1, cijk)
+        lev[m] = l + 1
     xi = np.zeros_like(X)
     for l in range(forest.n_levels):
         m = lev == l

@@ -1,0 +1,101 @@
+"""Transcribe the reference's golden stdout files into tests/golden/reference_goldens.json.
+
+Run in the build container (reads /root/reference, which does not exist on the GPU box):
+    python tests/golden/make_reference_goldens.py
+Every number is kept as the printed string's float together with file and line.  Also writes the
+small LAMMPS atom files the golden runs use (regenerated from their published coordinates by
+oracle.lammps.write, not copied)."""
+import json
+import os
+import re
+import sys
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+KEYS = [
+    (r"Number of active cells:\s+(\d+)", "n_active_cells", int),
+    (r"Number of degrees of freedom:\s+(\d+) \(by level: ([\d, ]+)\)", "n_dofs", None),
+    (r"L1 rhs norm (\S+)", "rhs_l1", float), (r"L2 rhs norm (\S+)", "rhs_l2", float),
+    (r"LInfinity rhs norm (\S+)", "rhs_linf", float),
+    (r"L1 Matrix norm (\S+)", "mat_l1", float), (r"LInfinity Matrix norm (\S+)", "mat_linf", float),
+    (r"Frobenius Matrix norm (\S+)", "mat_frob", float),
+    (r"Starting value (\S+)", "start", float), (r"CG converged in (\d+) iterations", "its", int),
+    (r"Convergence value (\S+)", "conv", float),
+    (r"L1 solution norm (\S+)", "sol_l1", float), (r"L2 solution norm (\S+)", "sol_l2", float),
+    (r"LInfinity solution norm (\S+)", "sol_linf", float),
+    (r"Threshold value for refinement:\s+(\S+)", "threshold", float),
+    (r"Total analytical electrostatic energy :\s+(\S+)", "energy_analytic", float),
+    (r"Short-ranged energy contribution :\s+(\S+)", "energy_short", float),
+    (r"FE solution long-ranged energy contribution :\s+(\S+)", "energy_fe", float),
+    (r"Self energy contribution :\s+(\S+)", "energy_self", float),
+    (r"Total electrostatic energy with split in short- and long-ranged :\s+(\S+)", "energy_total", float),
+    (r"Error in FE solution in energy norm:\s+(\S+)", "energy_norm_error", float),
+]
+
+
+def parse(relpath):
+    runs, run, cyc = [], None, None
+    with open(os.path.join(REF, relpath)) as f:
+        for no, line in enumerate(f, 1):
+            if line.startswith("Problem type is:"):
+                run = dict(file=relpath, line=no, cycles=[])
+                runs.append(run)
+                continue
+            if run is None:
+                continue
+            m = re.match(r"Number of atoms: (\d+)", line)
+            if m:
+                run["n_atoms"] = int(m.group(1))
+            m = re.match(r"Running with \w+ on (\d+) MPI", line)
+            if m:
+                run["ranks"] = int(m.group(1))
+            m = re.match(r"Cycle (\d+):", line)
+            if m:
+                cyc = dict(cycle=int(m.group(1)), line=no)
+                run["cycles"].append(cyc)
+                continue
+            if cyc is None:
+                continue
+            for pat, key, conv in KEYS:
+                m = re.search(pat, line)
+                if m:
+                    if key == "n_dofs":
+                        cyc["n_dofs"] = int(m.group(1))
+                        cyc["n_dofs_level"] = [int(t) for t in m.group(2).split(",")]
+                    else:
+                        cyc[key] = conv(m.group(1))
+                        cyc[key + "_digits"] = m.group(1)
+                    break
+    return runs
+
+
+FILES = {
+    "gaussian_charges_mpirun1": "tests/gaussian-charges.mpirun=1.output",
+    "gaussian_charges_mpirun3": "tests/gaussian-charges.mpirun=3.output",
+    "gaussian_charges_mpirun7": "tests/gaussian-charges.mpirun=7.output",
+    "step16_3d": "tests_3D/step-16.mpirun=1.output",
+    "step16_2d": "tests_2D/step-16.mpirun=1.output",
+    "gaussian_function_3d": "tests_3D/gaussian-charges.mpirun=1.output",
+    "gaussian_function_2d": "tests_2D/gaussian-charges.mpirun=1.output",
+    "optimal_parameters": "tests/test_with_optimal_parameters.mpirun=1.output",
+    "rc_variation": "tests_rhs_rc_variation/rc_variation.mpirun=1.output",
+    "cluster_ssor_run": "Cluster runs output and postprocessing/SSOR_run.o876223",
+    "cluster_ssor_64k": "Cluster runs output and postprocessing/SSOR_64k_atoms.o876224",
+    "cluster_without_opti": "Cluster runs output and postprocessing/without_opti.o875054",
+}
+
+if __name__ == "__main__":
+    out = {k: parse(v) for k, v in FILES.items()}
+    with open(os.path.join(HERE, "reference_goldens.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    from oracle import lammps
+    import numpy as np
+    for src, dst in (("tests/atom_n1_2.data", "atom_n1_2.data"), ("tests/atom_2.data", "atom_2.data"),
+                     ("atom/atom_n1_8.data", "atom_n1_8.data")):
+        pos, q, _ = lammps.read(os.path.join(REF, src))
+        lammps.write(os.path.join(HERE, dst), pos, q)
+        p2, q2, _ = lammps.read(os.path.join(HERE, dst))
+        assert np.array_equal(pos, p2) and np.array_equal(q, q2)
+    print({k: [len(r["cycles"]) for r in v] for k, v in out.items()})
