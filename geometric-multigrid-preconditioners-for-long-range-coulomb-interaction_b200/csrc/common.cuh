@@ -1,0 +1,117 @@
+// Shared device helpers for the sm_100a kernels: warp/block reductions, deterministic grid-wide
+// reductions ("last block finalises, fixed order"), streaming loads.
+#pragma once
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdint.h>
+
+namespace gmg {
+
+constexpr int WARP = 32;
+constexpr int SLICE = 32;  // sliced-ELL slice height = one warp
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Sum over the block; result valid in thread 0.  `red` needs blockDim.x/32 doubles.
+__device__ __forceinline__ double block_sum(double v, double *red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect `red` against a previous use
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    r = (lane < nw) ? red[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+__device__ __forceinline__ double block_max(double v, double *red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    r = (lane < nw) ? red[lane] : 0.0;
+    r = warp_max(r);
+  }
+  return r;
+}
+
+// Sum `n` partials in a fixed order with one warp (lane-strided serial sums, then a shuffle tree):
+// every block that calls this on the same data obtains the same bits.
+__device__ __forceinline__ double warp_sum_partials(const volatile double *p, int n) {
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (int i = lane; i < n; i += 32) s += p[i];
+  return warp_sum(s);
+}
+
+// Grid-wide deterministic reduction for ordinary (non-cooperative) launches: every block stores its
+// partial, the last block to arrive sums all partials in fixed order and writes *out.
+// `counter` must be 0 before the launch and is left at 0.
+__device__ __forceinline__ void grid_sum_finalize(double block_value /*thread 0*/, double *partials,
+                                                  unsigned int *counter, double *out, double *red) {
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = block_value;
+    __threadfence();
+    const unsigned int t = atomicInc(counter, gridDim.x - 1);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double s = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += ((volatile double *)partials)[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) *out = s;
+  }
+}
+
+// streaming (read-once) loads: keep the matrix stream out of L1 so the gathered vector stays there
+__device__ __forceinline__ double2 ld_stream_d2(const double2 *p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int2 ld_stream_i2(const int2 *p) {
+  int2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+struct SellView {
+  int n_rows, n_cols, n_slices;
+  const int64_t *slice_ptr;  // n_slices + 1 element offsets (multiples of 64)
+  const double *val;
+  const int *col;
+};
+
+struct PcgScalars {
+  double gh[2];   // g.h, double-buffered (beta = gh[new] / gh[old])
+  double dh;      // d.(A d)
+  double res2;    // g.g
+  double tmp;
+};
+
+struct CgResult {
+  int iterations;
+  int status;  // 0 converged, 1 max iterations reached
+  double res0, res;
+};
+
+}  // namespace gmg

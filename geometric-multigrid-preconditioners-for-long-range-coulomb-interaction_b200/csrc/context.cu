@@ -1,0 +1,1089 @@
+// gmg_b200 C ABI: hierarchy hand-over, setup, V-cycle, PCG, coarse CG (see include/gmg_b200.h).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "context.h"
+#include "kernels.cuh"
+
+using namespace gmg;
+
+namespace gmg {
+
+int fail(gmg_context *h, int code, const std::string &msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------ memory helpers
+template <class T>
+static cudaError_t dalloc(T **p, int64_t n) {
+  return cudaMalloc((void **)p, (size_t)std::max<int64_t>(n, 1) * sizeof(T));
+}
+template <class T>
+static void dfree(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+static void free_sell(Sell &s) {
+  dfree(s.slice_ptr);
+  dfree(s.val);
+  dfree(s.col);
+  s = Sell{};
+}
+static void free_csr(DevCsr &c) {
+  dfree(c.rowptr);
+  dfree(c.col);
+  dfree(c.val);
+  c = DevCsr{};
+}
+
+int ensure_stage(gmg_context *h, int64_t n) {
+  if (n <= h->stage_n) return GMG_OK;
+  dfree(h->stage_a);
+  dfree(h->stage_b);
+  GMG_CUDA(h, dalloc(&h->stage_a, n));
+  GMG_CUDA(h, dalloc(&h->stage_b, n));
+  h->stage_n = n;
+  return GMG_OK;
+}
+
+static int upload_csr(gmg_context *h, int n_rows, int n_cols, const int64_t *rowptr, const int32_t *col,
+                      const double *val, DevCsr &out) {
+  free_csr(out);
+  out.n_rows = n_rows;
+  out.n_cols = n_cols;
+  out.nnz = rowptr[n_rows];
+  GMG_CUDA(h, dalloc(&out.rowptr, n_rows + 1));
+  GMG_CUDA(h, dalloc(&out.col, out.nnz));
+  GMG_CUDA(h, dalloc(&out.val, out.nnz));
+  GMG_CUDA(h, cudaMemcpyAsync(out.rowptr, rowptr, sizeof(int64_t) * (n_rows + 1), cudaMemcpyHostToDevice, h->stream));
+  GMG_CUDA(h, cudaMemcpyAsync(out.col, col, sizeof(int) * out.nnz, cudaMemcpyHostToDevice, h->stream));
+  GMG_CUDA(h, cudaMemcpyAsync(out.val, val, sizeof(double) * out.nnz, cudaMemcpyHostToDevice, h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));  // the host buffers are only borrowed
+  return GMG_OK;
+}
+
+static int upload_host_csr(gmg_context *h, const HostCsr &m, DevCsr &out) {
+  return upload_csr(h, m.n_rows, m.n_cols, m.rowptr.data(), m.col.data(), m.val.data(), out);
+}
+
+// CSR (device) -> sliced ELL (device)
+static int build_sell(gmg_context *h, const DevCsr &c, double drop_tol, Sell &out) {
+  free_sell(out);
+  const int n_slices = cdiv(c.n_rows, SLICE);
+  int *width = nullptr, *row_nnz = nullptr;
+  GMG_CUDA(h, dalloc(&width, n_slices));
+  GMG_CUDA(h, dalloc(&row_nnz, c.n_rows));
+  if (n_slices > 0) {
+    csr_slice_widths<<<cdiv((int64_t)n_slices * 32, 256), 256, 0, h->stream>>>(c.n_rows, n_slices, c.rowptr, c.val,
+                                                                               drop_tol, width, row_nnz);
+    GMG_LAUNCH_CHECK(h);
+  }
+  std::vector<int> hw(n_slices), hn(c.n_rows);
+  GMG_CUDA(h, cudaMemcpyAsync(hw.data(), width, sizeof(int) * n_slices, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, cudaMemcpyAsync(hn.data(), row_nnz, sizeof(int) * c.n_rows, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  std::vector<int64_t> sp(n_slices + 1, 0);
+  int maxw = 0;
+  for (int s = 0; s < n_slices; ++s) {
+    sp[s + 1] = sp[s] + (int64_t)hw[s] * SLICE;
+    maxw = std::max(maxw, hw[s]);
+  }
+  out.stored_nnz = 0;
+  for (int r = 0; r < c.n_rows; ++r) out.stored_nnz += hn[r];
+  out.padded = sp[n_slices];
+  GMG_CUDA(h, dalloc(&out.slice_ptr, n_slices + 1));
+  GMG_CUDA(h, dalloc(&out.val, out.padded));
+  GMG_CUDA(h, dalloc(&out.col, out.padded));
+  GMG_CUDA(h, cudaMemcpyAsync(out.slice_ptr, sp.data(), sizeof(int64_t) * (n_slices + 1), cudaMemcpyHostToDevice,
+                              h->stream));
+  if (n_slices > 0) {
+    csr_to_sell<<<cdiv((int64_t)n_slices * 32, 256), 256, 0, h->stream>>>(c.n_rows, c.n_cols, c.rowptr, c.col, c.val,
+                                                                          drop_tol, out.slice_ptr, out.val, out.col);
+    GMG_LAUNCH_CHECK(h);
+  }
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  dfree(width);
+  dfree(row_nnz);
+  out.v = SellView{c.n_rows, c.n_cols, n_slices, out.slice_ptr, out.val, out.col};
+  out.valid = true;
+  return GMG_OK;
+}
+
+static int build_sell_host(gmg_context *h, const HostCsr &m, double drop_tol, Sell &out) {
+  DevCsr tmp;
+  int rc = upload_host_csr(h, m, tmp);
+  if (rc) return rc;
+  rc = build_sell(h, tmp, drop_tol, out);
+  free_csr(tmp);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------ host CSR algebra
+static HostCsr make_host(int n_rows, int n_cols, const int64_t *rowptr, const int32_t *col, const double *val) {
+  HostCsr m;
+  m.n_rows = n_rows;
+  m.n_cols = n_cols;
+  m.rowptr.assign(rowptr, rowptr + n_rows + 1);
+  m.col.assign(col, col + rowptr[n_rows]);
+  m.val.assign(val, val + rowptr[n_rows]);
+  return m;
+}
+
+static HostCsr transpose(const HostCsr &a) {
+  HostCsr t;
+  t.n_rows = a.n_cols;
+  t.n_cols = a.n_rows;
+  t.rowptr.assign(t.n_rows + 1, 0);
+  for (int64_t k = 0; k < a.nnz(); ++k) t.rowptr[a.col[k] + 1]++;
+  for (int r = 0; r < t.n_rows; ++r) t.rowptr[r + 1] += t.rowptr[r];
+  t.col.resize(a.nnz());
+  t.val.resize(a.nnz());
+  std::vector<int64_t> cur(t.rowptr.begin(), t.rowptr.end() - 1);
+  for (int r = 0; r < a.n_rows; ++r)
+    for (int64_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k) {
+      const int64_t at = cur[a.col[k]]++;
+      t.col[at] = r;
+      t.val[at] = a.val[k];
+    }
+  return t;
+}
+
+// C = A + B (same shape); rows merged, columns sorted
+static HostCsr add(const HostCsr &a, const HostCsr &b) {
+  HostCsr c;
+  c.n_rows = a.n_rows;
+  c.n_cols = a.n_cols;
+  c.rowptr.assign(a.n_rows + 1, 0);
+  std::vector<std::pair<int, double>> row;
+  for (int r = 0; r < a.n_rows; ++r) {
+    row.clear();
+    for (int64_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k) row.emplace_back(a.col[k], a.val[k]);
+    if (!b.empty())
+      for (int64_t k = b.rowptr[r]; k < b.rowptr[r + 1]; ++k) row.emplace_back(b.col[k], b.val[k]);
+    std::stable_sort(row.begin(), row.end(), [](auto &x, auto &y) { return x.first < y.first; });
+    for (size_t i = 0; i < row.size();) {
+      double v = 0.0;
+      size_t j = i;
+      for (; j < row.size() && row[j].first == row[i].first; ++j) v += row[j].second;
+      c.col.push_back(row[i].first);
+      c.val.push_back(v);
+      i = j;
+    }
+    c.rowptr[r + 1] = (int64_t)c.col.size();
+  }
+  return c;
+}
+
+static HostCsr select_rows(const HostCsr &a, const std::vector<int> &rows) {
+  HostCsr s;
+  s.n_rows = (int)rows.size();
+  s.n_cols = a.n_cols;
+  s.rowptr.assign(rows.size() + 1, 0);
+  for (size_t i = 0; i < rows.size(); ++i) {
+    const int r = rows[i];
+    for (int64_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k) {
+      s.col.push_back(a.col[k]);
+      s.val.push_back(a.val[k]);
+    }
+    s.rowptr[i + 1] = (int64_t)s.col.size();
+  }
+  return s;
+}
+
+// greedy distance-1 colouring in row order over the significant (non-zero) couplings
+static std::vector<int> greedy_coloring(const HostCsr &a, int &n_colors) {
+  std::vector<int> color(a.n_rows, -1);
+  std::vector<int> mark;
+  n_colors = 0;
+  // need symmetric adjacency; the level matrices are structurally symmetric
+  for (int r = 0; r < a.n_rows; ++r) {
+    mark.assign(n_colors + 1, 0);
+    for (int64_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k) {
+      const int c = a.col[k];
+      if (c != r && a.val[k] != 0.0 && color[c] >= 0) mark[color[c]] = 1;
+    }
+    int pick = 0;
+    while (pick < n_colors && mark[pick]) ++pick;
+    color[r] = pick;
+    if (pick == n_colors) ++n_colors;
+  }
+  return color;
+}
+
+// wavefront ("level") schedule of the forward / backward Gauss-Seidel sweeps in natural row order
+static std::vector<std::vector<int>> wavefronts(const HostCsr &a, bool forward) {
+  std::vector<int> lev(a.n_rows, 0);
+  int maxl = 0;
+  if (forward) {
+    for (int r = 0; r < a.n_rows; ++r) {
+      int l = 0;
+      for (int64_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k)
+        if (a.col[k] < r && a.val[k] != 0.0) l = std::max(l, lev[a.col[k]] + 1);
+      lev[r] = l;
+      maxl = std::max(maxl, l);
+    }
+  } else {
+    for (int r = a.n_rows - 1; r >= 0; --r) {
+      int l = 0;
+      for (int64_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k)
+        if (a.col[k] > r && a.val[k] != 0.0) l = std::max(l, lev[a.col[k]] + 1);
+      lev[r] = l;
+      maxl = std::max(maxl, l);
+    }
+  }
+  std::vector<std::vector<int>> out(a.n_rows ? maxl + 1 : 0);
+  for (int r = 0; r < a.n_rows; ++r) out[lev[r]].push_back(r);
+  return out;
+}
+
+static int build_colorset(gmg_context *h, const HostCsr &a, const std::vector<int> &rows, ColorSet &cs) {
+  cs.n = (int)rows.size();
+  HostCsr sub = select_rows(a, rows);
+  int rc = build_sell_host(h, sub, -1.0, cs.A);
+  if (rc) return rc;
+  GMG_CUDA(h, dalloc(&cs.rows, cs.n));
+  GMG_CUDA(h, cudaMemcpy(cs.rows, rows.data(), sizeof(int) * cs.n, cudaMemcpyHostToDevice));
+  return GMG_OK;
+}
+
+static void free_level(Level &L) {
+  free_csr(L.rawA);
+  free_sell(L.A);
+  free_sell(L.AI);
+  free_sell(L.IT);
+  free_sell(L.P);
+  free_sell(L.R);
+  dfree(L.dinv);
+  dfree(L.defect);
+  dfree(L.sol);
+  dfree(L.t);
+  dfree(L.tmp);
+  dfree(L.copy_g);
+  dfree(L.copy_l);
+  for (auto *set : {&L.colors, &L.wave_fwd, &L.wave_bwd}) {
+    for (auto &c : *set) {
+      free_sell(c.A);
+      dfree(c.rows);
+    }
+    set->clear();
+  }
+}
+
+// ------------------------------------------------------------------------------ kernel wrappers
+template <int EPI, int DOT>
+static int spmv(gmg_context *h, const Sell &A, const double *x, double *y, const double *b = nullptr,
+                const double *dinv = nullptr, double omega = 0.0, double *out = nullptr) {
+  if (A.v.n_slices == 0) return GMG_OK;
+  const int grid = cdiv((int64_t)A.v.n_slices * 32, 256);
+  if (DOT != DOT_NONE && grid > h->partials_cap) return fail(h, GMG_EINVAL, "partials buffer too small");
+  sell_spmv<EPI, DOT><<<grid, 256, 0, h->stream>>>(A.v, x, y, b, dinv, omega, h->partials, h->counter, out);
+  GMG_LAUNCH_CHECK(h);
+  return GMG_OK;
+}
+
+static int reduce_grid(gmg_context *h, int n) { return std::min(std::max(cdiv(n, 256 * 4), 1), h->sm_count * 4); }
+
+static int coarse_cg(gmg_context *h, const Sell &A, const double *b, double *x, int max_it, double tol) {
+  if (A.v.n_rows > h->cg_n) return fail(h, GMG_EINVAL, "coarse CG work vectors too small");
+  const int slot = h->cg_cursor % h->cg_ring;
+  h->cg_cursor++;
+  CgResult *res = h->cg_results + slot;
+  SellView v = A.v;
+  void *args[] = {&v, (void *)&b, &x, &h->cg_g, &h->cg_d, &h->cg_h, &h->cg_partials, &max_it, &tol, &res};
+  int ev = -1;
+  if (h->ev_used < (int)h->ev_begin.size()) {
+    ev = h->ev_used++;
+    cudaEventRecord(h->ev_begin[ev], h->stream);
+  }
+  GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent<512>, dim3(h->cg_grid), dim3(512), args, 0, h->stream));
+  h->launches++;
+  if (ev >= 0) {
+    cudaEventRecord(h->ev_end[ev], h->stream);
+    h->ev_result_slot[ev] = slot;
+  }
+  return GMG_OK;
+}
+
+static int collect_profile(gmg_context *h) {
+  if (h->ev_used == 0) return GMG_OK;
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < h->ev_used; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_begin[i], h->ev_end[i]);
+    CgResult r;
+    cudaMemcpy(&r, h->cg_results + h->ev_result_slot[i], sizeof(CgResult), cudaMemcpyDeviceToHost);
+    h->prof_ms += ms;
+    h->prof_launches++;
+    h->prof_iters += r.iterations;
+  }
+  h->ev_used = 0;
+  return GMG_OK;
+}
+
+// u <- smooth(u, rhs)
+static int smooth(gmg_context *h, Level &L, double *&u, const double *rhs, bool zero_start) {
+  const int n = L.n;
+  if (n == 0) return GMG_OK;
+  if (h->smoother == GMG_SMOOTHER_JACOBI) {
+    for (int s = 0; s < h->steps; ++s) {
+      if (zero_start && s == 0) {
+        vec_scale_dinv<<<cdiv(n, 256), 256, 0, h->stream>>>(n, h->omega, L.dinv, rhs, u);
+        GMG_LAUNCH_CHECK(h);
+      } else {
+        int rc = spmv<EPI_JACOBI, DOT_NONE>(h, L.A, u, L.tmp, rhs, L.dinv, h->omega);
+        if (rc) return rc;
+        std::swap(u, L.tmp);
+      }
+    }
+    return GMG_OK;
+  }
+  if (h->smoother == GMG_SMOOTHER_MC_SSOR || h->smoother == GMG_SMOOTHER_LEX_SSOR) {
+    // a relaxation sweep applied to (u, rhs) equals u + sweep(0, rhs - A u): no residual needed
+    if (zero_start) GMG_CUDA(h, cudaMemsetAsync(u, 0, sizeof(double) * n, h->stream));
+    const bool lex = h->smoother == GMG_SMOOTHER_LEX_SSOR;
+    auto &fwd = lex ? L.wave_fwd : L.colors;
+    auto &bwd = lex ? L.wave_bwd : L.colors;
+    auto relax = [&](ColorSet &c) -> int {
+      if (c.n == 0) return GMG_OK;
+      sell_color_relax<<<cdiv((int64_t)c.A.v.n_slices * 32, 256), 256, 0, h->stream>>>(c.A.v, c.rows, u, rhs, L.dinv,
+                                                                                        h->omega);
+      GMG_LAUNCH_CHECK(h);
+      return GMG_OK;
+    };
+    for (int s = 0; s < h->steps; ++s) {
+      for (size_t c = 0; c < fwd.size(); ++c)
+        if (int rc = relax(fwd[c])) return rc;
+      if (lex) {
+        for (size_t c = 0; c < bwd.size(); ++c)
+          if (int rc = relax(bwd[c])) return rc;
+      } else {
+        for (size_t c = bwd.size(); c-- > 0;)
+          if (int rc = relax(bwd[c])) return rc;
+      }
+    }
+    return GMG_OK;
+  }
+  if (h->smoother == GMG_SMOOTHER_CHEBYSHEV) {
+    // Chebyshev polynomial of degree `steps` in D^-1 A on [lambda_max/ratio, 1.1*lambda_max]
+    const double lmax = 1.1 * L.lambda_max, lmin = lmax / 10.0;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
+    const double sigma = theta / delta;
+    double rho_old = 1.0 / sigma;
+    // first step: u += (1/theta) D^-1 (rhs - A u)
+    if (zero_start) {
+      vec_scale_dinv<<<cdiv(n, 256), 256, 0, h->stream>>>(n, 1.0 / theta, L.dinv, rhs, u);
+      GMG_LAUNCH_CHECK(h);
+      GMG_CUDA(h, cudaMemcpyAsync(L.t, u, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));  // increment
+    } else {
+      int rc = spmv<EPI_RESID, DOT_NONE>(h, L.A, u, L.tmp, rhs);
+      if (rc) return rc;
+      vec_scale_dinv<<<cdiv(n, 256), 256, 0, h->stream>>>(n, 1.0 / theta, L.dinv, L.tmp, L.t);
+      GMG_LAUNCH_CHECK(h);
+      vec_axpby<<<cdiv(n, 256), 256, 0, h->stream>>>(n, 1.0, L.t, 1.0, u);
+      GMG_LAUNCH_CHECK(h);
+    }
+    for (int s = 1; s < h->steps; ++s) {
+      const double rho = 1.0 / (2.0 * sigma - rho_old);
+      // increment = rho*rho_old * increment + (2 rho / delta) D^-1 (rhs - A u) ; u += increment
+      int rc = spmv<EPI_RESID, DOT_NONE>(h, L.A, u, L.tmp, rhs);
+      if (rc) return rc;
+      cheb_update<<<cdiv(n, 256), 256, 0, h->stream>>>(n, rho * rho_old, 2.0 * rho / delta, L.dinv, L.tmp, L.t, u);
+      GMG_LAUNCH_CHECK(h);
+      rho_old = rho;
+    }
+    return GMG_OK;
+  }
+  return fail(h, GMG_EINVAL, "unknown smoother");
+}
+
+// PreconditionMG::vmult on device vectors
+static int vcycle(gmg_context *h, const double *src, double *dst) {
+  const int nl = h->n_levels;
+  for (int l = 0; l < nl; ++l) {
+    Level &L = h->levels[l];
+    GMG_CUDA(h, cudaMemsetAsync(L.defect, 0, sizeof(double) * std::max(L.n, 1), h->stream));
+    if (L.n_copy) {
+      vec_gather<<<cdiv(L.n_copy, 256), 256, 0, h->stream>>>(L.n_copy, L.copy_l, L.copy_g, src, L.defect);
+      GMG_LAUNCH_CHECK(h);
+    }
+  }
+  // down
+  for (int l = nl - 1; l >= 1; --l) {
+    Level &L = h->levels[l];
+    Level &C = h->levels[l - 1];
+    if (int rc = smooth(h, L, L.sol, L.defect, true)) return rc;
+    // t = defect - (A + I) sol
+    if (int rc = spmv<EPI_RESID, DOT_NONE>(h, L.AI, L.sol, L.t, L.defect)) return rc;
+    // defect[l-1] += P^T t
+    if (int rc = spmv<EPI_ADD, DOT_NONE>(h, C.R, L.t, C.defect)) return rc;
+  }
+  // coarse
+  {
+    Level &L0 = h->levels[0];
+    if (int rc = coarse_cg(h, L0.A, L0.defect, L0.sol, h->coarse_max_it, h->coarse_tol)) return rc;
+  }
+  // up
+  for (int l = 1; l < nl; ++l) {
+    Level &L = h->levels[l];
+    Level &C = h->levels[l - 1];
+    if (int rc = spmv<EPI_ADD, DOT_NONE>(h, C.P, C.sol, L.sol)) return rc;
+    if (L.IT.valid && L.IT.stored_nnz > 0)
+      if (int rc = spmv<EPI_SUB, DOT_NONE>(h, L.IT, L.sol, L.defect)) return rc;
+    if (int rc = smooth(h, L, L.sol, L.defect, false)) return rc;
+  }
+  GMG_CUDA(h, cudaMemsetAsync(dst, 0, sizeof(double) * h->n_sys, h->stream));
+  for (int l = 0; l < nl; ++l) {
+    Level &L = h->levels[l];
+    if (L.n_copy) {
+      vec_gather<<<cdiv(L.n_copy, 256), 256, 0, h->stream>>>(L.n_copy, L.copy_g, L.copy_l, L.sol, dst);
+      GMG_LAUNCH_CHECK(h);
+    }
+  }
+  return GMG_OK;
+}
+
+enum { PRECOND_GMG = 0, PRECOND_JACOBI = 1 };
+
+static int pcg(gmg_context *h, int precond, double jac_omega, const double *b, double *x, int max_it, double tol,
+               int *iters, double *res0_out, double *res_out) {
+  const int n = h->n_sys;
+  h->cg_solve_begin = h->cg_cursor;
+  PcgScalars hs;
+  auto apply_precond = [&](const double *src, double *dst) -> int {
+    if (precond == PRECOND_GMG) return vcycle(h, src, dst);
+    vec_scale_dinv<<<cdiv(n, 256), 256, 0, h->stream>>>(n, jac_omega, h->s_dinv, src, dst);
+    GMG_LAUNCH_CHECK(h);
+    return GMG_OK;
+  };
+  auto check_coarse = [&]() -> int {
+    if (precond != PRECOND_GMG || h->cg_cursor == 0) return GMG_OK;
+    CgResult r;
+    GMG_CUDA(h, cudaMemcpy(&r, h->cg_results + ((h->cg_cursor - 1) % h->cg_ring), sizeof(r), cudaMemcpyDeviceToHost));
+    if (r.status != 0)
+      return fail(h, GMG_ENOCONVERGENCE, "coarse-grid CG: Iterative method reported convergence failure in step " +
+                                             std::to_string(r.iterations) + ". The residual in the last step was " +
+                                             std::to_string(r.res));
+    return GMG_OK;
+  };
+  const int rg = reduce_grid(h, n);
+  // g = A x - b ; res = ||g||
+  if (int rc = spmv<EPI_NRESID, DOT_YY>(h, h->S, x, h->g, b, nullptr, 0.0, &h->scalars->res2)) return rc;
+  GMG_CUDA(h, cudaMemcpyAsync(&hs, h->scalars, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  double res = std::sqrt(hs.res2);
+  *res0_out = res;
+  *res_out = res;
+  *iters = 0;
+  if (res <= tol) return GMG_OK;
+  int slot = 0;
+  if (int rc = apply_precond(h->g, h->hh)) return rc;
+  pcg_init_direction<<<rg, 256, 0, h->stream>>>(n, h->g, h->hh, h->d, h->scalars, slot, h->partials, h->counter);
+  GMG_LAUNCH_CHECK(h);
+  int it = 0;
+  while (true) {
+    ++it;
+    if (int rc = spmv<EPI_ASSIGN, DOT_XY>(h, h->S, h->d, h->hh, nullptr, nullptr, 0.0, &h->scalars->dh)) return rc;
+    pcg_update<<<rg, 256, 0, h->stream>>>(n, x, h->g, h->d, h->hh, h->scalars, slot, h->partials, h->counter);
+    GMG_LAUNCH_CHECK(h);
+    GMG_CUDA(h, cudaMemcpyAsync(&hs, h->scalars, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
+    GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (int rc = check_coarse()) return rc;
+    res = std::sqrt(hs.res2);
+    *res_out = res;
+    *iters = it;
+    if (res <= tol) break;
+    if (it >= max_it || std::isnan(res))
+      return fail(h, GMG_ENOCONVERGENCE, "Iterative method reported convergence failure in step " + std::to_string(it) +
+                                             ". The residual in the last step was " + std::to_string(res));
+    if (int rc = apply_precond(h->g, h->hh)) return rc;
+    vec_dot<<<rg, 256, 0, h->stream>>>(n, h->g, h->hh, &h->scalars->gh[slot ^ 1], h->partials, h->counter);
+    GMG_LAUNCH_CHECK(h);
+    slot ^= 1;
+    pcg_new_direction<<<cdiv(n, 256), 256, 0, h->stream>>>(n, h->d, h->hh, h->scalars, slot);
+    GMG_LAUNCH_CHECK(h);
+  }
+  return GMG_OK;
+}
+
+static int fetch_coarse_its(gmg_context *h) {
+  h->last_coarse_its.clear();
+  const int n = std::min(h->cg_cursor - h->cg_solve_begin, h->cg_ring);
+  for (int i = h->cg_cursor - n; i < h->cg_cursor; ++i) {
+    CgResult r;
+    GMG_CUDA(h, cudaMemcpy(&r, h->cg_results + (i % h->cg_ring), sizeof(r), cudaMemcpyDeviceToHost));
+    h->last_coarse_its.push_back(r.iterations);
+  }
+  return GMG_OK;
+}
+
+static Sell *pick(gmg_context *h, int which, int level) {
+  if (which == GMG_SYSTEM) return h->S.valid ? &h->S : nullptr;
+  if (level < 0 || level >= h->n_levels) return nullptr;
+  Level &L = h->levels[level];
+  if (which == GMG_LEVEL) return L.A.valid ? &L.A : nullptr;
+  if (which == GMG_PROLONG) return L.P.valid ? &L.P : nullptr;
+  return nullptr;
+}
+
+}  // namespace gmg
+
+// =================================================================================== C ABI
+extern "C" {
+
+int gmg_compiled_arch(void) { return 100; }
+
+int gmg_create(int device, gmg_handle *out) {
+  if (!out) return GMG_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) return GMG_ENODEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return GMG_ENODEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GMG_ENODEVICE;
+  if (prop.major < 10) return GMG_ENODEVICE;  // sm_100a code only
+  gmg_context *h = new gmg_context();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return GMG_ENODEVICE;
+  }
+  h->own_stream = true;
+  h->partials_cap = 1 << 16;
+  bool ok = dalloc(&h->partials, 3 * h->partials_cap) == cudaSuccess && dalloc(&h->counter, 4) == cudaSuccess &&
+            dalloc(&h->scalars, 1) == cudaSuccess && dalloc(&h->cg_results, h->cg_ring) == cudaSuccess;
+  if (ok) {
+    cudaMemset(h->counter, 0, 4 * sizeof(unsigned int));
+    cudaMemset(h->scalars, 0, sizeof(PcgScalars));
+    cudaMemset(h->cg_results, 0, sizeof(CgResult) * h->cg_ring);
+    int per_sm = 0;
+    ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent<512>, 512, 0) == cudaSuccess && per_sm > 0;
+    h->cg_grid = h->sm_count * std::max(per_sm, 1);
+    ok = ok && dalloc(&h->cg_partials, 3 * h->cg_grid) == cudaSuccess;
+    h->ev_begin.resize(512);
+    h->ev_end.resize(512);
+    h->ev_result_slot.resize(512);
+    for (size_t i = 0; i < h->ev_begin.size(); ++i) {
+      cudaEventCreate(&h->ev_begin[i]);
+      cudaEventCreate(&h->ev_end[i]);
+    }
+  }
+  if (!ok) {
+    gmg_destroy(h);
+    return GMG_ENODEVICE;
+  }
+  *out = h;
+  return GMG_OK;
+}
+
+int gmg_destroy(gmg_handle h) {
+  if (!h) return GMG_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto &L : h->levels) free_level(L);
+  free_csr(h->rawS);
+  free_sell(h->S);
+  dfree(h->s_dinv);
+  dfree(h->g);
+  dfree(h->d);
+  dfree(h->hh);
+  dfree(h->cg_g);
+  dfree(h->cg_d);
+  dfree(h->cg_h);
+  dfree(h->stage_a);
+  dfree(h->stage_b);
+  dfree(h->partials);
+  dfree(h->counter);
+  dfree(h->scalars);
+  dfree(h->cg_partials);
+  dfree(h->cg_results);
+  dfree(h->atom_pos);
+  dfree(h->atom_q);
+  dfree(h->list_ptr);
+  dfree(h->list_atoms);
+  rhs_free(h);
+  for (auto e : h->ev_begin) cudaEventDestroy(e);
+  for (auto e : h->ev_end) cudaEventDestroy(e);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return GMG_OK;
+}
+
+const char *gmg_last_error(gmg_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int gmg_set_stream(gmg_handle h, void *s) {
+  if (!h) return GMG_EINVAL;
+  cudaStreamSynchronize(h->stream);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  h->own_stream = false;
+  h->stream = (cudaStream_t)s;
+  return GMG_OK;
+}
+
+int gmg_synchronize(gmg_handle h) {
+  if (!h) return GMG_EINVAL;
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return GMG_OK;
+}
+
+int64_t gmg_launch_count(gmg_handle h) { return h ? h->launches : 0; }
+
+int gmg_set_num_levels(gmg_handle h, int n_levels) {
+  if (!h || n_levels < 1) return GMG_EINVAL;
+  for (auto &L : h->levels) free_level(L);
+  h->levels.assign(n_levels, Level{});
+  h->n_levels = n_levels;
+  h->is_setup = false;
+  return GMG_OK;
+}
+
+int gmg_set_matrix(gmg_handle h, int which, int level, int32_t n_rows, int32_t n_cols, const int64_t *rowptr,
+                   const int32_t *col, const double *val) {
+  if (!h || !rowptr || n_rows < 0 || n_cols < 0) return GMG_EINVAL;
+  if (rowptr[n_rows] > 0 && (!col || !val)) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  h->is_setup = false;
+  if (which == GMG_SYSTEM) {
+    h->n_sys = n_rows;
+    return upload_csr(h, n_rows, n_cols, rowptr, col, val, h->rawS);
+  }
+  if (level < 0 || level >= h->n_levels) return fail(h, GMG_EINVAL, "level out of range (call gmg_set_num_levels)");
+  Level &L = h->levels[level];
+  if (which == GMG_LEVEL) {
+    L.n = n_rows;
+    if (level >= 1) L.hA = make_host(n_rows, n_cols, rowptr, col, val);
+    return upload_csr(h, n_rows, n_cols, rowptr, col, val, L.rawA);
+  }
+  if (which == GMG_EDGE) {
+    L.hI = make_host(n_rows, n_cols, rowptr, col, val);
+    return GMG_OK;
+  }
+  if (which == GMG_PROLONG) {
+    L.hP = make_host(n_rows, n_cols, rowptr, col, val);
+    return GMG_OK;
+  }
+  return fail(h, GMG_EINVAL, "unknown matrix kind");
+}
+
+int gmg_set_copy_indices(gmg_handle h, int level, int32_t n, const int32_t *gi, const int32_t *li) {
+  if (!h || level < 0 || level >= h->n_levels || n < 0) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  Level &L = h->levels[level];
+  dfree(L.copy_g);
+  dfree(L.copy_l);
+  L.n_copy = n;
+  GMG_CUDA(h, dalloc(&L.copy_g, n));
+  GMG_CUDA(h, dalloc(&L.copy_l, n));
+  GMG_CUDA(h, cudaMemcpy(L.copy_g, gi, sizeof(int) * n, cudaMemcpyHostToDevice));
+  GMG_CUDA(h, cudaMemcpy(L.copy_l, li, sizeof(int) * n, cudaMemcpyHostToDevice));
+  return GMG_OK;
+}
+
+int gmg_set_smoother(gmg_handle h, int kind, double omega, int steps) {
+  if (!h || kind < 0 || kind > GMG_SMOOTHER_LEX_SSOR || steps < 1) return GMG_EINVAL;
+  h->smoother = kind;
+  h->omega = omega;
+  h->steps = steps;
+  h->is_setup = false;
+  return GMG_OK;
+}
+
+int gmg_set_coarse(gmg_handle h, int max_it, double abs_tol) {
+  if (!h || max_it < 1) return GMG_EINVAL;
+  h->coarse_max_it = max_it;
+  h->coarse_tol = abs_tol;
+  return GMG_OK;
+}
+
+int gmg_set_drop_tolerance(gmg_handle h, double drop_tol) {
+  if (!h) return GMG_EINVAL;
+  h->drop_tol = drop_tol;
+  h->is_setup = false;
+  return GMG_OK;
+}
+
+int gmg_setup(gmg_handle h) {
+  if (!h) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  int rc;
+  if (h->rawS.rowptr) {
+    if ((rc = build_sell(h, h->rawS, h->drop_tol, h->S))) return rc;
+    free_csr(h->rawS);
+    dfree(h->s_dinv);
+    dfree(h->g);
+    dfree(h->d);
+    dfree(h->hh);
+    GMG_CUDA(h, dalloc(&h->s_dinv, h->n_sys));
+    GMG_CUDA(h, dalloc(&h->g, h->n_sys));
+    GMG_CUDA(h, dalloc(&h->d, h->n_sys));
+    GMG_CUDA(h, dalloc(&h->hh, h->n_sys));
+    if (h->n_sys) {
+      sell_extract_diag_inv<<<cdiv(h->n_sys, 256), 256, 0, h->stream>>>(h->S.v, h->s_dinv);
+      GMG_LAUNCH_CHECK(h);
+    }
+  }
+  int cg_n = 0;
+  for (int l = 0; l < h->n_levels; ++l) {
+    Level &L = h->levels[l];
+    if (L.rawA.rowptr) {
+      if ((rc = build_sell(h, L.rawA, h->drop_tol, L.A))) return rc;
+      free_csr(L.rawA);
+      dfree(L.dinv);
+      GMG_CUDA(h, dalloc(&L.dinv, L.n));
+      if (L.n) {
+        sell_extract_diag_inv<<<cdiv(L.n, 256), 256, 0, h->stream>>>(L.A.v, L.dinv);
+        GMG_LAUNCH_CHECK(h);
+      }
+    }
+    if (!L.A.valid) return fail(h, GMG_EINVAL, "level matrix missing on level " + std::to_string(l));
+    for (double **p : {&L.defect, &L.sol, &L.t, &L.tmp}) {
+      dfree(*p);
+      GMG_CUDA(h, dalloc(p, L.n));
+      GMG_CUDA(h, cudaMemset(*p, 0, sizeof(double) * std::max(L.n, 1)));
+    }
+    if (l == 0) cg_n = L.n;
+    if (l >= 1) {
+      if (L.hA.empty()) return fail(h, GMG_EINVAL, "host copy of level matrix missing");
+      HostCsr ai = add(L.hA, L.hI);
+      if ((rc = build_sell_host(h, ai, h->drop_tol, L.AI))) return rc;
+      free_sell(L.IT);
+      if (!L.hI.empty() && L.hI.nnz() > 0) {
+        HostCsr it = transpose(L.hI);
+        if ((rc = build_sell_host(h, it, 0.0, L.IT))) return rc;
+      }
+      for (auto *set : {&L.colors, &L.wave_fwd, &L.wave_bwd}) {
+        for (auto &c : *set) {
+          free_sell(c.A);
+          dfree(c.rows);
+        }
+        set->clear();
+      }
+      if (h->smoother == GMG_SMOOTHER_MC_SSOR) {
+        int nc = 0;
+        std::vector<int> color = greedy_coloring(L.hA, nc);
+        std::vector<std::vector<int>> rows(nc);
+        for (int r = 0; r < L.n; ++r) rows[color[r]].push_back(r);
+        L.colors.resize(nc);
+        for (int c = 0; c < nc; ++c)
+          if ((rc = build_colorset(h, L.hA, rows[c], L.colors[c]))) return rc;
+      } else if (h->smoother == GMG_SMOOTHER_LEX_SSOR) {
+        auto f = wavefronts(L.hA, true), b = wavefronts(L.hA, false);
+        L.wave_fwd.resize(f.size());
+        L.wave_bwd.resize(b.size());
+        for (size_t c = 0; c < f.size(); ++c)
+          if ((rc = build_colorset(h, L.hA, f[c], L.wave_fwd[c]))) return rc;
+        for (size_t c = 0; c < b.size(); ++c)
+          if ((rc = build_colorset(h, L.hA, b[c], L.wave_bwd[c]))) return rc;
+      } else if (h->smoother == GMG_SMOOTHER_CHEBYSHEV) {
+        // power iteration for lambda_max(D^-1 A) on the host copy (small levels), 20 steps
+        const HostCsr &a = L.hA;
+        std::vector<double> v(L.n), w(L.n), dg(L.n, 1.0);
+        for (int r = 0; r < L.n; ++r)
+          for (int64_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k)
+            if (a.col[k] == r) dg[r] = a.val[k];
+        for (int r = 0; r < L.n; ++r) v[r] = 1.0 + 0.37 * std::sin(1.0 + 0.61 * r);
+        double lam = 1.0;
+        for (int itp = 0; itp < 20; ++itp) {
+          double nv = 0.0;
+          for (int r = 0; r < L.n; ++r) {
+            double s = 0.0;
+            for (int64_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k) s += a.val[k] * v[a.col[k]];
+            w[r] = s / dg[r];
+            nv += w[r] * w[r];
+          }
+          nv = std::sqrt(nv);
+          double vv = 0.0;
+          for (int r = 0; r < L.n; ++r) vv += v[r] * v[r];
+          lam = nv / std::sqrt(vv);
+          for (int r = 0; r < L.n; ++r) v[r] = w[r] / (nv > 0 ? nv : 1.0);
+        }
+        L.lambda_max = lam;
+      }
+    }
+    if (!L.hP.empty()) {
+      if ((rc = build_sell_host(h, L.hP, 0.0, L.P))) return rc;
+      HostCsr r = transpose(L.hP);
+      if ((rc = build_sell_host(h, r, 0.0, L.R))) return rc;
+    } else if (l + 1 < h->n_levels) {
+      return fail(h, GMG_EINVAL, "prolongation from level " + std::to_string(l) + " missing");
+    }
+  }
+  // the coarse CG may also be called on the system matrix (tests / single-level)
+  cg_n = std::max(cg_n, h->n_sys);
+  if (cg_n > h->cg_n) {
+    dfree(h->cg_g);
+    dfree(h->cg_d);
+    dfree(h->cg_h);
+    GMG_CUDA(h, dalloc(&h->cg_g, cg_n));
+    GMG_CUDA(h, dalloc(&h->cg_d, cg_n));
+    GMG_CUDA(h, dalloc(&h->cg_h, cg_n));
+    h->cg_n = cg_n;
+  }
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->is_setup = true;
+  return GMG_OK;
+}
+
+// ------------------------------------------------------------------------------------ solve path
+int gmg_pcg_solve_dev(gmg_handle h, const double *b, double *x, int max_it, double abs_tol, int *iters, double *res0,
+                      double *res_final) {
+  if (!h || !h->is_setup || !h->S.valid || h->n_levels < 1) return h ? fail(h, GMG_EINVAL, "not set up") : GMG_EINVAL;
+  cudaSetDevice(h->device);
+  int it = 0;
+  double r0 = 0, r1 = 0;
+  int rc = pcg(h, PRECOND_GMG, 0.0, b, x, max_it, abs_tol, &it, &r0, &r1);
+  if (iters) *iters = it;
+  if (res0) *res0 = r0;
+  if (res_final) *res_final = r1;
+  int rc2 = fetch_coarse_its(h);
+  return rc ? rc : rc2;
+}
+
+static int with_host_vectors(gmg_handle h, int64_t n_in, const double *in, int64_t n_out, double *inout,
+                             bool upload_inout) {
+  if (int rc = ensure_stage(h, std::max(n_in, n_out))) return rc;
+  if (in) GMG_CUDA(h, cudaMemcpyAsync(h->stage_a, in, sizeof(double) * n_in, cudaMemcpyHostToDevice, h->stream));
+  if (upload_inout)
+    GMG_CUDA(h, cudaMemcpyAsync(h->stage_b, inout, sizeof(double) * n_out, cudaMemcpyHostToDevice, h->stream));
+  return GMG_OK;
+}
+
+int gmg_pcg_solve(gmg_handle h, const double *b, double *x, int max_it, double abs_tol, int *iters, double *res0,
+                  double *res_final) {
+  if (!h || !b || !x) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  const int n = h->n_sys;
+  if (int rc = with_host_vectors(h, n, b, n, x, true)) return rc;
+  int rc = gmg_pcg_solve_dev(h, h->stage_a, h->stage_b, max_it, abs_tol, iters, res0, res_final);
+  GMG_CUDA(h, cudaMemcpyAsync(x, h->stage_b, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return rc;
+}
+
+int gmg_pcg_solve_jacobi(gmg_handle h, const double *b, double *x, double omega, int max_it, double abs_tol, int *iters,
+                         double *res0, double *res_final) {
+  if (!h || !b || !x || !h->S.valid) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  const int n = h->n_sys;
+  if (int rc = with_host_vectors(h, n, b, n, x, true)) return rc;
+  int it = 0;
+  double r0 = 0, r1 = 0;
+  int rc = pcg(h, PRECOND_JACOBI, omega, h->stage_a, h->stage_b, max_it, abs_tol, &it, &r0, &r1);
+  if (iters) *iters = it;
+  if (res0) *res0 = r0;
+  if (res_final) *res_final = r1;
+  GMG_CUDA(h, cudaMemcpyAsync(x, h->stage_b, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return rc;
+}
+
+int gmg_vcycle_apply_dev(gmg_handle h, const double *src, double *dst) {
+  if (!h || !h->is_setup) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  h->cg_solve_begin = h->cg_cursor;
+  return vcycle(h, src, dst);
+}
+
+int gmg_vcycle_apply(gmg_handle h, const double *src, double *dst) {
+  if (!h || !src || !dst) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  const int n = h->n_sys;
+  if (int rc = with_host_vectors(h, n, src, n, dst, false)) return rc;
+  int rc = gmg_vcycle_apply_dev(h, h->stage_a, h->stage_b);
+  if (rc) return rc;
+  GMG_CUDA(h, cudaMemcpyAsync(dst, h->stage_b, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return fetch_coarse_its(h);
+}
+
+int gmg_spmv_dev(gmg_handle h, int which, int level, const double *x, double *y) {
+  if (!h) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  Sell *A = pick(h, which, level);
+  if (!A) return fail(h, GMG_EINVAL, "matrix not available (set + gmg_setup first)");
+  return spmv<EPI_ASSIGN, DOT_NONE>(h, *A, x, y);
+}
+
+int gmg_spmv(gmg_handle h, int which, int level, const double *x, double *y) {
+  if (!h || !x || !y) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  Sell *A = pick(h, which, level);
+  if (!A) return fail(h, GMG_EINVAL, "matrix not available (set + gmg_setup first)");
+  if (int rc = with_host_vectors(h, A->v.n_cols, x, A->v.n_rows, y, false)) return rc;
+  if (int rc = spmv<EPI_ASSIGN, DOT_NONE>(h, *A, h->stage_a, h->stage_b)) return rc;
+  GMG_CUDA(h, cudaMemcpyAsync(y, h->stage_b, sizeof(double) * A->v.n_rows, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return GMG_OK;
+}
+
+int gmg_cg_solve_dev(gmg_handle h, int which, int level, const double *b, double *x, int max_it, double abs_tol,
+                     int *iters, double *res_final) {
+  if (!h) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  Sell *A = pick(h, which, level);
+  if (!A || A->v.n_rows != A->v.n_cols) return fail(h, GMG_EINVAL, "square matrix not available");
+  if (int rc = coarse_cg(h, *A, b, x, max_it, abs_tol)) return rc;
+  CgResult r;
+  GMG_CUDA(h, cudaMemcpyAsync(&r, h->cg_results + ((h->cg_cursor - 1) % h->cg_ring), sizeof(r), cudaMemcpyDeviceToHost,
+                              h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (iters) *iters = r.iterations;
+  if (res_final) *res_final = r.res;
+  if (r.status != 0) return fail(h, GMG_ENOCONVERGENCE, "CG: convergence failure in step " + std::to_string(r.iterations));
+  return GMG_OK;
+}
+
+int gmg_cg_solve(gmg_handle h, int which, int level, const double *b, double *x, int max_it, double abs_tol, int *iters,
+                 double *res_final) {
+  if (!h || !b || !x) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  Sell *A = pick(h, which, level);
+  if (!A) return fail(h, GMG_EINVAL, "matrix not available");
+  const int n = A->v.n_rows;
+  if (int rc = with_host_vectors(h, n, b, n, x, false)) return rc;
+  int rc = gmg_cg_solve_dev(h, which, level, h->stage_a, h->stage_b, max_it, abs_tol, iters, res_final);
+  GMG_CUDA(h, cudaMemcpyAsync(x, h->stage_b, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return rc;
+}
+
+int gmg_smooth(gmg_handle h, int level, const double *rhs, double *u, int zero_start) {
+  if (!h || !h->is_setup || level < 1 || level >= h->n_levels || !rhs || !u) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  Level &L = h->levels[level];
+  const int n = L.n;
+  GMG_CUDA(h, cudaMemcpyAsync(L.defect, rhs, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  GMG_CUDA(h, cudaMemcpyAsync(L.sol, u, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  if (int rc = smooth(h, L, L.sol, L.defect, zero_start != 0)) return rc;
+  GMG_CUDA(h, cudaMemcpyAsync(u, L.sol, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return GMG_OK;
+}
+
+int gmg_matrix_norms(gmg_handle h, int which, int level, double out[3]) {
+  if (!h || !out) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  Sell *A = pick(h, which, level);
+  if (!A) return fail(h, GMG_EINVAL, "matrix not available");
+  const int n = A->v.n_rows, nc = A->v.n_cols;
+  const int grid = cdiv(std::max(n, 1), 256);
+  if (grid > h->partials_cap) return fail(h, GMG_EINVAL, "matrix too large for the partials buffer");
+  if (int rc = ensure_stage(h, nc)) return rc;
+  GMG_CUDA(h, cudaMemsetAsync(h->stage_a, 0, sizeof(double) * nc, h->stream));
+  sell_norm_partials<<<grid, 256, 0, h->stream>>>(A->v, h->stage_a, h->partials, h->partials + h->partials_cap);
+  GMG_LAUNCH_CHECK(h);
+  const int g2 = std::min(cdiv(std::max(nc, 1), 256), h->partials_cap);
+  vec_max_partials<<<g2, 256, 0, h->stream>>>(nc, h->stage_a, h->partials + 2 * h->partials_cap);
+  GMG_LAUNCH_CHECK(h);
+  std::vector<double> rowmax(grid), frob(grid), colmax(g2);
+  GMG_CUDA(h, cudaMemcpyAsync(rowmax.data(), h->partials, sizeof(double) * grid, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, cudaMemcpyAsync(frob.data(), h->partials + h->partials_cap, sizeof(double) * grid, cudaMemcpyDeviceToHost,
+                              h->stream));
+  GMG_CUDA(h, cudaMemcpyAsync(colmax.data(), h->partials + 2 * h->partials_cap, sizeof(double) * g2,
+                              cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  out[0] = *std::max_element(colmax.begin(), colmax.end());
+  out[1] = *std::max_element(rowmax.begin(), rowmax.end());
+  double f = 0.0;
+  for (double v : frob) f += v;
+  out[2] = std::sqrt(f);
+  return GMG_OK;
+}
+
+int gmg_vector_norms(gmg_handle h, int64_t n, const double *v, double out[3]) {
+  if (!h || !v || !out || n < 0) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  if (int rc = ensure_stage(h, n)) return rc;
+  GMG_CUDA(h, cudaMemcpyAsync(h->stage_a, v, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  const int grid = std::min(cdiv(std::max<int64_t>(n, 1), 256 * 4), h->partials_cap);
+  vec_norm_partials<<<grid, 256, 0, h->stream>>>(n, h->stage_a, h->partials, h->partials + h->partials_cap,
+                                                 h->partials + 2 * h->partials_cap);
+  GMG_LAUNCH_CHECK(h);
+  std::vector<double> a(grid), b(grid), c(grid);
+  GMG_CUDA(h, cudaMemcpyAsync(a.data(), h->partials, sizeof(double) * grid, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, cudaMemcpyAsync(b.data(), h->partials + h->partials_cap, sizeof(double) * grid, cudaMemcpyDeviceToHost,
+                              h->stream));
+  GMG_CUDA(h, cudaMemcpyAsync(c.data(), h->partials + 2 * h->partials_cap, sizeof(double) * grid, cudaMemcpyDeviceToHost,
+                              h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  double s1 = 0, s2 = 0, m = 0;
+  for (int i = 0; i < grid; ++i) {
+    s1 += a[i];
+    s2 += b[i];
+    m = std::max(m, c[i]);
+  }
+  out[0] = s1;
+  out[1] = std::sqrt(s2);
+  out[2] = m;
+  return GMG_OK;
+}
+
+int gmg_last_coarse_iterations(gmg_handle h, int32_t *out, int cap, int *n_out) {
+  if (!h || !n_out) return GMG_EINVAL;
+  const int n = (int)h->last_coarse_its.size();
+  *n_out = n;
+  for (int i = 0; i < std::min(n, cap); ++i) out[i] = h->last_coarse_its[i];
+  return GMG_OK;
+}
+
+int gmg_vec_alloc(gmg_handle h, int64_t n, double **dev_out) {
+  if (!h || !dev_out) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  GMG_CUDA(h, dalloc(dev_out, n));
+  GMG_CUDA(h, cudaMemset(*dev_out, 0, sizeof(double) * std::max<int64_t>(n, 1)));
+  return GMG_OK;
+}
+int gmg_vec_free(gmg_handle h, double *dev) {
+  if (!h) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  cudaFree(dev);
+  return GMG_OK;
+}
+int gmg_vec_upload(gmg_handle h, double *dev, const double *host, int64_t n) {
+  if (!h) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  GMG_CUDA(h, cudaMemcpyAsync(dev, host, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return GMG_OK;
+}
+int gmg_vec_download(gmg_handle h, double *host, const double *dev, int64_t n) {
+  if (!h) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  GMG_CUDA(h, cudaMemcpyAsync(host, dev, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return GMG_OK;
+}
+
+int gmg_matrix_traffic(gmg_handle h, int which, int level, double out[3]) {
+  if (!h || !out) return GMG_EINVAL;
+  Sell *A = pick(h, which, level);
+  if (!A) return fail(h, GMG_EINVAL, "matrix not available");
+  const double nnz = (double)A->stored_nnz, n = (double)A->v.n_rows;
+  out[0] = nnz;
+  out[1] = 12.0 * nnz + 4.0 * (n + 1.0) + 16.0 * n;  // CSR-equivalent algorithmic bytes
+  out[2] = out[1] + 72.0 * n;                         // + x,d,g,h reads and x,g,d writes of one CG iteration
+  return GMG_OK;
+}
+
+int gmg_coarse_profile(gmg_handle h, int reset, double *ms, int64_t *launches, int64_t *iters) {
+  if (!h) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  if (int rc = collect_profile(h)) return rc;
+  if (ms) *ms = h->prof_ms;
+  if (launches) *launches = h->prof_launches;
+  if (iters) *iters = h->prof_iters;
+  if (reset) {
+    h->prof_ms = 0.0;
+    h->prof_launches = 0;
+    h->prof_iters = 0;
+  }
+  return GMG_OK;
+}
+
+}  // extern "C"

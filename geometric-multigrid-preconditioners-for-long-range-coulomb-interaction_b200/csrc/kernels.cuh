@@ -1,0 +1,418 @@
+// sm_100a kernels of the MG-PCG path: sliced-ELL SpMV with fused epilogues, the persistent
+// cooperative coarse-grid CG, smoothers, fused PCG vector updates, transfers.
+//
+// Matrix layout (SELL-32-1, "pair-interleaved"): rows are cut into slices of 32 (one warp, one row
+// per lane); a slice of width w (even) stores its w/2 entry pairs so that lane L reads the 16-byte
+// pair p at  val2[slice_ptr/2 + p*32 + L]  -- every warp-wide load is one fully coalesced 512 B
+// (values) / 256 B (columns) transaction, 128-bit per lane.  Padding entries have value 0.
+#pragma once
+#include "common.cuh"
+
+namespace gmg {
+
+
+template <bool NC>
+__device__ __forceinline__ double ldx(const double *x, int c) {
+  if (NC) return __ldg(x + c);
+  return x[c];
+}
+
+// sum_j a_rj x_j for the row (slice, lane); j ascending = CSR order, one FMA chain.
+template <bool NC>
+__device__ __forceinline__ double sell_row_dot(const SellView &A, int slice, int lane, const double *__restrict__ x) {
+  const int64_t b = A.slice_ptr[slice];
+  const int npairs = (int)((A.slice_ptr[slice + 1] - b) >> 6);
+  const double2 *v2 = reinterpret_cast<const double2 *>(A.val) + (b >> 1) + lane;
+  const int2 *c2 = reinterpret_cast<const int2 *>(A.col) + (b >> 1) + lane;
+  double acc = 0.0;
+  int p = 0;
+  for (; p + 4 <= npairs; p += 4) {
+    double2 v[4];
+    int2 c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u] = ld_stream_d2(v2 + (p + u) * 32);
+      c[u] = ld_stream_i2(c2 + (p + u) * 32);
+    }
+    double xv[8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      xv[2 * u] = ldx<NC>(x, c[u].x);
+      xv[2 * u + 1] = ldx<NC>(x, c[u].y);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc = fma(v[u].x, xv[2 * u], acc);
+      acc = fma(v[u].y, xv[2 * u + 1], acc);
+    }
+  }
+  for (; p < npairs; ++p) {
+    const double2 v = ld_stream_d2(v2 + p * 32);
+    const int2 c = ld_stream_i2(c2 + p * 32);
+    acc = fma(v.x, ldx<NC>(x, c.x), acc);
+    acc = fma(v.y, ldx<NC>(x, c.y), acc);
+  }
+  return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSR -> SELL conversion (device side; the host hands over plain CSR)
+// ------------------------------------------------------------------------------------------------
+__global__ void csr_slice_widths(int n_rows, int n_slices, const int64_t *__restrict__ rowptr,
+                                 const double *__restrict__ val, double drop_tol, int *__restrict__ width,
+                                 int *__restrict__ row_nnz) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  int cnt = 0;
+  if (r < n_rows) {
+    if (drop_tol < 0.0) {
+      cnt = (int)(rowptr[r + 1] - rowptr[r]);
+    } else {
+      for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) cnt += (fabs(val[k]) > drop_tol) ? 1 : 0;
+    }
+    row_nnz[r] = cnt;
+  }
+  int m = cnt;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && (r >> 5) < n_slices) width[r >> 5] = (m + 1) & ~1;
+}
+
+__global__ void csr_to_sell(int n_rows, int n_cols, const int64_t *__restrict__ rowptr, const int *__restrict__ col,
+                            const double *__restrict__ val, double drop_tol, const int64_t *__restrict__ slice_ptr,
+                            double *__restrict__ sval, int *__restrict__ scol) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slice = r >> 5, lane = r & 31;
+  if (slice >= (n_rows + 31) / 32) return;
+  const int64_t b = slice_ptr[slice];
+  const int w = (int)((slice_ptr[slice + 1] - b) >> 5);
+  int j = 0;
+  const int pad_col = (r < n_cols) ? r : 0;
+  if (r < n_rows) {
+    for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+      const double v = val[k];
+      if (drop_tol >= 0.0 && !(fabs(v) > drop_tol)) continue;
+      const int64_t at = b + (int64_t)(j >> 1) * 64 + lane * 2 + (j & 1);
+      sval[at] = v;
+      scol[at] = col[k];
+      ++j;
+    }
+  }
+  for (; j < w; ++j) {
+    const int64_t at = b + (int64_t)(j >> 1) * 64 + lane * 2 + (j & 1);
+    sval[at] = 0.0;
+    scol[at] = pad_col;
+  }
+}
+
+__global__ void sell_extract_diag_inv(SellView A, double *__restrict__ dinv) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= A.n_rows) return;
+  const int slice = r >> 5, lane = r & 31;
+  const int64_t b = A.slice_ptr[slice];
+  const int w = (int)((A.slice_ptr[slice + 1] - b) >> 5);
+  double d = 0.0;
+  for (int j = 0; j < w; ++j) {
+    const int64_t at = b + (int64_t)(j >> 1) * 64 + lane * 2 + (j & 1);
+    if (A.col[at] == r) d += A.val[at];
+  }
+  dinv[r] = 1.0 / d;
+}
+
+// matrix norms: column abs-sums via atomics into colsum, per-block max row abs-sum and sum of squares
+__global__ void __launch_bounds__(256) sell_norm_partials(SellView A, double *colsum, double *rowmax_partial,
+                                                          double *frob_partial) {
+  __shared__ double red[32];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  double rs = 0.0, fs = 0.0;
+  if (r < A.n_rows) {
+    const int slice = r >> 5, lane = r & 31;
+    const int64_t b = A.slice_ptr[slice];
+    const int w = (int)((A.slice_ptr[slice + 1] - b) >> 5);
+    for (int j = 0; j < w; ++j) {
+      const int64_t at = b + (int64_t)(j >> 1) * 64 + lane * 2 + (j & 1);
+      const double a = fabs(A.val[at]);
+      rs += a;
+      fs += a * a;
+      if (a != 0.0) atomicAdd(colsum + A.col[at], a);
+    }
+  }
+  const double m = block_max(rs, red);
+  if (threadIdx.x == 0) rowmax_partial[blockIdx.x] = m;
+  const double f = block_sum(fs, red);
+  if (threadIdx.x == 0) frob_partial[blockIdx.x] = f;
+}
+
+__global__ void __launch_bounds__(256) vec_max_partials(int n, const double *__restrict__ v, double *pmax) {
+  __shared__ double red[32];
+  double m = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmax(m, fabs(v[i]));
+  const double sm = block_max(m, red);
+  if (threadIdx.x == 0) pmax[blockIdx.x] = sm;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SpMV with fused epilogues
+// ------------------------------------------------------------------------------------------------
+enum { EPI_ASSIGN = 0,   // y = A x
+       EPI_ADD = 1,      // y += A x
+       EPI_SUB = 2,      // y -= A x
+       EPI_RESID = 3,    // y = b - A x
+       EPI_NRESID = 4,   // y = A x - b            (SolverCG: g = A x - b)
+       EPI_JACOBI = 5 }; // y = x + omega * dinv * (b - A x)   (one damped Jacobi step, x != y)
+
+enum { DOT_NONE = 0, DOT_XY = 1 /* sum x_r y_r */, DOT_YY = 2 /* sum y_r^2 */ };
+
+template <int EPI, int DOT>
+__global__ void __launch_bounds__(256) sell_spmv(SellView A, const double *__restrict__ x, double *__restrict__ y,
+                                                 const double *__restrict__ b, const double *__restrict__ dinv,
+                                                 double omega, double *partials, unsigned int *counter, double *out) {
+  __shared__ double red[32];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slice = r >> 5, lane = r & 31;
+  double contrib = 0.0;
+  if (slice < A.n_slices) {
+    const double ax = sell_row_dot<true>(A, slice, lane, x);
+    if (r < A.n_rows) {
+      double yv;
+      if (EPI == EPI_ASSIGN) yv = ax;
+      else if (EPI == EPI_ADD) yv = y[r] + ax;
+      else if (EPI == EPI_SUB) yv = y[r] - ax;
+      else if (EPI == EPI_RESID) yv = b[r] - ax;
+      else if (EPI == EPI_NRESID) yv = ax - b[r];
+      else yv = x[r] + omega * dinv[r] * (b[r] - ax);
+      y[r] = yv;
+      if (DOT == DOT_XY) contrib = x[r] * yv;
+      if (DOT == DOT_YY) contrib = yv * yv;
+    }
+  }
+  if (DOT != DOT_NONE) {
+    const double s = block_sum(contrib, red);
+    grid_sum_finalize(s, partials, counter, out, red);
+  }
+}
+
+// rows of one colour, in place Gauss-Seidel update: u_i += omega (rhs_i - sum_j a_ij u_j) / a_ii
+// (A_c holds the rows of this colour; rows[k] is the global row of local row k; dinv global).
+__global__ void __launch_bounds__(256) sell_color_relax(SellView Ac, const int *__restrict__ rows, double *u,
+                                                        const double *__restrict__ rhs, const double *__restrict__ dinv,
+                                                        double omega) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slice = k >> 5, lane = k & 31;
+  if (slice >= Ac.n_slices) return;
+  const double ax = sell_row_dot<false>(Ac, slice, lane, u);
+  if (k < Ac.n_rows) {
+    const int i = rows[k];
+    u[i] += omega * (rhs[i] - ax) * dinv[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// vector kernels
+// ------------------------------------------------------------------------------------------------
+
+__global__ void vec_scale_dinv(int n, double omega, const double *__restrict__ dinv, const double *__restrict__ r,
+                               double *__restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = omega * dinv[i] * r[i];
+}
+
+// y = a x + b y
+__global__ void vec_axpby(int n, double a, const double *__restrict__ x, double b, double *__restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a * x[i] + b * y[i];
+}
+
+// Chebyshev: inc = c1 inc + c2 dinv r ; u += inc
+__global__ void cheb_update(int n, double c1, double c2, const double *__restrict__ dinv, const double *__restrict__ r,
+                            double *__restrict__ inc, double *__restrict__ u) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double v = c1 * inc[i] + c2 * dinv[i] * r[i];
+    inc[i] = v;
+    u[i] += v;
+  }
+}
+
+__global__ void vec_gather(int n, const int *__restrict__ dst_idx, const int *__restrict__ src_idx,
+                           const double *__restrict__ src, double *__restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[dst_idx[i]] = src[src_idx[i]];
+}
+
+// d = -h ; gh[slot] = g.h
+__global__ void __launch_bounds__(256) pcg_init_direction(int n, const double *__restrict__ g, const double *__restrict__ h,
+                                                          double *__restrict__ d, PcgScalars *s, int slot,
+                                                          double *partials, unsigned int *counter) {
+  __shared__ double red[32];
+  double c = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double hv = h[i];
+    d[i] = -hv;
+    c += g[i] * hv;
+  }
+  const double bs = block_sum(c, red);
+  grid_sum_finalize(bs, partials, counter, &s->gh[slot], red);
+}
+
+// alpha = gh[slot]/dh ; x += alpha d ; g += alpha h ; res2 = g.g      (Vector::add + add_and_dot)
+__global__ void __launch_bounds__(256) pcg_update(int n, double *__restrict__ x, double *__restrict__ g,
+                                                  const double *__restrict__ d, const double *__restrict__ h,
+                                                  PcgScalars *s, int slot, double *partials, unsigned int *counter) {
+  __shared__ double red[32];
+  const double alpha = s->gh[slot] / s->dh;
+  double c = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    x[i] += alpha * d[i];
+    const double gv = g[i] + alpha * h[i];
+    g[i] = gv;
+    c += gv * gv;
+  }
+  const double bs = block_sum(c, red);
+  grid_sum_finalize(bs, partials, counter, &s->res2, red);
+}
+
+// out = a.b
+__global__ void __launch_bounds__(256) vec_dot(int n, const double *__restrict__ a, const double *__restrict__ b,
+                                               double *out, double *partials, unsigned int *counter) {
+  __shared__ double red[32];
+  double c = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += a[i] * b[i];
+  const double bs = block_sum(c, red);
+  grid_sum_finalize(bs, partials, counter, out, red);
+}
+
+// beta = gh[slot_new] / gh[slot_old] ; d = beta d - h
+__global__ void pcg_new_direction(int n, double *__restrict__ d, const double *__restrict__ h, const PcgScalars *s,
+                                  int slot_new) {
+  const double beta = s->gh[slot_new] / s->gh[slot_new ^ 1];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = beta * d[i] - h[i];
+}
+
+// l1 / l2^2 / linf partials
+__global__ void __launch_bounds__(256) vec_norm_partials(int64_t n, const double *__restrict__ v, double *p1, double *p2,
+                                                         double *pinf) {
+  __shared__ double red[32];
+  double a = 0.0, b = 0.0, m = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double x = fabs(v[i]);
+    a += x;
+    b += x * x;
+    m = fmax(m, x);
+  }
+  const double sa = block_sum(a, red);
+  if (threadIdx.x == 0) p1[blockIdx.x] = sa;
+  const double sb = block_sum(b, red);
+  if (threadIdx.x == 0) p2[blockIdx.x] = sb;
+  const double sm = block_max(m, red);
+  if (threadIdx.x == 0) pinf[blockIdx.x] = sm;
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent cooperative CG (MGCoarseGridIterativeSolver<SolverCG, PreconditionIdentity>):
+// the whole solve is ONE launch; all scalars stay on the device; dot products are reduced through
+// per-block partials + grid.sync(), summed in a fixed order by every block.
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ double grid_total(const double *partials, int nblocks, double *bc) {
+  // every block sums the same partials in the same order
+  if (threadIdx.x < 32) {
+    const double s = warp_sum_partials(partials, nblocks);
+    if (threadIdx.x == 0) *bc = s;
+  }
+  __syncthreads();
+  const double r = *bc;
+  __syncthreads();
+  return r;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) cg_persistent(SellView A, const double *__restrict__ b, double *x, double *g,
+                                                       double *d, double *h, double *partials /* 3 * gridDim.x */,
+                                                       int max_it, double tol, CgResult *result) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double red[32];
+  __shared__ double bc;
+  const int nb = gridDim.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int WPB = BLOCK / 32;
+  // contiguous chunk of slices per block, warps stride through it
+  const int s_begin = (int)(((int64_t)A.n_slices * blockIdx.x) / nb);
+  const int s_end = (int)(((int64_t)A.n_slices * (blockIdx.x + 1)) / nb);
+  double *pa = partials, *pb = partials + nb, *pc = partials + 2 * nb;
+
+  // x = 0, g = -b, d = -g ; res0 = ||g||
+  double acc = 0.0;
+  for (int s = s_begin + warp; s < s_end; s += WPB) {
+    const int r = s * 32 + lane;
+    if (r < A.n_rows) {
+      const double bv = b[r];
+      x[r] = 0.0;
+      g[r] = -bv;
+      d[r] = bv;
+      acc += bv * bv;
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) pc[blockIdx.x] = acc;
+  grid.sync();
+  double res2 = grid_total(pc, nb, &bc);
+  double res = sqrt(res2);
+  const double res0 = res;
+  int it = 0, status = 0;
+  if (res > tol) {
+    double gh = res * res;
+    while (true) {
+      ++it;
+      // h = A d ; dh = d.h
+      acc = 0.0;
+      for (int s = s_begin + warp; s < s_end; s += WPB) {
+        const double ad = sell_row_dot<false>(A, s, lane, d);
+        const int r = s * 32 + lane;
+        if (r < A.n_rows) {
+          h[r] = ad;
+          acc += d[r] * ad;
+        }
+      }
+      acc = block_sum(acc, red);
+      if (threadIdx.x == 0) pa[blockIdx.x] = acc;
+      grid.sync();
+      const double alpha = gh / grid_total(pa, nb, &bc);
+      // x += alpha d ; g += alpha h ; res2 = g.g
+      acc = 0.0;
+      for (int s = s_begin + warp; s < s_end; s += WPB) {
+        const int r = s * 32 + lane;
+        if (r < A.n_rows) {
+          x[r] += alpha * d[r];
+          const double gv = g[r] + alpha * h[r];
+          g[r] = gv;
+          acc += gv * gv;
+        }
+      }
+      acc = block_sum(acc, red);
+      if (threadIdx.x == 0) pb[blockIdx.x] = acc;
+      grid.sync();
+      res2 = grid_total(pb, nb, &bc);
+      res = sqrt(res2);
+      if (res <= tol) break;
+      if (it >= max_it) { status = 1; break; }
+      const double beta = res2 / gh;
+      gh = res2;
+      // d = beta d - g
+      for (int s = s_begin + warp; s < s_end; s += WPB) {
+        const int r = s * 32 + lane;
+        if (r < A.n_rows) d[r] = beta * d[r] - g[r];
+      }
+      grid.sync();
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    result->iterations = it;
+    result->status = status;
+    result->res0 = res0;
+    result->res = res;
+  }
+}
+
+}  // namespace gmg

@@ -1,0 +1,554 @@
+// gmg_b200 C ABI, RHS path: atom->cell binning, Gaussian charge densities, load vector, point values.
+// Replaces rhs_assembly_optimization (src/step-50.cc:260-306), compute_charge_densities (:509-575)
+// and the load-vector part of assemble_system (:798-828) of the reference.
+#include <algorithm>
+#include <cmath>
+#include <cub/device/device_segmented_sort.cuh>
+#include <vector>
+
+#include "context.h"
+
+using namespace gmg;
+
+struct RhsState {
+  // cells of the last gmg_charge_density call
+  int n_cells = 0, n_q = 0;
+  double *cell_lo = nullptr, *cell_h = nullptr, *qpts = nullptr, *rho = nullptr;
+  int *list_of_cell = nullptr;
+  double r_c = 0.0;
+  // inputs of the last gmg_assemble_rhs call
+  int a_cells = 0, a_nq = 0, n_dofs = 0;
+  double *a_h = nullptr, *shape = nullptr, *weights = nullptr, *kref = nullptr, *ghat = nullptr, *hang_val = nullptr;
+  int *cell_dofs = nullptr, *hang_col = nullptr;
+  int64_t *hang_ptr = nullptr;
+  uint8_t *constrained = nullptr;
+  bool have_kref = false, have_ghat = false;
+  bool bin_pending = false;  // first call of the two-call gmg_bin_atoms protocol done
+};
+
+namespace {
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+template <class T>
+cudaError_t dalloc(T **p, int64_t n) {
+  return cudaMalloc((void **)p, (size_t)std::max<int64_t>(n, 1) * sizeof(T));
+}
+template <class T>
+void dfree(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+template <class T>
+int upload(gmg_context *h, T *&dst, const T *src, int64_t n) {
+  dfree(dst);
+  GMG_CUDA(h, dalloc(&dst, n));
+  if (n > 0) GMG_CUDA(h, cudaMemcpyAsync(dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, h->stream));
+  return GMG_OK;
+}
+
+RhsState *state(gmg_context *h) {
+  if (!h->rhs) h->rhs = new RhsState();
+  return h->rhs;
+}
+
+// ---------------------------------------------------------------------------------------- binning
+struct HashGrid {
+  double lo[3], hi[3];
+  double inv_s;
+  int n[3];
+};
+
+__device__ __forceinline__ int hash_coord(const HashGrid &g, double x, int d) {
+  int c = (int)floor((x - g.lo[d]) * g.inv_s);
+  return min(max(c, 0), g.n[d] - 1);
+}
+
+__global__ void hash_count(int n_atoms, const double *__restrict__ pos, HashGrid g, int *__restrict__ cell_of_atom,
+                           int *__restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_atoms) return;
+  const int cx = hash_coord(g, pos[3 * i], 0), cy = hash_coord(g, pos[3 * i + 1], 1), cz = hash_coord(g, pos[3 * i + 2], 2);
+  const int c = cx + g.n[0] * (cy + g.n[1] * cz);
+  cell_of_atom[i] = c;
+  atomicAdd(count + c, 1);
+}
+
+__global__ void hash_fill(int n_atoms, const int *__restrict__ cell_of_atom, const int *__restrict__ start,
+                          int *__restrict__ cursor, int *__restrict__ sorted_atoms) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_atoms) return;
+  const int c = cell_of_atom[i];
+  sorted_atoms[start[c] + atomicAdd(cursor + c, 1)] = i;
+}
+
+// The reference's criterion, bit for bit: exists vertex v with sqrt(dx^2+dy^2+dz^2) < radius.  The
+// minimum over the 8 vertices is attained at the per-axis nearest vertex (rounding is monotone), so
+// one distance per (cell, atom) decides.  No FMA contraction: explicit round-to-nearest intrinsics.
+__device__ __forceinline__ bool atom_in_cell_support(double lx, double ly, double lz, double hx, double hy, double hz,
+                                                     double X, double Y, double Z, double radius) {
+  const double dx = fmin(fabs(__dsub_rn(X, lx)), fabs(__dsub_rn(X, hx)));
+  const double dy = fmin(fabs(__dsub_rn(Y, ly)), fabs(__dsub_rn(Y, hy)));
+  const double dz = fmin(fabs(__dsub_rn(Z, lz)), fabs(__dsub_rn(Z, hz)));
+  const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  return __dsqrt_rn(d2) < radius;
+}
+
+// MODE 0: count hits per cell ; MODE 1: write hits at rowptr[cell] + k (hash order, sorted afterwards)
+template <int MODE>
+__global__ void __launch_bounds__(128) bin_cells(int n_cells, const double *__restrict__ cell_lo,
+                                                 const double *__restrict__ cell_h, const double *__restrict__ pos,
+                                                 HashGrid g, const int *__restrict__ hstart,
+                                                 const int *__restrict__ sorted_atoms, double radius,
+                                                 int64_t *__restrict__ rowptr_or_count, int *__restrict__ out_atoms) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  const double lx = cell_lo[3 * c], ly = cell_lo[3 * c + 1], lz = cell_lo[3 * c + 2], hh = cell_h[c];
+  const double hx = __dadd_rn(lx, hh), hy = __dadd_rn(ly, hh), hz = __dadd_rn(lz, hh);
+  if (hx + radius < g.lo[0] || lx - radius > g.hi[0] || hy + radius < g.lo[1] || ly - radius > g.hi[1] ||
+      hz + radius < g.lo[2] || lz - radius > g.hi[2]) {
+    if (MODE == 0) rowptr_or_count[c + 1] = 0;
+    return;
+  }
+  const int x0 = hash_coord(g, lx - radius, 0), x1 = hash_coord(g, hx + radius, 0);
+  const int y0 = hash_coord(g, ly - radius, 1), y1 = hash_coord(g, hy + radius, 1);
+  const int z0 = hash_coord(g, lz - radius, 2), z1 = hash_coord(g, hz + radius, 2);
+  int64_t k = (MODE == 1) ? rowptr_or_count[c] : 0;
+  int cnt = 0;
+  for (int z = z0; z <= z1; ++z)
+    for (int y = y0; y <= y1; ++y) {
+      const int row = g.n[0] * (y + g.n[1] * z);
+      const int a0 = hstart[row + x0], a1 = hstart[row + x1 + 1];  // contiguous run of hash cells along x
+      for (int a = a0; a < a1; ++a) {
+        const int i = sorted_atoms[a];
+        if (atom_in_cell_support(lx, ly, lz, hx, hy, hz, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], radius)) {
+          if (MODE == 1) out_atoms[k++] = i;
+          ++cnt;
+        }
+      }
+    }
+  if (MODE == 0) rowptr_or_count[c + 1] = cnt;
+}
+
+// ---------------------------------------------------------------------------------------- density
+// one block per cell; thread t owns quadrature point t % nq_pad and every (blockDim/nq_pad)-th atom
+__global__ void __launch_bounds__(128) density_kernel(int n_cells, const double *__restrict__ cell_lo,
+                                                      const double *__restrict__ cell_h,
+                                                      const int *__restrict__ list_of_cell,
+                                                      const int64_t *__restrict__ list_ptr,
+                                                      const int *__restrict__ list_atoms, int n_atoms,
+                                                      const double *__restrict__ pos, const double *__restrict__ charge,
+                                                      int n_q, const double *__restrict__ qpts, double C, double inv_rc2,
+                                                      double *__restrict__ rho) {
+  extern __shared__ double sacc[];  // blockDim.x
+  const int c = blockIdx.x;
+  const int t = threadIdx.x;
+  const int groups = max((int)blockDim.x / n_q, 1);  // threads per q-point
+  const int lo_t = t % n_q, grp = t / n_q;
+  const int list = list_of_cell[c];
+  int64_t a0 = 0, a1 = n_atoms;
+  if (list >= 0) {
+    a0 = list_ptr[list];
+    a1 = list_ptr[list + 1];
+  }
+  const double hh = cell_h[c];
+  for (int q0 = 0; q0 < n_q; q0 += blockDim.x) {  // more q-points than threads: several passes
+    const int q = q0 + lo_t;
+    double acc = 0.0;
+    if (q < n_q && grp < groups) {
+      const double xq = cell_lo[3 * c] + hh * qpts[3 * q];
+      const double yq = cell_lo[3 * c + 1] + hh * qpts[3 * q + 1];
+      const double zq = cell_lo[3 * c + 2] + hh * qpts[3 * q + 2];
+      for (int64_t a = a0 + grp; a < a1; a += groups) {
+        const int i = (list >= 0) ? list_atoms[a] : (int)a;
+        const double dx = pos[3 * i] - xq, dy = pos[3 * i + 1] - yq, dz = pos[3 * i + 2] - zq;
+        const double r = sqrt(dx * dx + dy * dy + dz * dz);  // Point::distance, then r*r (src/step-50.cc:563-564)
+        acc += C * exp(-(r * r) * inv_rc2) * charge[i];
+      }
+    }
+    sacc[t] = acc;
+    __syncthreads();
+    if (grp == 0 && q < n_q) {
+      double s = 0.0;
+      for (int gi = 0; gi < groups; ++gi) s += sacc[gi * n_q + lo_t];
+      rho[(int64_t)c * n_q + q] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------ load vector
+__global__ void __launch_bounds__(128) load_vector_kernel(int n_cells, const double *__restrict__ rho,
+                                                          const double *__restrict__ cell_h,
+                                                          const int *__restrict__ cell_dofs, int n_q,
+                                                          const double *__restrict__ shape,
+                                                          const double *__restrict__ weights,
+                                                          const double *__restrict__ kref, const double *__restrict__ ghat,
+                                                          const int64_t *__restrict__ hang_ptr,
+                                                          const int *__restrict__ hang_col,
+                                                          const double *__restrict__ hang_val,
+                                                          const uint8_t *__restrict__ constrained, double *b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  const double hh = cell_h[c];
+  const double jac = hh * hh * hh;
+  double f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool any = false;
+  for (int q = 0; q < n_q; ++q) {
+    const double rw = rho[(int64_t)c * n_q + q] * (weights[q] * jac);
+    if (rw != 0.0) any = true;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] += shape[q * 8 + i] * rw;
+  }
+  int dofs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dofs[i] = cell_dofs[(int64_t)c * 8 + i];
+  if (kref != nullptr && ghat != nullptr) {
+    double gl[8];
+    bool anyg = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gl[j] = ghat[dofs[j]];
+      anyg |= gl[j] != 0.0;
+    }
+    if (anyg) {
+      any = true;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += kref[i * 8 + j] * gl[j];
+        f[i] -= hh * s;
+      }
+    }
+  }
+  if (!any) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int dof = dofs[i];
+    const int64_t p0 = hang_ptr[dof], p1 = hang_ptr[dof + 1];
+    if (p1 > p0) {
+      for (int64_t p = p0; p < p1; ++p) {
+        const int par = hang_col[p];
+        if (!constrained[par]) atomicAdd(b + par, hang_val[p] * f[i]);
+      }
+    } else if (!constrained[dof]) {
+      atomicAdd(b + dof, f[i]);
+    }
+  }
+}
+
+__global__ void point_values_kernel(int n, const int *__restrict__ cell_dofs, const double *__restrict__ xi,
+                                    const double *__restrict__ u, double *__restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double x = xi[3 * p], y = xi[3 * p + 1], z = xi[3 * p + 2];
+  double s = 0.0;
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    const double w = ((v & 1) ? x : 1.0 - x) * ((v & 2) ? y : 1.0 - y) * ((v & 4) ? z : 1.0 - z);
+    s += w * u[cell_dofs[8 * p + v]];
+  }
+  out[p] = s;
+}
+
+int run_density(gmg_context *h, RhsState *s) {
+  if (s->n_cells == 0) return GMG_OK;
+  const double C = 4.0 * M_PI / (s->r_c * s->r_c * s->r_c * std::pow(M_PI, 1.5));  // src/step-50.cc:522
+  const int block = (s->n_q <= 64) ? 64 : 128;  // threads per cell: blockDim / n_q threads share a q-point
+  density_kernel<<<s->n_cells, block, sizeof(double) * block, h->stream>>>(
+      s->n_cells, s->cell_lo, s->cell_h, s->list_of_cell, h->list_ptr, h->list_atoms, h->n_atoms, h->atom_pos, h->atom_q,
+      s->n_q, s->qpts, C, 1.0 / (s->r_c * s->r_c), s->rho);
+  GMG_LAUNCH_CHECK(h);
+  return GMG_OK;
+}
+
+int run_load_vector(gmg_context *h, RhsState *s, const double *rho_dev, double *b_dev) {
+  GMG_CUDA(h, cudaMemsetAsync(b_dev, 0, sizeof(double) * s->n_dofs, h->stream));
+  if (s->a_cells == 0) return GMG_OK;
+  load_vector_kernel<<<cdiv(s->a_cells, 128), 128, 0, h->stream>>>(
+      s->a_cells, rho_dev, s->a_h, s->cell_dofs, s->a_nq, s->shape, s->weights, s->have_kref ? s->kref : nullptr,
+      s->have_ghat ? s->ghat : nullptr, s->hang_ptr, s->hang_col, s->hang_val, s->constrained, b_dev);
+  GMG_LAUNCH_CHECK(h);
+  return GMG_OK;
+}
+
+}  // namespace
+
+namespace gmg {
+void rhs_free(gmg_context *h) {
+  RhsState *s = h->rhs;
+  if (!s) return;
+  dfree(s->cell_lo);
+  dfree(s->cell_h);
+  dfree(s->qpts);
+  dfree(s->rho);
+  dfree(s->list_of_cell);
+  dfree(s->a_h);
+  dfree(s->shape);
+  dfree(s->weights);
+  dfree(s->kref);
+  dfree(s->ghat);
+  dfree(s->hang_val);
+  dfree(s->cell_dofs);
+  dfree(s->hang_col);
+  dfree(s->hang_ptr);
+  dfree(s->constrained);
+  delete s;
+  h->rhs = nullptr;
+}
+}  // namespace gmg
+
+extern "C" {
+
+int gmg_set_atoms(gmg_handle h, int32_t n_atoms, const double *pos, const double *charge) {
+  if (!h || n_atoms < 0 || (n_atoms && (!pos || !charge))) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  h->n_atoms = n_atoms;
+  if (int rc = upload(h, h->atom_pos, pos, 3 * (int64_t)n_atoms)) return rc;
+  if (int rc = upload(h, h->atom_q, charge, n_atoms)) return rc;
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return GMG_OK;
+}
+
+int gmg_set_atom_lists(gmg_handle h, int32_t n_lists, const int64_t *rowptr, const int32_t *atoms) {
+  if (!h || n_lists < 0 || !rowptr) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  h->n_lists = n_lists;
+  if (int rc = upload(h, h->list_ptr, rowptr, (int64_t)n_lists + 1)) return rc;
+  if (int rc = upload(h, h->list_atoms, atoms, rowptr[n_lists])) return rc;
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return GMG_OK;
+}
+
+int gmg_bin_atoms(gmg_handle h, int32_t n_cells, const double *cell_lo, const double *cell_h, int32_t n_atoms,
+                  const double *pos, double radius, int64_t *rowptr_out, int32_t *atoms_out) {
+  if (!h || n_cells < 0 || n_atoms < 0 || !rowptr_out || radius <= 0.0) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  if (atoms_out != nullptr && state(h)->bin_pending && h->n_lists == n_cells && h->list_ptr && h->list_atoms) {
+    state(h)->bin_pending = false;
+    // second call of the two-call protocol: hand out the lists computed by the first
+    GMG_CUDA(h, cudaMemcpy(rowptr_out, h->list_ptr, sizeof(int64_t) * (n_cells + 1), cudaMemcpyDeviceToHost));
+    if (rowptr_out[n_cells] > 0)
+      GMG_CUDA(h, cudaMemcpy(atoms_out, h->list_atoms, sizeof(int) * rowptr_out[n_cells], cudaMemcpyDeviceToHost));
+    return GMG_OK;
+  }
+  // hash grid over the atoms' bounding box, about one atom per hash cell
+  HashGrid g;
+  double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+  if (n_atoms > 0) {
+    for (int d = 0; d < 3; ++d) lo[d] = hi[d] = pos[d];
+    for (int i = 0; i < n_atoms; ++i)
+      for (int d = 0; d < 3; ++d) {
+        lo[d] = std::min(lo[d], pos[3 * i + d]);
+        hi[d] = std::max(hi[d], pos[3 * i + d]);
+      }
+  }
+  double vol = 1.0;
+  for (int d = 0; d < 3; ++d) vol *= std::max(hi[d] - lo[d], 1e-3);
+  double s = std::cbrt(vol / std::max(n_atoms, 1));
+  s = std::min(std::max(s, radius / 8.0), radius);
+  int64_t total = 1;
+  for (int d = 0; d < 3; ++d) {
+    g.lo[d] = lo[d];
+    g.hi[d] = hi[d];
+    g.n[d] = std::max(1, (int)std::floor((hi[d] - lo[d]) / s) + 1);
+    total *= g.n[d];
+  }
+  if (total > (int64_t)1 << 28) return fail(h, GMG_EINVAL, "atom hash grid too large");
+  g.inv_s = 1.0 / s;
+  const int nh = (int)total;
+  double *d_pos = nullptr, *d_lo = nullptr, *d_h = nullptr;
+  int *d_cell_of_atom = nullptr, *d_count = nullptr, *d_start = nullptr, *d_sorted = nullptr;
+  int64_t *d_rowptr = nullptr;
+  int *d_atoms = nullptr, *d_atoms_sorted = nullptr;
+  void *d_temp = nullptr;
+  int rc = GMG_OK;
+  auto cleanup = [&]() {
+    dfree(d_pos); dfree(d_lo); dfree(d_h); dfree(d_cell_of_atom); dfree(d_count); dfree(d_start); dfree(d_sorted);
+    dfree(d_atoms);
+    if (d_temp) cudaFree(d_temp);
+  };
+#define TRY(expr)                                                                         \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      cleanup();                                                                          \
+      dfree(d_rowptr);                                                                    \
+      dfree(d_atoms_sorted);                                                              \
+      return fail(h, GMG_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));     \
+    }                                                                                     \
+  } while (0)
+  TRY(dalloc(&d_pos, 3 * (int64_t)n_atoms));
+  TRY(dalloc(&d_lo, 3 * (int64_t)n_cells));
+  TRY(dalloc(&d_h, n_cells));
+  TRY(dalloc(&d_cell_of_atom, n_atoms));
+  TRY(dalloc(&d_count, nh + 1));
+  TRY(dalloc(&d_start, nh + 1));
+  TRY(dalloc(&d_sorted, n_atoms));
+  TRY(dalloc(&d_rowptr, (int64_t)n_cells + 1));
+  TRY(cudaMemcpyAsync(d_pos, pos, sizeof(double) * 3 * n_atoms, cudaMemcpyHostToDevice, h->stream));
+  TRY(cudaMemcpyAsync(d_lo, cell_lo, sizeof(double) * 3 * n_cells, cudaMemcpyHostToDevice, h->stream));
+  TRY(cudaMemcpyAsync(d_h, cell_h, sizeof(double) * n_cells, cudaMemcpyHostToDevice, h->stream));
+  TRY(cudaMemsetAsync(d_count, 0, sizeof(int) * (nh + 1), h->stream));
+  if (n_atoms > 0) {
+    hash_count<<<cdiv(n_atoms, 256), 256, 0, h->stream>>>(n_atoms, d_pos, g, d_cell_of_atom, d_count);
+    h->launches++;
+  }
+  // exclusive scan of the (small) hash histogram on the host
+  std::vector<int> cnt(nh + 1), start(nh + 1, 0);
+  TRY(cudaMemcpyAsync(cnt.data(), d_count, sizeof(int) * (nh + 1), cudaMemcpyDeviceToHost, h->stream));
+  TRY(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < nh; ++i) start[i + 1] = start[i] + cnt[i];
+  TRY(cudaMemcpyAsync(d_start, start.data(), sizeof(int) * (nh + 1), cudaMemcpyHostToDevice, h->stream));
+  TRY(cudaMemsetAsync(d_count, 0, sizeof(int) * (nh + 1), h->stream));
+  if (n_atoms > 0) {
+    hash_fill<<<cdiv(n_atoms, 256), 256, 0, h->stream>>>(n_atoms, d_cell_of_atom, d_start, d_count, d_sorted);
+    h->launches++;
+  }
+  // pass 1: counts
+  TRY(cudaMemsetAsync(d_rowptr, 0, sizeof(int64_t) * (n_cells + 1), h->stream));
+  if (n_cells > 0) {
+    bin_cells<0><<<cdiv(n_cells, 128), 128, 0, h->stream>>>(n_cells, d_lo, d_h, d_pos, g, d_start, d_sorted, radius,
+                                                            d_rowptr, nullptr);
+    h->launches++;
+  }
+  std::vector<int64_t> rp(n_cells + 1);
+  TRY(cudaMemcpyAsync(rp.data(), d_rowptr, sizeof(int64_t) * (n_cells + 1), cudaMemcpyDeviceToHost, h->stream));
+  TRY(cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < n_cells; ++c) rp[c + 1] += rp[c];
+  const int64_t n_pairs = rp[n_cells];
+  TRY(cudaMemcpyAsync(d_rowptr, rp.data(), sizeof(int64_t) * (n_cells + 1), cudaMemcpyHostToDevice, h->stream));
+  TRY(dalloc(&d_atoms, n_pairs));
+  TRY(dalloc(&d_atoms_sorted, n_pairs));
+  if (n_cells > 0 && n_pairs > 0) {
+    bin_cells<1><<<cdiv(n_cells, 128), 128, 0, h->stream>>>(n_cells, d_lo, d_h, d_pos, g, d_start, d_sorted, radius,
+                                                            d_rowptr, d_atoms);
+    h->launches++;
+    // ascending atom index inside every cell (std::set iteration order of the reference)
+    size_t temp_bytes = 0;
+    TRY(cub::DeviceSegmentedSort::SortKeys(nullptr, temp_bytes, d_atoms, d_atoms_sorted, n_pairs, n_cells, d_rowptr,
+                                           d_rowptr + 1, h->stream));
+    TRY(cudaMalloc(&d_temp, std::max<size_t>(temp_bytes, 1)));
+    TRY(cub::DeviceSegmentedSort::SortKeys(d_temp, temp_bytes, d_atoms, d_atoms_sorted, n_pairs, n_cells, d_rowptr,
+                                           d_rowptr + 1, h->stream));
+    h->launches++;
+  }
+  TRY(cudaStreamSynchronize(h->stream));
+  TRY(cudaGetLastError());
+#undef TRY
+  cleanup();
+  // keep the lists on the device as the current atom lists
+  dfree(h->list_ptr);
+  dfree(h->list_atoms);
+  h->list_ptr = d_rowptr;
+  h->list_atoms = d_atoms_sorted;
+  h->n_lists = n_cells;
+  std::copy(rp.begin(), rp.end(), rowptr_out);
+  state(h)->bin_pending = (atoms_out == nullptr);
+  if (atoms_out && n_pairs > 0)
+    GMG_CUDA(h, cudaMemcpy(atoms_out, h->list_atoms, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost));
+  return rc;
+}
+
+int gmg_charge_density(gmg_handle h, int32_t n_cells, const double *cell_lo, const double *cell_h,
+                       const int32_t *list_of_cell, int32_t n_q, const double *qpoints, double r_c, double *rho_out) {
+  if (!h || n_cells < 0 || n_q < 1 || !cell_lo || !cell_h || !list_of_cell || !qpoints) return GMG_EINVAL;
+  if (!h->atom_pos) return fail(h, GMG_EINVAL, "gmg_set_atoms first");
+  cudaSetDevice(h->device);
+  RhsState *s = state(h);
+  s->n_cells = n_cells;
+  s->n_q = n_q;
+  s->r_c = r_c;
+  if (int rc = upload(h, s->cell_lo, cell_lo, 3 * (int64_t)n_cells)) return rc;
+  if (int rc = upload(h, s->cell_h, cell_h, n_cells)) return rc;
+  if (int rc = upload(h, s->list_of_cell, list_of_cell, n_cells)) return rc;
+  if (int rc = upload(h, s->qpts, qpoints, 3 * (int64_t)n_q)) return rc;
+  dfree(s->rho);
+  GMG_CUDA(h, dalloc(&s->rho, (int64_t)n_cells * n_q));
+  if (int rc = run_density(h, s)) return rc;
+  if (rho_out)
+    GMG_CUDA(h, cudaMemcpyAsync(rho_out, s->rho, sizeof(double) * (int64_t)n_cells * n_q, cudaMemcpyDeviceToHost,
+                                h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return GMG_OK;
+}
+
+int gmg_assemble_rhs(gmg_handle h, int32_t n_cells, const double *rho, const double *cell_h, const int32_t *cell_dofs,
+                     int32_t n_q, const double *shape, const double *weights, const double *Kref, const double *ghat,
+                     int32_t n_dofs, const int64_t *hang_rowptr, const int32_t *hang_col, const double *hang_val,
+                     const uint8_t *constrained, double *b_out) {
+  if (!h || n_cells < 0 || !cell_h || !cell_dofs || !shape || !weights || !hang_rowptr || !constrained || !b_out)
+    return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  RhsState *s = state(h);
+  if (rho == nullptr && (s->rho == nullptr || s->n_cells != n_cells || s->n_q != n_q))
+    return fail(h, GMG_EINVAL, "rho == NULL needs a matching gmg_charge_density call first");
+  s->a_cells = n_cells;
+  s->a_nq = n_q;
+  s->n_dofs = n_dofs;
+  if (int rc = upload(h, s->a_h, cell_h, n_cells)) return rc;
+  if (int rc = upload(h, s->cell_dofs, cell_dofs, 8 * (int64_t)n_cells)) return rc;
+  if (int rc = upload(h, s->shape, shape, 8 * (int64_t)n_q)) return rc;
+  if (int rc = upload(h, s->weights, weights, n_q)) return rc;
+  s->have_kref = Kref != nullptr;
+  s->have_ghat = ghat != nullptr;
+  if (Kref)
+    if (int rc = upload(h, s->kref, Kref, 64)) return rc;
+  if (ghat)
+    if (int rc = upload(h, s->ghat, ghat, n_dofs)) return rc;
+  if (int rc = upload(h, s->hang_ptr, hang_rowptr, (int64_t)n_dofs + 1)) return rc;
+  if (int rc = upload(h, s->hang_col, hang_col, hang_rowptr[n_dofs])) return rc;
+  if (int rc = upload(h, s->hang_val, hang_val, hang_rowptr[n_dofs])) return rc;
+  if (int rc = upload(h, s->constrained, constrained, n_dofs)) return rc;
+  const double *rho_dev = s->rho;
+  if (rho != nullptr) {
+    if (int rc = ensure_stage(h, std::max<int64_t>((int64_t)n_cells * n_q, n_dofs))) return rc;
+    GMG_CUDA(h, cudaMemcpyAsync(h->stage_a, rho, sizeof(double) * (int64_t)n_cells * n_q, cudaMemcpyHostToDevice,
+                                h->stream));
+    rho_dev = h->stage_a;
+  } else if (int rc = ensure_stage(h, n_dofs)) {
+    return rc;
+  }
+  if (int rc = run_load_vector(h, s, rho_dev, h->stage_b)) return rc;
+  GMG_CUDA(h, cudaMemcpyAsync(b_out, h->stage_b, sizeof(double) * n_dofs, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return GMG_OK;
+}
+
+int gmg_rhs_step_dev(gmg_handle h, double *b_dev) {
+  if (!h || !h->rhs || !b_dev) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  RhsState *s = h->rhs;
+  if (s->n_cells != s->a_cells || s->n_q != s->a_nq) return fail(h, GMG_EINVAL, "density / load-vector inputs differ");
+  if (int rc = run_density(h, s)) return rc;
+  return run_load_vector(h, s, s->rho, b_dev);
+}
+
+int gmg_point_values(gmg_handle h, int32_t n_points, const int32_t *cell_dofs, const double *ref_coords, const double *u,
+                     int32_t n_dofs, double *phi_out) {
+  if (!h || n_points < 0 || !cell_dofs || !ref_coords || !u || !phi_out) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  int *d_dofs = nullptr;
+  double *d_xi = nullptr, *d_u = nullptr, *d_out = nullptr;
+  int rc = GMG_OK;
+  if ((rc = upload(h, d_dofs, cell_dofs, 8 * (int64_t)n_points)) == GMG_OK &&
+      (rc = upload(h, d_xi, ref_coords, 3 * (int64_t)n_points)) == GMG_OK && (rc = upload(h, d_u, u, n_dofs)) == GMG_OK &&
+      cudaMalloc(&d_out, sizeof(double) * std::max(n_points, 1)) == cudaSuccess) {
+    if (n_points > 0) {
+      point_values_kernel<<<cdiv(n_points, 128), 128, 0, h->stream>>>(n_points, d_dofs, d_xi, d_u, d_out);
+      h->launches++;
+    }
+    cudaMemcpyAsync(phi_out, d_out, sizeof(double) * n_points, cudaMemcpyDeviceToHost, h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, GMG_ECUDA, "point values failed");
+  } else if (rc == GMG_OK) {
+    rc = fail(h, GMG_ECUDA, "allocation failed");
+  }
+  dfree(d_dofs);
+  dfree(d_xi);
+  dfree(d_u);
+  dfree(d_out);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+/* gmg_b200.h -- C ABI of the B200-native MG-PCG + Gaussian-charge RHS path.
+ *
+ * The reference (vinayak-gholap1993/Geometric-Multigrid-preconditioners-for-long-range-Coulomb-
+ * interaction) has no plugin/FFI layer: its hot path is `LaplaceProblem<dim>::solve()`
+ * (src/step-50.cc:938-1017) wiring deal.II / Trilinos objects together, fed by
+ * `rhs_assembly_optimization()` (:260-306), `compute_charge_densities()` (:509-575) and the
+ * load-vector part of `assemble_system()` (:798-828).  The entry points below are exactly the
+ * operations that path performs on data the host hands over (assembled CSR matrices, transfer
+ * matrices, copy indices, atoms, cell lists); each cites the reference construct it replaces.
+ *
+ * Conventions: every function returns 0 on success or a negative GMG_E* code; the message is
+ * available from gmg_last_error().  All pointers are HOST memory borrowed for the duration of the
+ * call unless the name ends in `_dev` / the function says "device".  One caller thread per handle.
+ * Indices are 32-bit (deal.II `types::global_dof_index` is `unsigned int` in the reference build),
+ * row pointers 64-bit, values fp64.  There is no CPU fallback: without a CUDA device gmg_create
+ * fails with GMG_ENODEVICE.
+ */
+#ifndef GMG_B200_H
+#define GMG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gmg_context *gmg_handle;
+
+enum {
+  GMG_OK = 0,
+  GMG_EINVAL = -1,        /* bad argument / call order */
+  GMG_ENODEVICE = -2,     /* no CUDA device, or CUDA runtime error at creation */
+  GMG_ECUDA = -3,         /* CUDA runtime error */
+  GMG_ENOCONVERGENCE = -4,/* SolverControl::NoConvergence (outer > max_it, or coarse > its limit) */
+  GMG_ENCCL = -5
+};
+
+/* which matrix */
+enum {
+  GMG_SYSTEM = 0,  /* system_matrix              (include/step_50.h:156)                         */
+  GMG_LEVEL = 1,   /* mg_matrices[level]         (include/step_50.h:168, src/step-50.cc:888-889) */
+  GMG_EDGE = 2,    /* mg_interface_matrices[l]   (include/step_50.h:169, src/step-50.cc:896-925) */
+  GMG_PROLONG = 3  /* MGTransferPrebuilt prolongation level -> level+1 (src/step-50.cc:957-958)  */
+};
+
+/* smoother kinds (src/step-50.cc:969-973 selects the smoother at source level) */
+enum {
+  GMG_SMOOTHER_JACOBI = 0,      /* LA::MPI::PreconditionJacobi(omega), `steps` steps               */
+  GMG_SMOOTHER_CHEBYSHEV = 1,   /* Chebyshev-accelerated Jacobi of degree `steps`                  */
+  GMG_SMOOTHER_MC_SSOR = 2,     /* multicolour SSOR(omega): stands in for Ifpack's sequential SSOR */
+  GMG_SMOOTHER_LEX_SSOR = 3     /* Ifpack's lexicographic SSOR(omega) itself, level-scheduled      */
+};
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int gmg_create(int device, gmg_handle *out);
+int gmg_destroy(gmg_handle h);
+const char *gmg_last_error(gmg_handle h);
+/* Launch all kernels of this handle on an existing CUDA stream (a `cudaStream_t` passed as void*),
+ * e.g. torch's current stream, so that the caller's CUDA events bracket the work. */
+int gmg_set_stream(gmg_handle h, void *cuda_stream);
+int gmg_synchronize(gmg_handle h);
+/* library build info: returns the sm arch the kernels were compiled for (100) */
+int gmg_compiled_arch(void);
+
+/* ---- hierarchy hand-over (replaces the deal.II objects `solve()` wires together) ------------- */
+int gmg_set_num_levels(gmg_handle h, int n_levels);
+/* CSR, sorted or unsorted columns, explicit zeros allowed (Epetra keeps the pattern's zeros). */
+int gmg_set_matrix(gmg_handle h, int which, int level, int32_t n_rows, int32_t n_cols,
+                   const int64_t *rowptr, const int32_t *col, const double *val);
+/* MGLevelGlobalTransfer::copy_indices[level]: (global dof, level dof) pairs. */
+int gmg_set_copy_indices(gmg_handle h, int level, int32_t n, const int32_t *global_idx,
+                         const int32_t *level_idx);
+/* MGSmootherPrecondition<...>::initialize(mg_matrices, AdditionalData(omega)); set_steps(steps). */
+int gmg_set_smoother(gmg_handle h, int kind, double omega, int steps);
+/* SolverControl coarse_solver_control(max_it, abs_tol) + SolverCG + PreconditionIdentity. */
+int gmg_set_coarse(gmg_handle h, int max_it, double abs_tol);
+/* Drop stored entries with |a_ij| <= drop_tol when building the device format (default: keep all). */
+int gmg_set_drop_tolerance(gmg_handle h, double drop_tol);
+/* Build device formats (sliced ELL), transposes, colourings, eigenvalue bounds. */
+int gmg_setup(gmg_handle h);
+
+/* ---- the solve path --------------------------------------------------------------------------- */
+/* solver.solve(system_matrix, solution, system_rhs, PreconditionMG) -- SolverCG recurrences,
+ * stop when ||g||_2 <= abs_tol, fail (GMG_ENOCONVERGENCE) at max_it.  x_inout: initial guess in,
+ * solution out.  res0 = "Starting value", res_final = "Convergence value". */
+int gmg_pcg_solve(gmg_handle h, const double *b, double *x_inout, int max_it, double abs_tol,
+                  int *iters, double *res0, double *res_final);
+/* PreconditionerType == "Jacobi": PCG with omega * D^-1 (src/step-50.cc:996-1006). */
+int gmg_pcg_solve_jacobi(gmg_handle h, const double *b, double *x_inout, double omega, int max_it,
+                         double abs_tol, int *iters, double *res0, double *res_final);
+/* PreconditionMG::vmult: dst = M^-1 src (one V-cycle incl. copy_to_mg / copy_from_mg). */
+int gmg_vcycle_apply(gmg_handle h, const double *src, double *dst);
+/* matrix.vmult */
+int gmg_spmv(gmg_handle h, int which, int level, const double *x, double *y);
+/* MGCoarseGridIterativeSolver / plain SolverCG with identity preconditioner from x = 0. */
+int gmg_cg_solve(gmg_handle h, int which, int level, const double *b, double *x, int max_it,
+                 double abs_tol, int *iters, double *res_final);
+/* one application of the level smoother: u <- smooth(u, rhs) (`steps` steps), zero_start != 0
+ * ignores u on input. */
+int gmg_smooth(gmg_handle h, int level, const double *rhs, double *u_inout, int zero_start);
+/* system_matrix.l1_norm / linfty_norm / frobenius_norm (src/step-50.cc:950-952) -> out[3] */
+int gmg_matrix_norms(gmg_handle h, int which, int level, double out[3]);
+/* vector l1 / l2 / linfty norms (src/step-50.cc:946-948, 1012-1014) -> out[3] */
+int gmg_vector_norms(gmg_handle h, int64_t n, const double *v, double out[3]);
+/* inner coarse-CG iteration counts of the V-cycles of the last gmg_pcg_solve (at most cap). */
+int gmg_last_coarse_iterations(gmg_handle h, int32_t *out, int cap, int *n_out);
+
+/* ---- device-resident variants (bench `value` leg: inputs already in HBM) ---------------------- */
+int gmg_vec_alloc(gmg_handle h, int64_t n, double **dev_out);
+int gmg_vec_free(gmg_handle h, double *dev);
+int gmg_vec_upload(gmg_handle h, double *dev, const double *host, int64_t n);
+int gmg_vec_download(gmg_handle h, double *host, const double *dev, int64_t n);
+int gmg_pcg_solve_dev(gmg_handle h, const double *b_dev, double *x_dev, int max_it, double abs_tol,
+                      int *iters, double *res0, double *res_final);
+int gmg_vcycle_apply_dev(gmg_handle h, const double *src_dev, double *dst_dev);
+int gmg_spmv_dev(gmg_handle h, int which, int level, const double *x_dev, double *y_dev);
+int gmg_cg_solve_dev(gmg_handle h, int which, int level, const double *b_dev, double *x_dev,
+                     int max_it, double abs_tol, int *iters, double *res_final);
+/* bytes one SpMV / one coarse-CG iteration with this matrix moves algorithmically
+ * (SURVEY.md section 8d): out[0] = stored nnz, out[1] = SpMV bytes, out[2] = CG-iteration bytes */
+int gmg_matrix_traffic(gmg_handle h, int which, int level, double out[3]);
+/* accumulated device time (ms, CUDA events on the handle's stream) and launch count of the
+ * persistent coarse-CG kernel since the last reset; inner iterations summed in *iters. */
+int gmg_coarse_profile(gmg_handle h, int reset, double *ms, int64_t *launches, int64_t *iters);
+/* number of kernel launches issued by this handle since creation */
+int64_t gmg_launch_count(gmg_handle h);
+
+/* ---- the RHS path ----------------------------------------------------------------------------- */
+/* rhs_assembly_optimization (src/step-50.cc:260-306): cell c lists atom i iff some vertex v of the
+ * axis-aligned cube [lo_c, lo_c + h_c]^3 has ||X_i - v||_2 < radius (strict).  Output CSR with
+ * ascending atom indices per cell.  Call with atoms_out == NULL to obtain rowptr_out (n_cells+1)
+ * and the total count, then again with a buffer of rowptr_out[n_cells] entries. */
+int gmg_bin_atoms(gmg_handle h, int32_t n_cells, const double *cell_lo /*[n_cells][3]*/,
+                  const double *cell_h /*[n_cells]*/, int32_t n_atoms, const double *pos /*[n][3]*/,
+                  double radius, int64_t *rowptr_out, int32_t *atoms_out);
+/* Keep per-list atom indices on the device for gmg_charge_density; children inherit the parent's
+ * list (src/step-50.cc:441-449) by pointing at the same list id. */
+int gmg_set_atom_lists(gmg_handle h, int32_t n_lists, const int64_t *rowptr, const int32_t *atoms);
+int gmg_set_atoms(gmg_handle h, int32_t n_atoms, const double *pos /*[n][3]*/, const double *charge);
+/* compute_charge_densities (src/step-50.cc:509-575): rho[c][q] = sum_k C exp(-|X_k - x_q|^2/r_c^2) q_k,
+ * x_q = lo_c + h_c * qpoint[q]; list_of_cell[c] < 0 sums over all atoms (flag off). */
+int gmg_charge_density(gmg_handle h, int32_t n_cells, const double *cell_lo, const double *cell_h,
+                       const int32_t *list_of_cell, int32_t n_q, const double *qpoints /*[n_q][3] unit cell*/,
+                       double r_c, double *rho_out /*[n_cells][n_q]*/);
+/* load vector + constraints (src/step-50.cc:813-828): for every cell, cell_rhs(i) = sum_q shape[q][i]
+ * rho[c][q] w[q] h_c^3 - h_c * sum_j Kref[i][j] ghat[dof_j]; distributed into b with hanging-node
+ * weights (constraint CSR over dofs; rows of unconstrained dofs empty); dofs flagged in
+ * `constrained` end at 0.  ghat may be NULL (homogeneous). */
+int gmg_assemble_rhs(gmg_handle h, int32_t n_cells, const double *rho, const double *cell_h,
+                     const int32_t *cell_dofs /*[n_cells][8]*/, int32_t n_q, const double *shape /*[n_q][8]*/,
+                     const double *weights /*[n_q]*/, const double *Kref /*[8][8] or NULL*/,
+                     const double *ghat /*[n_dofs] or NULL*/, int32_t n_dofs,
+                     const int64_t *hang_rowptr, const int32_t *hang_col, const double *hang_val,
+                     const uint8_t *constrained, double *b_out);
+/* phi_h(X_i) for the energy (src/step-50.cc:1353-1366): trilinear evaluation in given cells. */
+int gmg_point_values(gmg_handle h, int32_t n_points, const int32_t *cell_dofs /*[n][8]*/,
+                     const double *ref_coords /*[n][3]*/, const double *u, int32_t n_dofs,
+                     double *phi_out);
+/* fused device-resident RHS step used by the bench `value` leg: densities + load vector with the
+ * inputs of the last gmg_charge_density / gmg_assemble_rhs calls kept on the device. */
+int gmg_rhs_step_dev(gmg_handle h, double *b_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMG_B200_H */

@@ -139,6 +139,7 @@ class LaplaceProblem:
     def solve(self, x0):
         A, b = self.system.A, self.b
         rec = self.rec
+        self.x0 = np.zeros(self.dofs.n) if x0 is None else x0.copy()
         rec["rhs_l1"], rec["rhs_l2"], rec["rhs_linf"] = float(np.abs(b).sum()), float(np.sqrt(b @ b)), float(np.abs(b).max())
         rec["mat_l1"] = float(abs(A).sum(0).max())
         rec["mat_linf"] = float(abs(A).sum(1).max())

@@ -1,0 +1,122 @@
+"""GPU parity tests of the RHS path (binning, charge densities, load vector, point values) through the
+C ABI against the CPU oracle.  Binning: bit-exact lists.  Densities / rhs: 1e-12 relative L2
+(north star), the only differences being summation order, FMA contraction and CUDA's exp (<= 1 ulp)."""
+import numpy as np
+import pytest
+
+from conftest import make_prm
+from helpers import oracle_cycle, pkg, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    return pkg().capi
+
+
+def active_cell_arrays(P):
+    """Flatten the oracle's active cells (level by level) into the arrays the C ABI takes."""
+    f, d = P.forest, P.dofs
+    lo, h, dofs, base = [], [], [], []
+    for l in range(f.n_levels):
+        act = d.active_cells[l]
+        lo.append(f.lo + f.ijk[l][act] * f.h(l))
+        h.append(np.full(len(act), f.h(l)))
+        dofs.append(d.cell_dofs[l])
+        anc = act.copy()
+        for k in range(l, 0, -1):
+            anc = f.parent[k][anc]
+        base.append(anc)
+    return np.concatenate(lo), np.concatenate(h), np.concatenate(dofs), np.concatenate(base)
+
+
+def base_cells(P):
+    f = P.forest
+    return f.lo + f.ijk[0] * f.H, np.full(f.n_cells(0), f.H)
+
+
+@pytest.mark.parametrize("atom", ["atom_n1_2.data", "atom_n1_8.data"])
+def test_binning_bit_exact(capi, atom):
+    P = oracle_cycle(make_prm(atom=atom, bc="Homogeneous"), 0)
+    lo, h = base_cells(P)
+    g = capi.Gmg()
+    ptr, idx = g.bin_atoms(lo, h, P.pos, P.cutoff * P.r_c)
+    optr, oidx = P.lists0
+    assert np.array_equal(ptr, optr)
+    assert np.array_equal(idx, oidx)
+    g.close()
+
+
+def test_binning_random_atoms_and_empty_input(capi):
+    from oracle import rhs
+    from oracle.mesh import Forest
+    f = Forest(16, -1.0, 3.0)
+    rng = np.random.default_rng(5)
+    pos = rng.uniform(-0.5, 2.5, size=(40, 3))
+    lo, h = f.lo + f.ijk[0] * f.H, np.full(f.n_cells(0), f.H)
+    g = capi.Gmg()
+    ptr, idx = g.bin_atoms(lo, h, pos, 0.9)
+    optr, oidx = rhs.bin_atoms_bruteforce(f, pos, 0.9)
+    assert np.array_equal(ptr, optr) and np.array_equal(idx, oidx)
+    ptr, idx = g.bin_atoms(lo, h, np.zeros((0, 3)), 0.9)
+    assert ptr[-1] == 0 and len(idx) == 0
+    g.close()
+
+
+@pytest.fixture(scope="module")
+def P2():
+    """2-atom case at cycle 2: two levels, hanging nodes, Exact (inhomogeneous) boundary values, nq = 5."""
+    return oracle_cycle(make_prm(cycles=3, bc="Exact", atom="atom_n1_2.data", nq=4), 2)
+
+
+def _rhs_on_device(capi, P, use_lists=True):
+    from oracle import fe
+    lo, h, dofs, base = active_cell_arrays(P)
+    pts, wts = fe.tensor_rule(P.nq_rhs, 3)
+    g = capi.Gmg()
+    g.set_atoms(P.pos, P.charges)
+    if use_lists:
+        g.set_atom_lists(*P.lists0)
+    rho = g.charge_density(lo, h, base if use_lists else -np.ones(len(h), dtype=np.int32), pts, P.r_c)
+    d = P.dofs
+    n = d.n
+    order = np.argsort(d.hang_rows, kind="stable")
+    hptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(hptr, d.hang_rows + 1, 1)
+    hptr = np.cumsum(hptr)
+    ghat = P.system.T @ P.g
+    b = g.assemble_rhs(None, h, dofs, fe.shape_values(pts, 3), wts, n, hptr, d.hang_cols[order], d.hang_vals[order],
+                       d.constrained, kref=fe.stiffness(1.0, 3), ghat=ghat)
+    g.close()
+    return rho, b
+
+
+def test_density_and_load_vector_with_lists(capi, P2):
+    rho, b = _rhs_on_device(capi, P2)
+    assert rel_l2(rho, np.concatenate(P2.dens)) < 1e-12
+    assert rel_l2(b, P2.b) < 1e-12
+    assert np.all(b[P2.dofs.constrained] == 0.0)
+
+
+def test_density_without_lists_sums_all_atoms(capi):
+    P = oracle_cycle(make_prm(atom="atom_n1_8.data", flag="false", left=0, right=1, vacuum=2), 0)
+    rho, b = _rhs_on_device(capi, P, use_lists=False)
+    assert rel_l2(rho, np.concatenate(P.dens)) < 1e-12
+    assert rel_l2(b, P.b) < 1e-12
+
+
+def test_point_values_energy_term(capi, P2, goldens):
+    from oracle import estimate
+    lev, idx, xi = estimate.locate(P2.forest, P2.dofs, P2.pos)
+    dofs = []
+    for a in range(len(P2.pos)):
+        l = lev[a]
+        pos = np.nonzero(P2.dofs.active_cells[l] == idx[a])[0][0]
+        dofs.append(P2.dofs.cell_dofs[l][pos])
+    g = capi.Gmg()
+    phi = g.point_values(np.array(dofs), xi, P2.u)
+    g.close()
+    fe_energy = float((0.5 * P2.charges * phi).sum())
+    gold = goldens["gaussian_charges_mpirun1"][0]["cycles"][2]
+    assert abs(fe_energy - gold["energy_fe"]) < 1e-9
