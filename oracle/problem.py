@@ -51,6 +51,7 @@ class LaplaceProblem:
         self.verbose = verbose
         self.lines = []
         self.records = []
+        self.flag_history = []
         self.out("Problem type is:   " + self.problem)
         self.out("Preconditioner :    " + self.precond)
         self.out("Rhs assembly optimization ENABLED" if self.flag_rhs else "Without rhs assembly optimization")
@@ -204,6 +205,8 @@ class LaplaceProblem:
                 break
             eta = estimate.kelly_plus_residual(self.forest, self.dofs, self.u, self.dens, self.nq_rhs)
             rec["threshold"], self.flags = estimate.mark(self.forest, self.dofs, eta)
+            self.eta = eta
+            self.flag_history.append([f.copy() for f in self.flags])
             rec["n_flagged"] = int(sum(f.sum() for f in self.flags))
             self.out("Threshold value for refinement:\t%.10e" % rec["threshold"])
             if self.lammps and len(self.charges) < energy_gate:

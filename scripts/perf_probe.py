@@ -1,0 +1,57 @@
+"""Developer probe (not the bench): time level-0 SpMV and the persistent coarse CG on an n-atom lattice
+level-0 operator built by the oracle.  python scripts/perf_probe.py 20"""
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
+from helpers import pkg
+from oracle.mesh import Forest
+from oracle.dofs import DoFs
+from oracle import assemble
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+reps = 2 * (2 * n + 20)
+t = time.time()
+f = Forest(reps, -5.0, n + 5.0)
+d = DoFs(f)
+ops = assemble.LevelOps(f, d)
+A = ops.A_stored[0]
+print("assembled", A.shape, A.nnz, "in %.1fs" % (time.time() - t), flush=True)
+capi = pkg().capi
+g = capi.Gmg()
+g.set_num_levels(1)
+g.set_matrix(capi.GMG_SYSTEM, 0, A)
+g.set_matrix(capi.GMG_LEVEL, 0, A)
+g.set_copy_indices(0, np.arange(A.shape[0]), np.arange(A.shape[0]))
+for drop in (-1.0, 0.0):
+    g.set_drop_tolerance(drop)
+    t = time.time(); g.setup(); print("setup %.2fs" % (time.time() - t))
+    tr = g.matrix_traffic(capi.GMG_LEVEL, 0)
+    print("drop", drop, tr)
+    N = A.shape[0]
+    rng = np.random.default_rng(0)
+    x = g.vec_alloc(N); y = g.vec_alloc(N)
+    g.vec_upload(x, rng.standard_normal(N))
+    for _ in range(5): g.spmv_dev(capi.GMG_LEVEL, 0, x, y)
+    g.synchronize(); t = time.time()
+    R = 50
+    for _ in range(R): g.spmv_dev(capi.GMG_LEVEL, 0, x, y)
+    g.synchronize(); dt = (time.time() - t) / R
+    print("spmv %.3f ms  %.0f GB/s (CSR-equivalent algorithmic bytes)" % (dt * 1e3, tr["spmv_bytes"] / dt / 1e9))
+    b = rng.standard_normal(N); b[d.level_boundary[0]] = 0
+    g.vec_upload(x, b)
+    g.coarse_profile(True)
+    for rep in range(3):
+        it, res = g.cg_solve_dev(capi.GMG_LEVEL, 0, x, y, 300, 1e-30) if False else (None, None)
+    try:
+        it, res = g.cg_solve_dev(capi.GMG_LEVEL, 0, x, y, 200, 1e-300)
+    except capi.NoConvergence:
+        pass
+    try:
+        g.cg_solve_dev(capi.GMG_LEVEL, 0, x, y, 200, 1e-300)
+    except capi.NoConvergence:
+        pass
+    p = g.coarse_profile(True)
+    per = p["ms"] / p["iterations"]
+    print("cg: %d its in %.2f ms -> %.4f ms/it, %.0f GB/s algorithmic" % (p["iterations"], p["ms"], per, tr["cg_iter_bytes"] / per / 1e6))
+    g.vec_free(x); g.vec_free(y)

@@ -1,0 +1,73 @@
+"""GPU end-to-end tests of the drop-in: the C++ `LaplaceProblem` (host) + CUDA library reproduce the
+reference's golden stdout, cycle by cycle, like the reference's own regression tests."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, make_prm
+from helpers import pkg
+import hostlib
+from test_oracle_goldens import check_cycle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_atoms_six_cycles_reproduce_reference_golden(goldens):
+    """tests/gaussian-charges.cc: all printed numbers of all 6 adaptive cycles (SSOR = lexicographic,
+    level-scheduled on the device; iteration counts 1,6,7,6,7,7)."""
+    gold = goldens["gaussian_charges_mpirun1"][0]
+    text, recs = hostlib.run_problem(make_prm(cycles=6, bc="Exact", atom="atom_n1_2.data", nq=4))
+    assert len(recs) == 6
+    for rec, g in zip(recs, gold["cycles"]):
+        check_cycle(rec, g)
+    assert recs[0]["coarse_its"] == [112]
+    assert "Threshold value for refinement:\t4.4445997238e+00" in text
+    assert "   Starting value 0.9219052997" in text
+    assert "   CG converged in 6 iterations." in text
+
+
+@pytest.mark.parametrize("smoother,expected", [("Jacobi", None), ("MulticolourSSOR", None), ("Chebyshev", None)])
+def test_other_smoothers_same_solution(goldens, smoother, expected):
+    gold = goldens["gaussian_charges_mpirun1"][0]["cycles"]
+    extra = f"subsection Solver input data\n set Smoother = {smoother}\nend\n"
+    _, recs = hostlib.run_problem(make_prm(cycles=3, bc="Exact", atom="atom_n1_2.data", nq=4, extra=extra))
+    for rec, g in zip(recs, gold):
+        # the mesh sequence, rhs and matrices do not depend on the smoother; the solution agrees to the CG tolerance
+        assert rec["n_dofs_level"] == g["n_dofs_level"]
+        assert abs(rec["rhs_l2"] - g["rhs_l2"]) < 1e-9
+        assert abs(rec["sol_l2"] - g["sol_l2"]) < 1e-6 * g["sol_l2"]
+        assert abs(rec["its"] - g["its"]) <= 3
+        assert abs(rec["threshold"] - g["threshold"]) < 1e-6 * g["threshold"]
+
+
+def test_main_executable_lattice_8_atoms(tmp_path, goldens):
+    """`main file.prm` on atom_n1_8 (configs[0]): cycle 0 of the cluster log, 2 cycles run."""
+    prm = tmp_path / "gaussian-charges.prm"
+    prm.write_text(make_prm(cycles=2, atom=os.path.join(GOLDEN, "atom_n1_8.data")))
+    exe = os.path.join(os.path.dirname(pkg().capi.LIB_PATH), "main")
+    out = subprocess.run([exe, str(prm)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    g = goldens["cluster_ssor_run"][0]["cycles"]
+    assert "Number of atoms: 8" in out.stdout
+    m = re.findall(r"Starting value (\S+)", out.stdout)
+    assert abs(float(m[0]) - g[0]["start"]) < 1e-6
+    its = [int(x) for x in re.findall(r"CG converged in (\d+) iterations", out.stdout)]
+    assert its[0] == 1 and abs(its[1] - g[1]["its"]) <= 2  # 20-rank block SSOR in the log: +-2
+    cells = [int(x) for x in re.findall(r"Number of active cells:\s+(\d+)", out.stdout)]
+    assert cells == [g[0]["n_active_cells"], g[1]["n_active_cells"]]
+    dofs = re.findall(r"Number of degrees of freedom: (\d+)", out.stdout)
+    assert int(dofs[1]) == g[1]["n_dofs"]
+    l2 = [float(x) for x in re.findall(r"L2 solution norm (\S+)", out.stdout)]
+    assert abs(l2[0] - g[0]["sol_l2"]) < 1e-9 and abs(l2[1] - g[1]["sol_l2"]) < 1e-7 * g[1]["sol_l2"]
+
+
+def test_missing_parameter_file_and_bad_device_fail_loudly(tmp_path):
+    exe = os.path.join(os.path.dirname(pkg().capi.LIB_PATH), "main")
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode != 0 and "Invalid inputs" in out.stderr
+    extra = "subsection Solver input data\n set GPU device = 99\nend\n"
+    with pytest.raises(hostlib.HostError, match="no CPU fallback"):
+        hostlib.run_problem(make_prm(cycles=1, extra=extra))
