@@ -5,5 +5,5 @@ Layout: `csrc/` hand-written sm_100a CUDA kernels + the C ABI (`include/gmg_b200
 `host/` the C++ host side mirroring `Step50::LaplaceProblem`, `capi.py` the ctypes binding used by
 tests and bench.  No CPU fallback: everything here needs the compiled library and a B200.
 """
-from . import capi  # noqa: F401
+from . import capi, hostapi, lattice  # noqa: F401
 from .capi import Gmg, GmgError, NoConvergence, load_library  # noqa: F401

@@ -51,6 +51,8 @@ SIGNATURES = {
     "gmg_vec_free": (_i, [_h, C.c_void_p]),
     "gmg_vec_upload": (_i, [_h, C.c_void_p, _pd, _i64]),
     "gmg_vec_download": (_i, [_h, _pd, C.c_void_p, _i64]),
+    "gmg_vec_copy_dev": (_i, [_h, C.c_void_p, C.c_void_p, _i64]),
+    "gmg_transfer_bytes": (_i, [_h, _i, _pi64, _pi64]),
     "gmg_pcg_solve_dev": (_i, [_h, C.c_void_p, C.c_void_p, _i, _d, C.POINTER(_i), _pd, _pd]),
     "gmg_vcycle_apply_dev": (_i, [_h, C.c_void_p, C.c_void_p]),
     "gmg_spmv_dev": (_i, [_h, _i, _i, C.c_void_p, C.c_void_p]),
@@ -269,6 +271,11 @@ class Gmg:
         ms, n, it = _d(0), _i64(0), _i64(0)
         self._ck(self.lib.gmg_coarse_profile(self.h, int(reset), C.byref(ms), C.byref(n), C.byref(it)))
         return dict(ms=ms.value, launches=n.value, iterations=it.value)
+
+    def transfer_bytes(self, reset=True):
+        a, b = _i64(0), _i64(0)
+        self._ck(self.lib.gmg_transfer_bytes(self.h, int(reset), C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def launch_count(self):
         return int(self.lib.gmg_launch_count(self.h))

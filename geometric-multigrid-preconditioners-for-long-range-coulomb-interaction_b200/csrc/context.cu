@@ -61,9 +61,9 @@ static int upload_csr(gmg_context *h, int n_rows, int n_cols, const int64_t *row
   GMG_CUDA(h, dalloc(&out.rowptr, n_rows + 1));
   GMG_CUDA(h, dalloc(&out.col, out.nnz));
   GMG_CUDA(h, dalloc(&out.val, out.nnz));
-  GMG_CUDA(h, cudaMemcpyAsync(out.rowptr, rowptr, sizeof(int64_t) * (n_rows + 1), cudaMemcpyHostToDevice, h->stream));
-  GMG_CUDA(h, cudaMemcpyAsync(out.col, col, sizeof(int) * out.nnz, cudaMemcpyHostToDevice, h->stream));
-  GMG_CUDA(h, cudaMemcpyAsync(out.val, val, sizeof(double) * out.nnz, cudaMemcpyHostToDevice, h->stream));
+  GMG_CUDA(h, gmg::copy(h, out.rowptr, rowptr, sizeof(int64_t) * (n_rows + 1), cudaMemcpyHostToDevice));
+  GMG_CUDA(h, gmg::copy(h, out.col, col, sizeof(int) * out.nnz, cudaMemcpyHostToDevice));
+  GMG_CUDA(h, gmg::copy(h, out.val, val, sizeof(double) * out.nnz, cudaMemcpyHostToDevice));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));  // the host buffers are only borrowed
   return GMG_OK;
 }
@@ -85,8 +85,8 @@ static int build_sell(gmg_context *h, const DevCsr &c, double drop_tol, Sell &ou
     GMG_LAUNCH_CHECK(h);
   }
   std::vector<int> hw(n_slices), hn(c.n_rows);
-  GMG_CUDA(h, cudaMemcpyAsync(hw.data(), width, sizeof(int) * n_slices, cudaMemcpyDeviceToHost, h->stream));
-  GMG_CUDA(h, cudaMemcpyAsync(hn.data(), row_nnz, sizeof(int) * c.n_rows, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, gmg::copy(h, hw.data(), width, sizeof(int) * n_slices, cudaMemcpyDeviceToHost));
+  GMG_CUDA(h, gmg::copy(h, hn.data(), row_nnz, sizeof(int) * c.n_rows, cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   std::vector<int64_t> sp(n_slices + 1, 0);
   int maxw = 0;
@@ -100,8 +100,7 @@ static int build_sell(gmg_context *h, const DevCsr &c, double drop_tol, Sell &ou
   GMG_CUDA(h, dalloc(&out.slice_ptr, n_slices + 1));
   GMG_CUDA(h, dalloc(&out.val, out.padded));
   GMG_CUDA(h, dalloc(&out.col, out.padded));
-  GMG_CUDA(h, cudaMemcpyAsync(out.slice_ptr, sp.data(), sizeof(int64_t) * (n_slices + 1), cudaMemcpyHostToDevice,
-                              h->stream));
+  GMG_CUDA(h, gmg::copy(h, out.slice_ptr, sp.data(), sizeof(int64_t) * (n_slices + 1), cudaMemcpyHostToDevice));
   if (n_slices > 0) {
     csr_to_sell<<<cdiv((int64_t)n_slices * 32, 256), 256, 0, h->stream>>>(c.n_rows, c.n_cols, c.rowptr, c.col, c.val,
                                                                           drop_tol, out.slice_ptr, out.val, out.col);
@@ -248,7 +247,7 @@ static int build_colorset(gmg_context *h, const HostCsr &a, const std::vector<in
   int rc = build_sell_host(h, sub, -1.0, cs.A);
   if (rc) return rc;
   GMG_CUDA(h, dalloc(&cs.rows, cs.n));
-  GMG_CUDA(h, cudaMemcpy(cs.rows, rows.data(), sizeof(int) * cs.n, cudaMemcpyHostToDevice));
+  GMG_CUDA(h, gmg::copy_sync(h, cs.rows, rows.data(), sizeof(int) * cs.n, cudaMemcpyHostToDevice));
   return GMG_OK;
 }
 
@@ -317,7 +316,7 @@ static int collect_profile(gmg_context *h) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev_begin[i], h->ev_end[i]);
     CgResult r;
-    cudaMemcpy(&r, h->cg_results + h->ev_result_slot[i], sizeof(CgResult), cudaMemcpyDeviceToHost);
+    gmg::copy_sync(h, &r, h->cg_results + h->ev_result_slot[i], sizeof(CgResult), cudaMemcpyDeviceToHost);
     h->prof_ms += ms;
     h->prof_launches++;
     h->prof_iters += r.iterations;
@@ -379,7 +378,7 @@ static int smooth(gmg_context *h, Level &L, double *&u, const double *rhs, bool 
     if (zero_start) {
       vec_scale_dinv<<<cdiv(n, 256), 256, 0, h->stream>>>(n, 1.0 / theta, L.dinv, rhs, u);
       GMG_LAUNCH_CHECK(h);
-      GMG_CUDA(h, cudaMemcpyAsync(L.t, u, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));  // increment
+      GMG_CUDA(h, gmg::copy(h, L.t, u, sizeof(double) * n, cudaMemcpyDeviceToDevice));  // increment
     } else {
       int rc = spmv<EPI_RESID, DOT_NONE>(h, L.A, u, L.tmp, rhs);
       if (rc) return rc;
@@ -464,7 +463,7 @@ static int pcg(gmg_context *h, int precond, double jac_omega, const double *b, d
   auto check_coarse = [&]() -> int {
     if (precond != PRECOND_GMG || h->cg_cursor == 0) return GMG_OK;
     CgResult r;
-    GMG_CUDA(h, cudaMemcpy(&r, h->cg_results + ((h->cg_cursor - 1) % h->cg_ring), sizeof(r), cudaMemcpyDeviceToHost));
+    GMG_CUDA(h, gmg::copy_sync(h, &r, h->cg_results + ((h->cg_cursor - 1) % h->cg_ring), sizeof(r), cudaMemcpyDeviceToHost));
     if (r.status != 0)
       return fail(h, GMG_ENOCONVERGENCE, "coarse-grid CG: Iterative method reported convergence failure in step " +
                                              std::to_string(r.iterations) + ". The residual in the last step was " +
@@ -474,7 +473,7 @@ static int pcg(gmg_context *h, int precond, double jac_omega, const double *b, d
   const int rg = reduce_grid(h, n);
   // g = A x - b ; res = ||g||
   if (int rc = spmv<EPI_NRESID, DOT_YY>(h, h->S, x, h->g, b, nullptr, 0.0, &h->scalars->res2)) return rc;
-  GMG_CUDA(h, cudaMemcpyAsync(&hs, h->scalars, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, gmg::copy(h, &hs, h->scalars, sizeof(hs), cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   double res = std::sqrt(hs.res2);
   *res0_out = res;
@@ -491,7 +490,7 @@ static int pcg(gmg_context *h, int precond, double jac_omega, const double *b, d
     if (int rc = spmv<EPI_ASSIGN, DOT_XY>(h, h->S, h->d, h->hh, nullptr, nullptr, 0.0, &h->scalars->dh)) return rc;
     pcg_update<<<rg, 256, 0, h->stream>>>(n, x, h->g, h->d, h->hh, h->scalars, slot, h->partials, h->counter);
     GMG_LAUNCH_CHECK(h);
-    GMG_CUDA(h, cudaMemcpyAsync(&hs, h->scalars, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
+    GMG_CUDA(h, gmg::copy(h, &hs, h->scalars, sizeof(hs), cudaMemcpyDeviceToHost));
     GMG_CUDA(h, cudaStreamSynchronize(h->stream));
     if (int rc = check_coarse()) return rc;
     res = std::sqrt(hs.res2);
@@ -516,7 +515,7 @@ static int fetch_coarse_its(gmg_context *h) {
   const int n = std::min(h->cg_cursor - h->cg_solve_begin, h->cg_ring);
   for (int i = h->cg_cursor - n; i < h->cg_cursor; ++i) {
     CgResult r;
-    GMG_CUDA(h, cudaMemcpy(&r, h->cg_results + (i % h->cg_ring), sizeof(r), cudaMemcpyDeviceToHost));
+    GMG_CUDA(h, gmg::copy_sync(h, &r, h->cg_results + (i % h->cg_ring), sizeof(r), cudaMemcpyDeviceToHost));
     h->last_coarse_its.push_back(r.iterations);
   }
   return GMG_OK;
@@ -680,8 +679,8 @@ int gmg_set_copy_indices(gmg_handle h, int level, int32_t n, const int32_t *gi, 
   L.n_copy = n;
   GMG_CUDA(h, dalloc(&L.copy_g, n));
   GMG_CUDA(h, dalloc(&L.copy_l, n));
-  GMG_CUDA(h, cudaMemcpy(L.copy_g, gi, sizeof(int) * n, cudaMemcpyHostToDevice));
-  GMG_CUDA(h, cudaMemcpy(L.copy_l, li, sizeof(int) * n, cudaMemcpyHostToDevice));
+  GMG_CUDA(h, gmg::copy_sync(h, L.copy_g, gi, sizeof(int) * n, cudaMemcpyHostToDevice));
+  GMG_CUDA(h, gmg::copy_sync(h, L.copy_l, li, sizeof(int) * n, cudaMemcpyHostToDevice));
   return GMG_OK;
 }
 
@@ -848,9 +847,9 @@ int gmg_pcg_solve_dev(gmg_handle h, const double *b, double *x, int max_it, doub
 static int with_host_vectors(gmg_handle h, int64_t n_in, const double *in, int64_t n_out, double *inout,
                              bool upload_inout) {
   if (int rc = ensure_stage(h, std::max(n_in, n_out))) return rc;
-  if (in) GMG_CUDA(h, cudaMemcpyAsync(h->stage_a, in, sizeof(double) * n_in, cudaMemcpyHostToDevice, h->stream));
+  if (in) GMG_CUDA(h, gmg::copy(h, h->stage_a, in, sizeof(double) * n_in, cudaMemcpyHostToDevice));
   if (upload_inout)
-    GMG_CUDA(h, cudaMemcpyAsync(h->stage_b, inout, sizeof(double) * n_out, cudaMemcpyHostToDevice, h->stream));
+    GMG_CUDA(h, gmg::copy(h, h->stage_b, inout, sizeof(double) * n_out, cudaMemcpyHostToDevice));
   return GMG_OK;
 }
 
@@ -861,7 +860,7 @@ int gmg_pcg_solve(gmg_handle h, const double *b, double *x, int max_it, double a
   const int n = h->n_sys;
   if (int rc = with_host_vectors(h, n, b, n, x, true)) return rc;
   int rc = gmg_pcg_solve_dev(h, h->stage_a, h->stage_b, max_it, abs_tol, iters, res0, res_final);
-  GMG_CUDA(h, cudaMemcpyAsync(x, h->stage_b, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, gmg::copy(h, x, h->stage_b, sizeof(double) * n, cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return rc;
 }
@@ -878,7 +877,7 @@ int gmg_pcg_solve_jacobi(gmg_handle h, const double *b, double *x, double omega,
   if (iters) *iters = it;
   if (res0) *res0 = r0;
   if (res_final) *res_final = r1;
-  GMG_CUDA(h, cudaMemcpyAsync(x, h->stage_b, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, gmg::copy(h, x, h->stage_b, sizeof(double) * n, cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return rc;
 }
@@ -897,7 +896,7 @@ int gmg_vcycle_apply(gmg_handle h, const double *src, double *dst) {
   if (int rc = with_host_vectors(h, n, src, n, dst, false)) return rc;
   int rc = gmg_vcycle_apply_dev(h, h->stage_a, h->stage_b);
   if (rc) return rc;
-  GMG_CUDA(h, cudaMemcpyAsync(dst, h->stage_b, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, gmg::copy(h, dst, h->stage_b, sizeof(double) * n, cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return fetch_coarse_its(h);
 }
@@ -917,7 +916,7 @@ int gmg_spmv(gmg_handle h, int which, int level, const double *x, double *y) {
   if (!A) return fail(h, GMG_EINVAL, "matrix not available (set + gmg_setup first)");
   if (int rc = with_host_vectors(h, A->v.n_cols, x, A->v.n_rows, y, false)) return rc;
   if (int rc = spmv<EPI_ASSIGN, DOT_NONE>(h, *A, h->stage_a, h->stage_b)) return rc;
-  GMG_CUDA(h, cudaMemcpyAsync(y, h->stage_b, sizeof(double) * A->v.n_rows, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, gmg::copy(h, y, h->stage_b, sizeof(double) * A->v.n_rows, cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return GMG_OK;
 }
@@ -930,8 +929,7 @@ int gmg_cg_solve_dev(gmg_handle h, int which, int level, const double *b, double
   if (!A || A->v.n_rows != A->v.n_cols) return fail(h, GMG_EINVAL, "square matrix not available");
   if (int rc = coarse_cg(h, *A, b, x, max_it, abs_tol)) return rc;
   CgResult r;
-  GMG_CUDA(h, cudaMemcpyAsync(&r, h->cg_results + ((h->cg_cursor - 1) % h->cg_ring), sizeof(r), cudaMemcpyDeviceToHost,
-                              h->stream));
+  GMG_CUDA(h, gmg::copy(h, &r, h->cg_results + ((h->cg_cursor - 1) % h->cg_ring), sizeof(r), cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   if (iters) *iters = r.iterations;
   if (res_final) *res_final = r.res;
@@ -948,7 +946,7 @@ int gmg_cg_solve(gmg_handle h, int which, int level, const double *b, double *x,
   const int n = A->v.n_rows;
   if (int rc = with_host_vectors(h, n, b, n, x, false)) return rc;
   int rc = gmg_cg_solve_dev(h, which, level, h->stage_a, h->stage_b, max_it, abs_tol, iters, res_final);
-  GMG_CUDA(h, cudaMemcpyAsync(x, h->stage_b, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, gmg::copy(h, x, h->stage_b, sizeof(double) * n, cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return rc;
 }
@@ -958,10 +956,10 @@ int gmg_smooth(gmg_handle h, int level, const double *rhs, double *u, int zero_s
   cudaSetDevice(h->device);
   Level &L = h->levels[level];
   const int n = L.n;
-  GMG_CUDA(h, cudaMemcpyAsync(L.defect, rhs, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
-  GMG_CUDA(h, cudaMemcpyAsync(L.sol, u, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  GMG_CUDA(h, gmg::copy(h, L.defect, rhs, sizeof(double) * n, cudaMemcpyHostToDevice));
+  GMG_CUDA(h, gmg::copy(h, L.sol, u, sizeof(double) * n, cudaMemcpyHostToDevice));
   if (int rc = smooth(h, L, L.sol, L.defect, zero_start != 0)) return rc;
-  GMG_CUDA(h, cudaMemcpyAsync(u, L.sol, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, gmg::copy(h, u, L.sol, sizeof(double) * n, cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return GMG_OK;
 }
@@ -982,11 +980,9 @@ int gmg_matrix_norms(gmg_handle h, int which, int level, double out[3]) {
   vec_max_partials<<<g2, 256, 0, h->stream>>>(nc, h->stage_a, h->partials + 2 * h->partials_cap);
   GMG_LAUNCH_CHECK(h);
   std::vector<double> rowmax(grid), frob(grid), colmax(g2);
-  GMG_CUDA(h, cudaMemcpyAsync(rowmax.data(), h->partials, sizeof(double) * grid, cudaMemcpyDeviceToHost, h->stream));
-  GMG_CUDA(h, cudaMemcpyAsync(frob.data(), h->partials + h->partials_cap, sizeof(double) * grid, cudaMemcpyDeviceToHost,
-                              h->stream));
-  GMG_CUDA(h, cudaMemcpyAsync(colmax.data(), h->partials + 2 * h->partials_cap, sizeof(double) * g2,
-                              cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, gmg::copy(h, rowmax.data(), h->partials, sizeof(double) * grid, cudaMemcpyDeviceToHost));
+  GMG_CUDA(h, gmg::copy(h, frob.data(), h->partials + h->partials_cap, sizeof(double) * grid, cudaMemcpyDeviceToHost));
+  GMG_CUDA(h, gmg::copy(h, colmax.data(), h->partials + 2 * h->partials_cap, sizeof(double) * g2, cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   out[0] = *std::max_element(colmax.begin(), colmax.end());
   out[1] = *std::max_element(rowmax.begin(), rowmax.end());
@@ -1000,17 +996,15 @@ int gmg_vector_norms(gmg_handle h, int64_t n, const double *v, double out[3]) {
   if (!h || !v || !out || n < 0) return GMG_EINVAL;
   cudaSetDevice(h->device);
   if (int rc = ensure_stage(h, n)) return rc;
-  GMG_CUDA(h, cudaMemcpyAsync(h->stage_a, v, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  GMG_CUDA(h, gmg::copy(h, h->stage_a, v, sizeof(double) * n, cudaMemcpyHostToDevice));
   const int grid = std::min(cdiv(std::max<int64_t>(n, 1), 256 * 4), h->partials_cap);
   vec_norm_partials<<<grid, 256, 0, h->stream>>>(n, h->stage_a, h->partials, h->partials + h->partials_cap,
                                                  h->partials + 2 * h->partials_cap);
   GMG_LAUNCH_CHECK(h);
   std::vector<double> a(grid), b(grid), c(grid);
-  GMG_CUDA(h, cudaMemcpyAsync(a.data(), h->partials, sizeof(double) * grid, cudaMemcpyDeviceToHost, h->stream));
-  GMG_CUDA(h, cudaMemcpyAsync(b.data(), h->partials + h->partials_cap, sizeof(double) * grid, cudaMemcpyDeviceToHost,
-                              h->stream));
-  GMG_CUDA(h, cudaMemcpyAsync(c.data(), h->partials + 2 * h->partials_cap, sizeof(double) * grid, cudaMemcpyDeviceToHost,
-                              h->stream));
+  GMG_CUDA(h, gmg::copy(h, a.data(), h->partials, sizeof(double) * grid, cudaMemcpyDeviceToHost));
+  GMG_CUDA(h, gmg::copy(h, b.data(), h->partials + h->partials_cap, sizeof(double) * grid, cudaMemcpyDeviceToHost));
+  GMG_CUDA(h, gmg::copy(h, c.data(), h->partials + 2 * h->partials_cap, sizeof(double) * grid, cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   double s1 = 0, s2 = 0, m = 0;
   for (int i = 0; i < grid; ++i) {
@@ -1048,15 +1042,30 @@ int gmg_vec_free(gmg_handle h, double *dev) {
 int gmg_vec_upload(gmg_handle h, double *dev, const double *host, int64_t n) {
   if (!h) return GMG_EINVAL;
   cudaSetDevice(h->device);
-  GMG_CUDA(h, cudaMemcpyAsync(dev, host, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  GMG_CUDA(h, gmg::copy(h, dev, host, sizeof(double) * n, cudaMemcpyHostToDevice));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return GMG_OK;
 }
 int gmg_vec_download(gmg_handle h, double *host, const double *dev, int64_t n) {
   if (!h) return GMG_EINVAL;
   cudaSetDevice(h->device);
-  GMG_CUDA(h, cudaMemcpyAsync(host, dev, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, gmg::copy(h, host, dev, sizeof(double) * n, cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return GMG_OK;
+}
+
+int gmg_vec_copy_dev(gmg_handle h, double *dst, const double *src, int64_t n) {
+  if (!h) return GMG_EINVAL;
+  cudaSetDevice(h->device);
+  GMG_CUDA(h, gmg::copy(h, dst, src, sizeof(double) * n, cudaMemcpyDeviceToDevice));
+  return GMG_OK;
+}
+
+int gmg_transfer_bytes(gmg_handle h, int reset, int64_t *h2d, int64_t *d2h) {
+  if (!h) return GMG_EINVAL;
+  if (h2d) *h2d = h->h2d_bytes;
+  if (d2h) *d2h = h->d2h_bytes;
+  if (reset) h->h2d_bytes = h->d2h_bytes = 0;
   return GMG_OK;
 }
 

@@ -66,6 +66,7 @@ struct gmg_context {
   bool own_stream = false;
   std::string err;
   int64_t launches = 0;
+  int64_t h2d_bytes = 0, d2h_bytes = 0;  // host<->device traffic of the host-pointer entry points
 
   int n_levels = 0;
   std::vector<gmg::Level> levels;
@@ -119,6 +120,15 @@ namespace gmg {
 int fail(gmg_context *h, int code, const std::string &msg);
 int ensure_stage(gmg_context *h, int64_t n);
 void rhs_free(gmg_context *h);
+inline cudaError_t copy(gmg_context *h, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+  if (kind == cudaMemcpyHostToDevice) h->h2d_bytes += (int64_t)bytes;
+  if (kind == cudaMemcpyDeviceToHost) h->d2h_bytes += (int64_t)bytes;
+  return cudaMemcpyAsync(dst, src, bytes, kind, h->stream);
+}
+inline cudaError_t copy_sync(gmg_context *h, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+  cudaError_t e = copy(h, dst, src, bytes, kind);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(h->stream);
+}
 }  // namespace gmg
 
 #define GMG_CUDA(h, expr)                                                                          \

@@ -43,7 +43,7 @@ template <class T>
 int upload(gmg_context *h, T *&dst, const T *src, int64_t n) {
   dfree(dst);
   GMG_CUDA(h, dalloc(&dst, n));
-  if (n > 0) GMG_CUDA(h, cudaMemcpyAsync(dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, h->stream));
+  if (n > 0) GMG_CUDA(h, gmg::copy(h, dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
   return GMG_OK;
 }
 
@@ -328,9 +328,9 @@ int gmg_bin_atoms(gmg_handle h, int32_t n_cells, const double *cell_lo, const do
   if (atoms_out != nullptr && state(h)->bin_pending && h->n_lists == n_cells && h->list_ptr && h->list_atoms) {
     state(h)->bin_pending = false;
     // second call of the two-call protocol: hand out the lists computed by the first
-    GMG_CUDA(h, cudaMemcpy(rowptr_out, h->list_ptr, sizeof(int64_t) * (n_cells + 1), cudaMemcpyDeviceToHost));
+    GMG_CUDA(h, gmg::copy_sync(h, rowptr_out, h->list_ptr, sizeof(int64_t) * (n_cells + 1), cudaMemcpyDeviceToHost));
     if (rowptr_out[n_cells] > 0)
-      GMG_CUDA(h, cudaMemcpy(atoms_out, h->list_atoms, sizeof(int) * rowptr_out[n_cells], cudaMemcpyDeviceToHost));
+      GMG_CUDA(h, gmg::copy_sync(h, atoms_out, h->list_atoms, sizeof(int) * rowptr_out[n_cells], cudaMemcpyDeviceToHost));
     return GMG_OK;
   }
   // hash grid over the atoms' bounding box, about one atom per hash cell
@@ -387,9 +387,9 @@ int gmg_bin_atoms(gmg_handle h, int32_t n_cells, const double *cell_lo, const do
   TRY(dalloc(&d_start, nh + 1));
   TRY(dalloc(&d_sorted, n_atoms));
   TRY(dalloc(&d_rowptr, (int64_t)n_cells + 1));
-  TRY(cudaMemcpyAsync(d_pos, pos, sizeof(double) * 3 * n_atoms, cudaMemcpyHostToDevice, h->stream));
-  TRY(cudaMemcpyAsync(d_lo, cell_lo, sizeof(double) * 3 * n_cells, cudaMemcpyHostToDevice, h->stream));
-  TRY(cudaMemcpyAsync(d_h, cell_h, sizeof(double) * n_cells, cudaMemcpyHostToDevice, h->stream));
+  TRY(gmg::copy(h, d_pos, pos, sizeof(double) * 3 * n_atoms, cudaMemcpyHostToDevice));
+  TRY(gmg::copy(h, d_lo, cell_lo, sizeof(double) * 3 * n_cells, cudaMemcpyHostToDevice));
+  TRY(gmg::copy(h, d_h, cell_h, sizeof(double) * n_cells, cudaMemcpyHostToDevice));
   TRY(cudaMemsetAsync(d_count, 0, sizeof(int) * (nh + 1), h->stream));
   if (n_atoms > 0) {
     hash_count<<<cdiv(n_atoms, 256), 256, 0, h->stream>>>(n_atoms, d_pos, g, d_cell_of_atom, d_count);
@@ -397,10 +397,10 @@ int gmg_bin_atoms(gmg_handle h, int32_t n_cells, const double *cell_lo, const do
   }
   // exclusive scan of the (small) hash histogram on the host
   std::vector<int> cnt(nh + 1), start(nh + 1, 0);
-  TRY(cudaMemcpyAsync(cnt.data(), d_count, sizeof(int) * (nh + 1), cudaMemcpyDeviceToHost, h->stream));
+  TRY(gmg::copy(h, cnt.data(), d_count, sizeof(int) * (nh + 1), cudaMemcpyDeviceToHost));
   TRY(cudaStreamSynchronize(h->stream));
   for (int i = 0; i < nh; ++i) start[i + 1] = start[i] + cnt[i];
-  TRY(cudaMemcpyAsync(d_start, start.data(), sizeof(int) * (nh + 1), cudaMemcpyHostToDevice, h->stream));
+  TRY(gmg::copy(h, d_start, start.data(), sizeof(int) * (nh + 1), cudaMemcpyHostToDevice));
   TRY(cudaMemsetAsync(d_count, 0, sizeof(int) * (nh + 1), h->stream));
   if (n_atoms > 0) {
     hash_fill<<<cdiv(n_atoms, 256), 256, 0, h->stream>>>(n_atoms, d_cell_of_atom, d_start, d_count, d_sorted);
@@ -414,11 +414,11 @@ int gmg_bin_atoms(gmg_handle h, int32_t n_cells, const double *cell_lo, const do
     h->launches++;
   }
   std::vector<int64_t> rp(n_cells + 1);
-  TRY(cudaMemcpyAsync(rp.data(), d_rowptr, sizeof(int64_t) * (n_cells + 1), cudaMemcpyDeviceToHost, h->stream));
+  TRY(gmg::copy(h, rp.data(), d_rowptr, sizeof(int64_t) * (n_cells + 1), cudaMemcpyDeviceToHost));
   TRY(cudaStreamSynchronize(h->stream));
   for (int c = 0; c < n_cells; ++c) rp[c + 1] += rp[c];
   const int64_t n_pairs = rp[n_cells];
-  TRY(cudaMemcpyAsync(d_rowptr, rp.data(), sizeof(int64_t) * (n_cells + 1), cudaMemcpyHostToDevice, h->stream));
+  TRY(gmg::copy(h, d_rowptr, rp.data(), sizeof(int64_t) * (n_cells + 1), cudaMemcpyHostToDevice));
   TRY(dalloc(&d_atoms, n_pairs));
   TRY(dalloc(&d_atoms_sorted, n_pairs));
   if (n_cells > 0 && n_pairs > 0) {
@@ -447,7 +447,7 @@ int gmg_bin_atoms(gmg_handle h, int32_t n_cells, const double *cell_lo, const do
   std::copy(rp.begin(), rp.end(), rowptr_out);
   state(h)->bin_pending = (atoms_out == nullptr);
   if (atoms_out && n_pairs > 0)
-    GMG_CUDA(h, cudaMemcpy(atoms_out, h->list_atoms, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost));
+    GMG_CUDA(h, gmg::copy_sync(h, atoms_out, h->list_atoms, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost));
   return rc;
 }
 
@@ -468,8 +468,7 @@ int gmg_charge_density(gmg_handle h, int32_t n_cells, const double *cell_lo, con
   GMG_CUDA(h, dalloc(&s->rho, (int64_t)n_cells * n_q));
   if (int rc = run_density(h, s)) return rc;
   if (rho_out)
-    GMG_CUDA(h, cudaMemcpyAsync(rho_out, s->rho, sizeof(double) * (int64_t)n_cells * n_q, cudaMemcpyDeviceToHost,
-                                h->stream));
+    GMG_CUDA(h, gmg::copy(h, rho_out, s->rho, sizeof(double) * (int64_t)n_cells * n_q, cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return GMG_OK;
 }
@@ -504,14 +503,13 @@ int gmg_assemble_rhs(gmg_handle h, int32_t n_cells, const double *rho, const dou
   const double *rho_dev = s->rho;
   if (rho != nullptr) {
     if (int rc = ensure_stage(h, std::max<int64_t>((int64_t)n_cells * n_q, n_dofs))) return rc;
-    GMG_CUDA(h, cudaMemcpyAsync(h->stage_a, rho, sizeof(double) * (int64_t)n_cells * n_q, cudaMemcpyHostToDevice,
-                                h->stream));
+    GMG_CUDA(h, gmg::copy(h, h->stage_a, rho, sizeof(double) * (int64_t)n_cells * n_q, cudaMemcpyHostToDevice));
     rho_dev = h->stage_a;
   } else if (int rc = ensure_stage(h, n_dofs)) {
     return rc;
   }
   if (int rc = run_load_vector(h, s, rho_dev, h->stage_b)) return rc;
-  GMG_CUDA(h, cudaMemcpyAsync(b_out, h->stage_b, sizeof(double) * n_dofs, cudaMemcpyDeviceToHost, h->stream));
+  GMG_CUDA(h, gmg::copy(h, b_out, h->stage_b, sizeof(double) * n_dofs, cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return GMG_OK;
 }
@@ -539,7 +537,7 @@ int gmg_point_values(gmg_handle h, int32_t n_points, const int32_t *cell_dofs, c
       point_values_kernel<<<cdiv(n_points, 128), 128, 0, h->stream>>>(n_points, d_dofs, d_xi, d_u, d_out);
       h->launches++;
     }
-    cudaMemcpyAsync(phi_out, d_out, sizeof(double) * n_points, cudaMemcpyDeviceToHost, h->stream);
+    gmg::copy(h, phi_out, d_out, sizeof(double) * n_points, cudaMemcpyDeviceToHost);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, GMG_ECUDA, "point values failed");
   } else if (rc == GMG_OK) {
     rc = fail(h, GMG_ECUDA, "allocation failed");

@@ -643,7 +643,7 @@ inline double normal_derivative(const double U[NV], double h, int a, double s, d
 }  // namespace
 
 std::vector<std::vector<float>> error_indicator(const Forest &f, const DoFs &d, const std::vector<double> &u,
-                                                const std::vector<double> &rho, int nq) {
+                                                const std::vector<double> &rho, int nq, bool residual_term) {
   const int nl = f.n_levels();
   std::vector<double> gp2, gw2, gp, gw;
   gauss_unit(2, gp2, gw2);
@@ -708,7 +708,7 @@ std::vector<std::vector<float>> error_indicator(const Forest &f, const DoFs &d, 
       for (int face = 0; face < 6; ++face) err = (float)((double)err + FI[l][p][face] * diam);
       const float kelly = (float)std::sqrt((double)err);
       double resid = 0.0;
-      const double *r = rho.empty() ? nullptr : &rho[off * nq3];
+      const double *r = (rho.empty() || !residual_term) ? nullptr : &rho[off * nq3];
       if (r)
         for (int qz = 0, q = 0; qz < nq; ++qz)
           for (int qy = 0; qy < nq; ++qy)

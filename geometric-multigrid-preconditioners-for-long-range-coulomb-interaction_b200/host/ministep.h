@@ -110,7 +110,8 @@ void distribute(const DoFs &d, const std::vector<double> &g, std::vector<double>
 
 // Kelly(cell_diameter) + h_K^2 * int (4 pi rho)^2, Vector<float> storage (src/step-50.cc:1020-1090)
 std::vector<std::vector<float>> error_indicator(const Forest &f, const DoFs &d, const std::vector<double> &u,
-                                                const std::vector<double> &rho /*active cells x nq^3*/, int nq);
+                                                const std::vector<double> &rho /*active cells x nq^3*/, int nq,
+                                                bool residual_term = true);
 // threshold = 0.6 max eta; flags where eta >= threshold (GridRefinement::refine, :1084-1089)
 double mark_cells(const Forest &f, const DoFs &d, const std::vector<std::vector<float>> &eta,
                   std::vector<std::vector<char>> &flags);

@@ -52,6 +52,9 @@ void ParameterReader::declare_parameters() {
   prm.declare_entry("Output time summary table", "true", Patterns::Bool(),
                     "Set flag for whether to output the time summary");
   // new, B200 path only (defaults keep the reference's behaviour)
+  prm.declare_entry("Refinement indicator", "KellyAndResidual", Patterns::Selection("KellyAndResidual | Kelly"),
+                    "KellyAndResidual = the shipped source (src/step-50.cc:1040-1081); Kelly = the older build that "
+                    "produced the cluster logs (marks with the Kelly estimator alone)");
   prm.declare_entry("Energy postprocessing atom limit", "300", Patterns::Integer(),
                     "postprocess_electrostatic_energy runs only below this atom count (reference: 300)");
   prm.leave_subsection();
@@ -141,6 +144,7 @@ LaplaceProblem<dim>::LaplaceProblem(
     prm.leave_subsection();
     prm.enter_subsection("Misc");
     energy_atom_limit = (unsigned int)prm.get_integer("Energy postprocessing atom limit");
+    indicator_with_residual = prm.get("Refinement indicator") == "KellyAndResidual";
     prm.leave_subsection();
   } catch (const ExcParameter &) {
     prm.leave_subsection();
@@ -345,7 +349,14 @@ void LaplaceProblem<dim>::assemble_system() {
   if (Problemtype == "Step16")
     coef = [](double x, double y, double z) { return (x * x + y * y + z * z < 0.5 * 0.5) ? 5.0 : 1.0; };
   system_matrix = assemble_system_matrix(f, d, coef);
+  assemble_rhs_on_device();
+}
 
+// load vector + constraints on the device (the RHS part of assemble_system, src/step-50.cc:798-828)
+template <int dim>
+void LaplaceProblem<dim>::assemble_rhs_on_device() {
+  const Forest &f = *triangulation;
+  const DoFs &d = *mg_dof_handler;
   const auto t0 = std::chrono::steady_clock::now();
   const int nq = (int)(degree + quadrature_degree_rhs), nq3 = nq * nq * nq;
   std::vector<double> gp, gw;
@@ -491,7 +502,8 @@ template <int dim>
 void LaplaceProblem<dim>::estimate_error_and_mark_cells() {
   TimerOutput::Scope t(computing_timer, "Estimate error and mark cells");
   const int nq = (int)(degree + quadrature_degree_rhs);
-  error_per_cell = error_indicator(*triangulation, *mg_dof_handler, distributed_solution, density_values, nq);
+  error_per_cell = error_indicator(*triangulation, *mg_dof_handler, distributed_solution, density_values, nq,
+                                   indicator_with_residual);
   const double threshold = mark_cells(*triangulation, *mg_dof_handler, error_per_cell, refine_flags);
   *pcout << "Threshold value for refinement:\t" << threshold << std::endl;
   if (rec) {
@@ -630,7 +642,7 @@ void LaplaceProblem<dim>::postprocess_error_in_energy_norm() {
 
 // =============================================================================== run (src/step-50.cc:1463-1573)
 template <int dim>
-void LaplaceProblem<dim>::run() {
+void LaplaceProblem<dim>::begin_run() {
   std::ostream &out = *pcout;
   out << "Problem type is:   " << Problemtype << std::endl;
   out << "Preconditioner :    " << PreconditionerType << std::endl;
@@ -643,47 +655,69 @@ void LaplaceProblem<dim>::run() {
   if (gmg_create(gpu_device, &gmg) != GMG_OK)
     throw ExcMessage("gmg_create failed: no B200 (sm_100) CUDA device; this path has no CPU fallback.");
   computing_timer.reset();
-  const auto t_total = std::chrono::steady_clock::now();
+  run_start = std::chrono::steady_clock::now();
   out << "Dimension:\t" << dim << std::endl;
   read_lammps_input_file(LammpsInputFilename);
   if (lammpsinput)
     gmg_check(gmg_set_atoms(gmg, (int)number_of_atoms, atom_positions.data(), charges.data()), "gmg_set_atoms");
   cycle_records.clear();
   cycle_records.reserve(number_of_adaptive_refinement_cycles);
-  for (unsigned int cycle = 0; cycle < number_of_adaptive_refinement_cycles; ++cycle) {
-    cycle_records.emplace_back();
-    rec = &cycle_records.back();
-    out << "Cycle " << cycle << ':' << std::endl;
-    if (cycle == 0)
-      make_mesh();
-    else
-      refine_grid(cycle);
-    rec->n_active_cells = (long)triangulation->n_active_cells();
-    out << "   Number of active cells:       " << rec->n_active_cells << std::endl;
-    if (cycle == 0) setup_system(cycle);
-    rec->n_dofs = mg_dof_handler->n;
-    out << "   Number of degrees of freedom: " << mg_dof_handler->n << " (by level: ";
-    for (int level = 0; level < triangulation->n_levels(); ++level) {
-      rec->n_dofs_level.push_back(mg_dof_handler->level_n[level]);
-      out << mg_dof_handler->level_n[level] << (level == triangulation->n_levels() - 1 ? ")" : ", ");
-    }
-    out << std::endl;
-    assemble_system();
-    if (PreconditionerType == "GMG") assemble_multigrid();
-    solve();
-    estimate_error_and_mark_cells();
-    output_results(cycle);
-    if (lammpsinput && number_of_atoms < energy_atom_limit) {
-      postprocess_electrostatic_energy();
-      postprocess_error_in_energy_norm();
-    }
+}
+
+template <int dim>
+void LaplaceProblem<dim>::cycle_until_solve(const unsigned int cycle) {
+  std::ostream &out = *pcout;
+  cycle_records.emplace_back();
+  rec = &cycle_records.back();
+  out << "Cycle " << cycle << ':' << std::endl;
+  if (cycle == 0)
+    make_mesh();
+  else
+    refine_grid(cycle);
+  rec->n_active_cells = (long)triangulation->n_active_cells();
+  out << "   Number of active cells:       " << rec->n_active_cells << std::endl;
+  if (cycle == 0) setup_system(cycle);
+  rec->n_dofs = mg_dof_handler->n;
+  out << "   Number of degrees of freedom: " << mg_dof_handler->n << " (by level: ";
+  for (int level = 0; level < triangulation->n_levels(); ++level) {
+    rec->n_dofs_level.push_back(mg_dof_handler->level_n[level]);
+    out << mg_dof_handler->level_n[level] << (level == triangulation->n_levels() - 1 ? ")" : ", ");
   }
+  out << std::endl;
+  assemble_system();
+  if (PreconditionerType == "GMG") assemble_multigrid();
+}
+
+template <int dim>
+void LaplaceProblem<dim>::cycle_after_solve(const unsigned int cycle) {
+  estimate_error_and_mark_cells();
+  output_results(cycle);
+  if (lammpsinput && number_of_atoms < energy_atom_limit) {
+    postprocess_electrostatic_energy();
+    postprocess_error_in_energy_norm();
+  }
+}
+
+template <int dim>
+void LaplaceProblem<dim>::end_run() {
+  std::ostream &out = *pcout;
   rec = nullptr;
   if (flag_output_time) computing_timer.print_summary(out);
   if (flag_output_time)
     out << "   \nTotal Elapsed wall time for solution: "
-        << std::chrono::duration<double>(std::chrono::steady_clock::now() - t_total).count() << " seconds.\n"
+        << std::chrono::duration<double>(std::chrono::steady_clock::now() - run_start).count() << " seconds.\n"
         << std::endl;
+}
+
+template <int dim>
+void LaplaceProblem<dim>::run() {
+  begin_run();
+  for (unsigned int cycle = 0; cycle < number_of_adaptive_refinement_cycles; ++cycle) {
+    cycle_until_solve(cycle);
+    solve();
+    cycle_after_solve(cycle);
+  }
+  end_run();
 }
 
 template class LaplaceProblem<2>;

@@ -92,6 +92,7 @@ class LaplaceProblem {
   // B200-path extras (not in the reference): where stdout goes, what the cycles produced
   void set_output(std::ostream &os) { pcout = &os; }
   const std::vector<CycleRecord> &records() const { return cycle_records; }
+  gmg_handle device() const { return gmg; }
 
  protected:
   void setup_system(const unsigned int &cycle);
@@ -110,6 +111,12 @@ class LaplaceProblem {
   double long_ranged_potential(const double p[3], const double atom[3], const double &charge) const;
   double short_ranged_potential(const double p[3], const double atom[3], const double &charge) const;
   void make_mesh();
+  // run() = begin_run(); for every cycle { cycle_until_solve; solve; cycle_after_solve }; end_run()
+  void begin_run();
+  void cycle_until_solve(const unsigned int cycle);
+  void cycle_after_solve(const unsigned int cycle);
+  void end_run();
+  void assemble_rhs_on_device();
   void hand_over_hierarchy();
   void boundary_values();
 
@@ -137,6 +144,7 @@ class LaplaceProblem {
   int smoothing_steps = 2;
   int gpu_device = 0;
   unsigned int energy_atom_limit = 300;
+  bool indicator_with_residual = true;  // false: Kelly part only (the build behind the cluster logs)
 
   std::unique_ptr<ministep::Forest> triangulation;
   std::unique_ptr<ministep::DoFs> mg_dof_handler;
@@ -149,6 +157,7 @@ class LaplaceProblem {
   std::vector<std::vector<float>> error_per_cell;
   std::vector<std::vector<char>> refine_flags;
   gmg_handle gmg = nullptr;
+  std::chrono::steady_clock::time_point run_start;
   std::vector<CycleRecord> cycle_records;
   CycleRecord *rec = nullptr;
   void gmg_check(int rc, const char *what);

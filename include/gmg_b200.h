@@ -110,6 +110,9 @@ int gmg_vec_alloc(gmg_handle h, int64_t n, double **dev_out);
 int gmg_vec_free(gmg_handle h, double *dev);
 int gmg_vec_upload(gmg_handle h, double *dev, const double *host, int64_t n);
 int gmg_vec_download(gmg_handle h, double *host, const double *dev, int64_t n);
+int gmg_vec_copy_dev(gmg_handle h, double *dst_dev, const double *src_dev, int64_t n);
+/* bytes moved host->device / device->host by the host-pointer entry points since the last reset */
+int gmg_transfer_bytes(gmg_handle h, int reset, int64_t *h2d, int64_t *d2h);
 int gmg_pcg_solve_dev(gmg_handle h, const double *b_dev, double *x_dev, int max_it, double abs_tol,
                       int *iters, double *res0, double *res_final);
 int gmg_vcycle_apply_dev(gmg_handle h, const double *src_dev, double *dst_dev);

@@ -30,7 +30,7 @@ def _normal_derivative(U, h, a, side_pts, VO):
     return out
 
 
-def kelly_plus_residual(forest, dofs, u, dens, nq_rhs):
+def kelly_plus_residual(forest, dofs, u, dens, nq_rhs, residual_term=True):
     """Per-level float32 indicators eta_K on active cells (u: solution after constraints.distribute)."""
     dim, VO = forest.dim, forest.VO
     fpts, fw = fe.tensor_rule(2, dim - 1)  # QGauss<dim-1>(degree+1)
@@ -93,6 +93,8 @@ def kelly_plus_residual(forest, dofs, u, dens, nq_rhs):
         kelly = np.sqrt(err.astype(np.float64)).astype(np.float32)
         jxw = wq * h ** dim
         res = (((4.0 * math.pi * dens[l]) ** 2) * jxw).sum(1) if len(err) else np.zeros(0)
+        if not residual_term:  # the build that produced the cluster logs marked with the Kelly part only
+            res = res * 0.0
         eta.append(np.sqrt(kelly.astype(np.float64) ** 2 + diam ** 2 * res).astype(np.float32))
     return eta
 

@@ -28,7 +28,8 @@ def gaussian_rhs_function(xq, r_c):
 
 class LaplaceProblem:
     def __init__(self, params, smoother="ssor", omega=0.5, smoothing_steps=2, ssor_ranks=1, verbose=False,
-                 base_dir=None):
+                 base_dir=None, indicator="kelly+residual"):
+        self.indicator = indicator
         p = self.p = params
         g = lambda s, k: p[(s, k)]
         self.dim = g("Problem Selection", "Dimension")
@@ -203,7 +204,8 @@ class LaplaceProblem:
             last = cycle == self.n_cycles - 1
             if last and stop_after_solve_of_last_cycle:
                 break
-            eta = estimate.kelly_plus_residual(self.forest, self.dofs, self.u, self.dens, self.nq_rhs)
+            eta = estimate.kelly_plus_residual(self.forest, self.dofs, self.u, self.dens, self.nq_rhs,
+                                               residual_term=self.indicator == "kelly+residual")
             rec["threshold"], self.flags = estimate.mark(self.forest, self.dofs, eta)
             self.eta = eta
             self.flag_history.append([f.copy() for f in self.flags])
