@@ -18,16 +18,7 @@ int fail(gmg_context *h, int code, const std::string &msg) {
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-// ------------------------------------------------------------------------------ memory helpers
-template <class T>
-static cudaError_t dalloc(T **p, int64_t n) {
-  return cudaMalloc((void **)p, (size_t)std::max<int64_t>(n, 1) * sizeof(T));
-}
-template <class T>
-static void dfree(T *&p) {
-  if (p) cudaFree(p);
-  p = nullptr;
-}
+thread_local cudaStream_t tl_stream = nullptr;
 
 static void free_sell(Sell &s) {
   dfree(s.slice_ptr);
@@ -76,6 +67,7 @@ static int upload_host_csr(gmg_context *h, const HostCsr &m, DevCsr &out) {
 static int build_sell(gmg_context *h, const DevCsr &c, double drop_tol, Sell &out) {
   free_sell(out);
   const int n_slices = cdiv(c.n_rows, SLICE);
+  TraceScope trb("        build_sell");
   int *width = nullptr, *row_nnz = nullptr;
   GMG_CUDA(h, dalloc(&width, n_slices));
   GMG_CUDA(h, dalloc(&row_nnz, c.n_rows));
@@ -554,6 +546,14 @@ int gmg_create(int device, gmg_handle *out) {
     return GMG_ENODEVICE;
   }
   h->own_stream = true;
+  gmg::enter(h);
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   h->partials_cap = 1 << 16;
   bool ok = dalloc(&h->partials, 3 * h->partials_cap) == cudaSuccess && dalloc(&h->counter, 4) == cudaSuccess &&
             dalloc(&h->scalars, 1) == cudaSuccess && dalloc(&h->cg_results, h->cg_ring) == cudaSuccess;
@@ -583,7 +583,7 @@ int gmg_create(int device, gmg_handle *out) {
 
 int gmg_destroy(gmg_handle h) {
   if (!h) return GMG_OK;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   cudaDeviceSynchronize();
   for (auto &L : h->levels) free_level(L);
   free_csr(h->rawS);
@@ -607,6 +607,7 @@ int gmg_destroy(gmg_handle h) {
   dfree(h->list_ptr);
   dfree(h->list_atoms);
   rhs_free(h);
+  cudaStreamSynchronize(h->stream);
   for (auto e : h->ev_begin) cudaEventDestroy(e);
   for (auto e : h->ev_end) cudaEventDestroy(e);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -646,7 +647,8 @@ int gmg_set_matrix(gmg_handle h, int which, int level, int32_t n_rows, int32_t n
                    const int32_t *col, const double *val) {
   if (!h || !rowptr || n_rows < 0 || n_cols < 0) return GMG_EINVAL;
   if (rowptr[n_rows] > 0 && (!col || !val)) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  TraceScope tr("gmg_set_matrix");
+  gmg::enter(h);
   h->is_setup = false;
   if (which == GMG_SYSTEM) {
     h->n_sys = n_rows;
@@ -672,7 +674,7 @@ int gmg_set_matrix(gmg_handle h, int which, int level, int32_t n_rows, int32_t n
 
 int gmg_set_copy_indices(gmg_handle h, int level, int32_t n, const int32_t *gi, const int32_t *li) {
   if (!h || level < 0 || level >= h->n_levels || n < 0) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   Level &L = h->levels[level];
   dfree(L.copy_g);
   dfree(L.copy_l);
@@ -709,9 +711,11 @@ int gmg_set_drop_tolerance(gmg_handle h, double drop_tol) {
 
 int gmg_setup(gmg_handle h) {
   if (!h) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
+  TraceScope tr_all("gmg_setup total");
   int rc;
   if (h->rawS.rowptr) {
+    TraceScope tr("  system -> sell");
     if ((rc = build_sell(h, h->rawS, h->drop_tol, h->S))) return rc;
     free_csr(h->rawS);
     dfree(h->s_dinv);
@@ -730,7 +734,9 @@ int gmg_setup(gmg_handle h) {
   int cg_n = 0;
   for (int l = 0; l < h->n_levels; ++l) {
     Level &L = h->levels[l];
+    TraceScope tr_l("  level total");
     if (L.rawA.rowptr) {
+      TraceScope tr("    A -> sell");
       if ((rc = build_sell(h, L.rawA, h->drop_tol, L.A))) return rc;
       free_csr(L.rawA);
       dfree(L.dinv);
@@ -741,6 +747,7 @@ int gmg_setup(gmg_handle h) {
       }
     }
     if (!L.A.valid) return fail(h, GMG_EINVAL, "level matrix missing on level " + std::to_string(l));
+    TraceScope trv("    vectors");
     for (double **p : {&L.defect, &L.sol, &L.t, &L.tmp}) {
       dfree(*p);
       GMG_CUDA(h, dalloc(p, L.n));
@@ -749,8 +756,12 @@ int gmg_setup(gmg_handle h) {
     if (l == 0) cg_n = L.n;
     if (l >= 1) {
       if (L.hA.empty()) return fail(h, GMG_EINVAL, "host copy of level matrix missing");
-      HostCsr ai = add(L.hA, L.hI);
-      if ((rc = build_sell_host(h, ai, h->drop_tol, L.AI))) return rc;
+      {
+        TraceScope tr("    A+I");
+        HostCsr ai = add(L.hA, L.hI);
+        if ((rc = build_sell_host(h, ai, h->drop_tol, L.AI))) return rc;
+      }
+      TraceScope tr_s("    I^T, colours / wavefronts");
       free_sell(L.IT);
       if (!L.hI.empty() && L.hI.nnz() > 0) {
         HostCsr it = transpose(L.hI);
@@ -806,8 +817,17 @@ int gmg_setup(gmg_handle h) {
       }
     }
     if (!L.hP.empty()) {
-      if ((rc = build_sell_host(h, L.hP, 0.0, L.P))) return rc;
-      HostCsr r = transpose(L.hP);
+      TraceScope trp("    P, R");
+      {
+        TraceScope t1("      P -> sell");
+        if ((rc = build_sell_host(h, L.hP, 0.0, L.P))) return rc;
+      }
+      HostCsr r;
+      {
+        TraceScope t2("      transpose");
+        r = transpose(L.hP);
+      }
+      TraceScope t3("      R -> sell");
       if ((rc = build_sell_host(h, r, 0.0, L.R))) return rc;
     } else if (l + 1 < h->n_levels) {
       return fail(h, GMG_EINVAL, "prolongation from level " + std::to_string(l) + " missing");
@@ -833,7 +853,7 @@ int gmg_setup(gmg_handle h) {
 int gmg_pcg_solve_dev(gmg_handle h, const double *b, double *x, int max_it, double abs_tol, int *iters, double *res0,
                       double *res_final) {
   if (!h || !h->is_setup || !h->S.valid || h->n_levels < 1) return h ? fail(h, GMG_EINVAL, "not set up") : GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   int it = 0;
   double r0 = 0, r1 = 0;
   int rc = pcg(h, PRECOND_GMG, 0.0, b, x, max_it, abs_tol, &it, &r0, &r1);
@@ -856,7 +876,7 @@ static int with_host_vectors(gmg_handle h, int64_t n_in, const double *in, int64
 int gmg_pcg_solve(gmg_handle h, const double *b, double *x, int max_it, double abs_tol, int *iters, double *res0,
                   double *res_final) {
   if (!h || !b || !x) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   const int n = h->n_sys;
   if (int rc = with_host_vectors(h, n, b, n, x, true)) return rc;
   int rc = gmg_pcg_solve_dev(h, h->stage_a, h->stage_b, max_it, abs_tol, iters, res0, res_final);
@@ -868,7 +888,7 @@ int gmg_pcg_solve(gmg_handle h, const double *b, double *x, int max_it, double a
 int gmg_pcg_solve_jacobi(gmg_handle h, const double *b, double *x, double omega, int max_it, double abs_tol, int *iters,
                          double *res0, double *res_final) {
   if (!h || !b || !x || !h->S.valid) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   const int n = h->n_sys;
   if (int rc = with_host_vectors(h, n, b, n, x, true)) return rc;
   int it = 0;
@@ -884,14 +904,14 @@ int gmg_pcg_solve_jacobi(gmg_handle h, const double *b, double *x, double omega,
 
 int gmg_vcycle_apply_dev(gmg_handle h, const double *src, double *dst) {
   if (!h || !h->is_setup) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   h->cg_solve_begin = h->cg_cursor;
   return vcycle(h, src, dst);
 }
 
 int gmg_vcycle_apply(gmg_handle h, const double *src, double *dst) {
   if (!h || !src || !dst) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   const int n = h->n_sys;
   if (int rc = with_host_vectors(h, n, src, n, dst, false)) return rc;
   int rc = gmg_vcycle_apply_dev(h, h->stage_a, h->stage_b);
@@ -903,7 +923,7 @@ int gmg_vcycle_apply(gmg_handle h, const double *src, double *dst) {
 
 int gmg_spmv_dev(gmg_handle h, int which, int level, const double *x, double *y) {
   if (!h) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   Sell *A = pick(h, which, level);
   if (!A) return fail(h, GMG_EINVAL, "matrix not available (set + gmg_setup first)");
   return spmv<EPI_ASSIGN, DOT_NONE>(h, *A, x, y);
@@ -911,7 +931,7 @@ int gmg_spmv_dev(gmg_handle h, int which, int level, const double *x, double *y)
 
 int gmg_spmv(gmg_handle h, int which, int level, const double *x, double *y) {
   if (!h || !x || !y) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   Sell *A = pick(h, which, level);
   if (!A) return fail(h, GMG_EINVAL, "matrix not available (set + gmg_setup first)");
   if (int rc = with_host_vectors(h, A->v.n_cols, x, A->v.n_rows, y, false)) return rc;
@@ -924,7 +944,7 @@ int gmg_spmv(gmg_handle h, int which, int level, const double *x, double *y) {
 int gmg_cg_solve_dev(gmg_handle h, int which, int level, const double *b, double *x, int max_it, double abs_tol,
                      int *iters, double *res_final) {
   if (!h) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   Sell *A = pick(h, which, level);
   if (!A || A->v.n_rows != A->v.n_cols) return fail(h, GMG_EINVAL, "square matrix not available");
   if (int rc = coarse_cg(h, *A, b, x, max_it, abs_tol)) return rc;
@@ -940,7 +960,7 @@ int gmg_cg_solve_dev(gmg_handle h, int which, int level, const double *b, double
 int gmg_cg_solve(gmg_handle h, int which, int level, const double *b, double *x, int max_it, double abs_tol, int *iters,
                  double *res_final) {
   if (!h || !b || !x) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   Sell *A = pick(h, which, level);
   if (!A) return fail(h, GMG_EINVAL, "matrix not available");
   const int n = A->v.n_rows;
@@ -953,7 +973,7 @@ int gmg_cg_solve(gmg_handle h, int which, int level, const double *b, double *x,
 
 int gmg_smooth(gmg_handle h, int level, const double *rhs, double *u, int zero_start) {
   if (!h || !h->is_setup || level < 1 || level >= h->n_levels || !rhs || !u) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   Level &L = h->levels[level];
   const int n = L.n;
   GMG_CUDA(h, gmg::copy(h, L.defect, rhs, sizeof(double) * n, cudaMemcpyHostToDevice));
@@ -966,7 +986,7 @@ int gmg_smooth(gmg_handle h, int level, const double *rhs, double *u, int zero_s
 
 int gmg_matrix_norms(gmg_handle h, int which, int level, double out[3]) {
   if (!h || !out) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   Sell *A = pick(h, which, level);
   if (!A) return fail(h, GMG_EINVAL, "matrix not available");
   const int n = A->v.n_rows, nc = A->v.n_cols;
@@ -994,7 +1014,7 @@ int gmg_matrix_norms(gmg_handle h, int which, int level, double out[3]) {
 
 int gmg_vector_norms(gmg_handle h, int64_t n, const double *v, double out[3]) {
   if (!h || !v || !out || n < 0) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   if (int rc = ensure_stage(h, n)) return rc;
   GMG_CUDA(h, gmg::copy(h, h->stage_a, v, sizeof(double) * n, cudaMemcpyHostToDevice));
   const int grid = std::min(cdiv(std::max<int64_t>(n, 1), 256 * 4), h->partials_cap);
@@ -1028,27 +1048,27 @@ int gmg_last_coarse_iterations(gmg_handle h, int32_t *out, int cap, int *n_out) 
 
 int gmg_vec_alloc(gmg_handle h, int64_t n, double **dev_out) {
   if (!h || !dev_out) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   GMG_CUDA(h, dalloc(dev_out, n));
   GMG_CUDA(h, cudaMemset(*dev_out, 0, sizeof(double) * std::max<int64_t>(n, 1)));
   return GMG_OK;
 }
 int gmg_vec_free(gmg_handle h, double *dev) {
   if (!h) return GMG_EINVAL;
-  cudaSetDevice(h->device);
-  cudaFree(dev);
+  gmg::enter(h);
+  dfree(dev);
   return GMG_OK;
 }
 int gmg_vec_upload(gmg_handle h, double *dev, const double *host, int64_t n) {
   if (!h) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   GMG_CUDA(h, gmg::copy(h, dev, host, sizeof(double) * n, cudaMemcpyHostToDevice));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return GMG_OK;
 }
 int gmg_vec_download(gmg_handle h, double *host, const double *dev, int64_t n) {
   if (!h) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   GMG_CUDA(h, gmg::copy(h, host, dev, sizeof(double) * n, cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return GMG_OK;
@@ -1056,7 +1076,7 @@ int gmg_vec_download(gmg_handle h, double *host, const double *dev, int64_t n) {
 
 int gmg_vec_copy_dev(gmg_handle h, double *dst, const double *src, int64_t n) {
   if (!h) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   GMG_CUDA(h, gmg::copy(h, dst, src, sizeof(double) * n, cudaMemcpyDeviceToDevice));
   return GMG_OK;
 }
@@ -1082,7 +1102,7 @@ int gmg_matrix_traffic(gmg_handle h, int which, int level, double out[3]) {
 
 int gmg_coarse_profile(gmg_handle h, int reset, double *ms, int64_t *launches, int64_t *iters) {
   if (!h) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   if (int rc = collect_profile(h)) return rc;
   if (ms) *ms = h->prof_ms;
   if (launches) *launches = h->prof_launches;

@@ -2,6 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -117,6 +120,22 @@ struct gmg_context {
 };
 
 namespace gmg {
+// Stream-ordered allocation from the device's memory pool (release threshold = never): cudaMalloc / cudaFree
+// cost milliseconds each and a hierarchy hand-over does hundreds of them.
+extern thread_local cudaStream_t tl_stream;
+inline void enter(gmg_context *h) {
+  cudaSetDevice(h->device);
+  tl_stream = h->stream;
+}
+template <class T>
+inline cudaError_t dalloc(T **p, int64_t n) {
+  return cudaMallocAsync((void **)p, (size_t)(n > 0 ? n : 1) * sizeof(T), tl_stream);
+}
+template <class T>
+inline void dfree(T *&p) {
+  if (p) cudaFreeAsync(p, tl_stream);
+  p = nullptr;
+}
 int fail(gmg_context *h, int code, const std::string &msg);
 int ensure_stage(gmg_context *h, int64_t n);
 void rhs_free(gmg_context *h);
@@ -130,6 +149,21 @@ inline cudaError_t copy_sync(gmg_context *h, void *dst, const void *src, size_t 
   return e != cudaSuccess ? e : cudaStreamSynchronize(h->stream);
 }
 }  // namespace gmg
+
+// GMG_TRACE=1: wall-clock of the set-up phases on stderr
+struct TraceScope {
+  const char *name;
+  std::chrono::steady_clock::time_point t0;
+  bool on;
+  explicit TraceScope(const char *n) : name(n), t0(std::chrono::steady_clock::now()), on(std::getenv("GMG_TRACE") != nullptr) {}
+  ~TraceScope() {
+    if (on) {
+      cudaDeviceSynchronize();
+      std::fprintf(stderr, "[gmg trace] %-28s %9.3f ms\n", name,
+                   1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+  }
+};
 
 #define GMG_CUDA(h, expr)                                                                          \
   do {                                                                                             \

@@ -31,15 +31,6 @@ namespace {
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 template <class T>
-cudaError_t dalloc(T **p, int64_t n) {
-  return cudaMalloc((void **)p, (size_t)std::max<int64_t>(n, 1) * sizeof(T));
-}
-template <class T>
-void dfree(T *&p) {
-  if (p) cudaFree(p);
-  p = nullptr;
-}
-template <class T>
 int upload(gmg_context *h, T *&dst, const T *src, int64_t n) {
   dfree(dst);
   GMG_CUDA(h, dalloc(&dst, n));
@@ -303,7 +294,7 @@ extern "C" {
 
 int gmg_set_atoms(gmg_handle h, int32_t n_atoms, const double *pos, const double *charge) {
   if (!h || n_atoms < 0 || (n_atoms && (!pos || !charge))) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   h->n_atoms = n_atoms;
   if (int rc = upload(h, h->atom_pos, pos, 3 * (int64_t)n_atoms)) return rc;
   if (int rc = upload(h, h->atom_q, charge, n_atoms)) return rc;
@@ -313,7 +304,7 @@ int gmg_set_atoms(gmg_handle h, int32_t n_atoms, const double *pos, const double
 
 int gmg_set_atom_lists(gmg_handle h, int32_t n_lists, const int64_t *rowptr, const int32_t *atoms) {
   if (!h || n_lists < 0 || !rowptr) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   h->n_lists = n_lists;
   if (int rc = upload(h, h->list_ptr, rowptr, (int64_t)n_lists + 1)) return rc;
   if (int rc = upload(h, h->list_atoms, atoms, rowptr[n_lists])) return rc;
@@ -324,7 +315,7 @@ int gmg_set_atom_lists(gmg_handle h, int32_t n_lists, const int64_t *rowptr, con
 int gmg_bin_atoms(gmg_handle h, int32_t n_cells, const double *cell_lo, const double *cell_h, int32_t n_atoms,
                   const double *pos, double radius, int64_t *rowptr_out, int32_t *atoms_out) {
   if (!h || n_cells < 0 || n_atoms < 0 || !rowptr_out || radius <= 0.0) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   if (atoms_out != nullptr && state(h)->bin_pending && h->n_lists == n_cells && h->list_ptr && h->list_atoms) {
     state(h)->bin_pending = false;
     // second call of the two-call protocol: hand out the lists computed by the first
@@ -367,7 +358,7 @@ int gmg_bin_atoms(gmg_handle h, int32_t n_cells, const double *cell_lo, const do
   auto cleanup = [&]() {
     dfree(d_pos); dfree(d_lo); dfree(d_h); dfree(d_cell_of_atom); dfree(d_count); dfree(d_start); dfree(d_sorted);
     dfree(d_atoms);
-    if (d_temp) cudaFree(d_temp);
+    if (d_temp) cudaFreeAsync(d_temp, tl_stream);
   };
 #define TRY(expr)                                                                         \
   do {                                                                                    \
@@ -429,7 +420,7 @@ int gmg_bin_atoms(gmg_handle h, int32_t n_cells, const double *cell_lo, const do
     size_t temp_bytes = 0;
     TRY(cub::DeviceSegmentedSort::SortKeys(nullptr, temp_bytes, d_atoms, d_atoms_sorted, n_pairs, n_cells, d_rowptr,
                                            d_rowptr + 1, h->stream));
-    TRY(cudaMalloc(&d_temp, std::max<size_t>(temp_bytes, 1)));
+    TRY(cudaMallocAsync(&d_temp, std::max<size_t>(temp_bytes, 1), tl_stream));
     TRY(cub::DeviceSegmentedSort::SortKeys(d_temp, temp_bytes, d_atoms, d_atoms_sorted, n_pairs, n_cells, d_rowptr,
                                            d_rowptr + 1, h->stream));
     h->launches++;
@@ -455,7 +446,7 @@ int gmg_charge_density(gmg_handle h, int32_t n_cells, const double *cell_lo, con
                        const int32_t *list_of_cell, int32_t n_q, const double *qpoints, double r_c, double *rho_out) {
   if (!h || n_cells < 0 || n_q < 1 || !cell_lo || !cell_h || !list_of_cell || !qpoints) return GMG_EINVAL;
   if (!h->atom_pos) return fail(h, GMG_EINVAL, "gmg_set_atoms first");
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   RhsState *s = state(h);
   s->n_cells = n_cells;
   s->n_q = n_q;
@@ -479,7 +470,7 @@ int gmg_assemble_rhs(gmg_handle h, int32_t n_cells, const double *rho, const dou
                      const uint8_t *constrained, double *b_out) {
   if (!h || n_cells < 0 || !cell_h || !cell_dofs || !shape || !weights || !hang_rowptr || !constrained || !b_out)
     return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   RhsState *s = state(h);
   if (rho == nullptr && (s->rho == nullptr || s->n_cells != n_cells || s->n_q != n_q))
     return fail(h, GMG_EINVAL, "rho == NULL needs a matching gmg_charge_density call first");
@@ -516,7 +507,7 @@ int gmg_assemble_rhs(gmg_handle h, int32_t n_cells, const double *rho, const dou
 
 int gmg_rhs_step_dev(gmg_handle h, double *b_dev) {
   if (!h || !h->rhs || !b_dev) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   RhsState *s = h->rhs;
   if (s->n_cells != s->a_cells || s->n_q != s->a_nq) return fail(h, GMG_EINVAL, "density / load-vector inputs differ");
   if (int rc = run_density(h, s)) return rc;
@@ -526,13 +517,13 @@ int gmg_rhs_step_dev(gmg_handle h, double *b_dev) {
 int gmg_point_values(gmg_handle h, int32_t n_points, const int32_t *cell_dofs, const double *ref_coords, const double *u,
                      int32_t n_dofs, double *phi_out) {
   if (!h || n_points < 0 || !cell_dofs || !ref_coords || !u || !phi_out) return GMG_EINVAL;
-  cudaSetDevice(h->device);
+  gmg::enter(h);
   int *d_dofs = nullptr;
   double *d_xi = nullptr, *d_u = nullptr, *d_out = nullptr;
   int rc = GMG_OK;
   if ((rc = upload(h, d_dofs, cell_dofs, 8 * (int64_t)n_points)) == GMG_OK &&
       (rc = upload(h, d_xi, ref_coords, 3 * (int64_t)n_points)) == GMG_OK && (rc = upload(h, d_u, u, n_dofs)) == GMG_OK &&
-      cudaMalloc(&d_out, sizeof(double) * std::max(n_points, 1)) == cudaSuccess) {
+      dalloc(&d_out, n_points) == cudaSuccess) {
     if (n_points > 0) {
       point_values_kernel<<<cdiv(n_points, 128), 128, 0, h->stream>>>(n_points, d_dofs, d_xi, d_u, d_out);
       h->launches++;

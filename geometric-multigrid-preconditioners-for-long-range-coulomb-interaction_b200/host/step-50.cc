@@ -456,7 +456,11 @@ void LaplaceProblem<dim>::solve() {
   TimerOutput::Scope t(computing_timer, "Solve");
   const auto t0 = std::chrono::steady_clock::now();
   std::ostream &out = *pcout;
+  const bool trace = std::getenv("GMG_TRACE") != nullptr;
   hand_over_hierarchy();
+  if (trace)
+    std::fprintf(stderr, "[step50 trace] hand_over_hierarchy %.3f ms\n",
+                 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   double bn[3], mn[3], sn[3];
   gmg_check(gmg_vector_norms(gmg, (int64_t)system_rhs.size(), system_rhs.data(), bn), "gmg_vector_norms");
   gmg_check(gmg_matrix_norms(gmg, GMG_SYSTEM, 0, mn), "gmg_matrix_norms");
@@ -475,6 +479,9 @@ void LaplaceProblem<dim>::solve() {
   else
     rc = gmg_pcg_solve_jacobi(gmg, system_rhs.data(), solution.data(), 0.6, 500, tol, &its, &res0, &res);
   gmg_check(rc, "solver.solve");
+  if (trace)
+    std::fprintf(stderr, "[step50 trace] through pcg %.3f ms\n",
+                 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   gmg_check(gmg_vector_norms(gmg, (int64_t)solution.size(), solution.data(), sn), "gmg_vector_norms");
   out << "   Starting value " << std::fixed << res0 << std::endl;
   out << "   CG converged in " << its << " iterations." << std::endl;
