@@ -155,7 +155,16 @@ def run_b200(args):
     atom_file, pos, q = write_atoms(args)
     t0 = time.time()
     prm = P.lattice.cluster_prm(atom_file, args.atoms_n, cycles=args.cycles, smoother=args.smoother, device=local)
-    B = P.hostapi.BenchProblem(prm)
+    connect = None
+    if world > 1:
+        def connect(gmg):
+            def all_gather_bytes(b):
+                out = [None] * world
+                dist.all_gather_object(out, b)
+                return out
+            P.capi.connect_ranks(gmg, rank, world, all_gather_bytes)
+            dist.barrier()
+    B = P.hostapi.BenchProblem(prm, connect=connect)
     setup_s = time.time() - t0
     g = B.gmg
     stream = torch.cuda.Stream()
@@ -193,25 +202,35 @@ def run_b200(args):
     ms, outs, launches, prof = timed(B.step_device, args.steps)
     clocks = sampler.stop()
     its = [o[0] for o in outs]
-    dofs_total = B.n_dofs * args.steps * world
+    # N > 1: ONE problem row-partitioned over the GPUs (strong scaling): every rank times the same solve
+    dofs_total = B.n_dofs * args.steps
     value = dofs_total / (ms * 1e-3)
 
     # end to end through the host-buffer entry points (the LaplaceProblem methods themselves)
     e2e_steps = args.e2e_steps or max(2, min(args.steps, 5))
-    B.step_host(True)
+    full_e2e = world == 1  # N > 1: the hierarchy hand-over (partitioning) is set-up; rhs + solve go through host buffers
+    B.step_host(full_e2e)
     g.transfer_bytes(True)
-    ms_e, outs_e, _, _ = timed(lambda: B.step_host(True), e2e_steps)
+    ms_e, outs_e, _, _ = timed(lambda: B.step_host(full_e2e), e2e_steps)
     h2d, d2h = g.transfer_bytes(True)
-    e2e_value = B.n_dofs * e2e_steps * world / (ms_e * 1e-3)
+    e2e_value = B.n_dofs * e2e_steps / (ms_e * 1e-3)
     ms_e2, _, _, _ = timed(lambda: B.step_host(False), e2e_steps)
 
     peak, peak_src = measured_peak()
-    cg_bytes = traffic["cg_iter_bytes"]
+    cg_bytes = traffic["cg_iter_bytes"]  # of this rank's row block
+    if world > 1:
+        t = torch.tensor([cg_bytes], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        cg_bytes = float(t.item())  # all ranks together, per inner iteration
+        peak_scale = world
+    else:
+        peak_scale = 1
     achieved = cg_bytes * prof["iterations"] / (prof["ms"] * 1e-3) / 1e9 if prof["ms"] > 0 else 0.0
     tr = profile_traffic()
     roofline = {
         "bound": "hbm", "kernel": "gmg::cg_persistent<512> (coarse-level CG, one cooperative launch per V-cycle)",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "achieved": achieved, "peak": peak * peak_scale, "unit": "GB/s", "frac": achieved / (peak * peak_scale),
+        "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
         "algorithmic_bytes_per_inner_iteration": cg_bytes, "stored_nnz_level0": traffic["nnz"],
         "inner_iterations_per_launch": prof["iterations"] / max(prof["launches"], 1),
         "launches_in_timed_region": prof["launches"], "avg_launch_ms": prof["ms"] / max(prof["launches"], 1),
@@ -220,18 +239,20 @@ def run_b200(args):
     }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "impl": "b200",
         "config": workload_config(args, {
             "n_dofs": B.n_dofs, "n_dofs_level": B.level_n, "n_active_cells": B.n_cells, "n_atoms": B.n_atoms,
             "cell_atom_pairs": B.n_pairs, "outer_iterations": its[-1], "parallelism": "1 GPU" if world == 1 else
-            f"{world} independent replicas (domain-decomposed solve: see DESIGN.md multi-GPU)",
+            f"{world} GPUs: level 0 + system matrix row-partitioned in z-slabs, patch levels replicated, halos / all-reduces "
+            f"over NVLink peer memory inside the kernels (no NCCL on the data path)",
             "v_cycle_ms": None, "setup_seconds_untimed": setup_s}),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                 "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps,
                 "ms_per_step_hierarchy_already_on_device": ms_e2 / e2e_steps,
-                "what": "compute_charge_densities + rhs assembly + solve() with host buffers: atoms/cells/CSR matrices/vectors H2D, "
-                        "densities/rhs/solution D2H"},
+                "what": ("compute_charge_densities + rhs assembly + solve() with host buffers: atoms/cells/CSR matrices/vectors H2D, "
+                         "densities/rhs/solution D2H") if full_e2e else
+                        "compute_charge_densities + rhs assembly + gmg_pcg_solve with host buffers (hierarchy partitioned at set-up)"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }
     # V-cycle time: first (largest) and mean over the solve, from the coarse profile + one direct measurement

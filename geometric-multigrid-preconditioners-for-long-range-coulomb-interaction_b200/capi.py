@@ -60,6 +60,14 @@ SIGNATURES = {
     "gmg_matrix_traffic": (_i, [_h, _i, _i, _pd]),
     "gmg_coarse_profile": (_i, [_h, _i, _pd, _pi64, _pi64]),
     "gmg_launch_count": (_i64, [_h]),
+    "gmg_dist_init": (_i, [_h, _i, _i, _i64, C.c_void_p]),
+    "gmg_dist_connect": (_i, [_h, C.c_void_p]),
+    "gmg_set_ownership": (_i, [_h, _i, _i, C.c_int32, _pi32]),
+    "gmg_dist_rank": (_i, [_h, C.POINTER(_i), C.POINTER(_i)]),
+    "gmg_partition_probe": (_i, [_i, _i, C.c_int32, _pi64, _pi32, _pd, _pi32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                 C.POINTER(_pi64), C.POINTER(_pi32), C.POINTER(_pd), C.POINTER(_pi32), C.POINTER(_pi32),
+                                 C.POINTER(_pi32), C.POINTER(_pi32), C.POINTER(_pi32)]),
+    "gmg_free_host": (None, [C.c_void_p]),
     "gmg_bin_atoms": (_i, [_h, C.c_int32, _pd, _pd, C.c_int32, _pd, _d, _pi64, _pi32]),
     "gmg_set_atom_lists": (_i, [_h, C.c_int32, _pi64, _pi32]),
     "gmg_set_atoms": (_i, [_h, C.c_int32, _pd, _pd]),
@@ -280,6 +288,21 @@ class Gmg:
     def launch_count(self):
         return int(self.lib.gmg_launch_count(self.h))
 
+    # ---- multi-GPU
+    def dist_init(self, rank, world, comm_bytes=512 << 20):
+        """Allocate this rank's peer-mapped communication buffer; returns its 64-byte CUDA IPC handle."""
+        buf = (C.c_char * 64)()
+        self._ck(self.lib.gmg_dist_init(self.h, rank, world, comm_bytes, C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def dist_connect(self, all_handles):
+        blob = b"".join(all_handles)
+        self._ck(self.lib.gmg_dist_connect(self.h, C.cast(C.c_char_p(blob), C.c_void_p)))
+
+    def set_ownership(self, which, level, owner):
+        owner = _i32(owner)
+        self._ck(self.lib.gmg_set_ownership(self.h, which, level, len(owner), owner.ctypes.data_as(_pi32)))
+
     # ---- RHS path
     def set_atoms(self, pos, charge):
         pos, charge = _f64(pos), _f64(charge)
@@ -352,3 +375,37 @@ def hand_over_hierarchy(gmg, system_A, level_A, level_I, prolong, copy_global, c
         if l + 1 < nl:
             gmg.set_matrix(GMG_PROLONG, l, prolong[l])
         gmg.set_copy_indices(l, copy_global[l], copy_level[l])
+
+
+def connect_ranks(gmg, rank, world, all_gather_bytes, comm_bytes=512 << 20):
+    """Map every rank's communication buffer on every other rank.  `all_gather_bytes(b) -> [b_0 .. b_{W-1}]` is the
+    caller's collective (torch.distributed / MPI); it also acts as the barrier between init and connect."""
+    handle = gmg.dist_init(rank, world, comm_bytes)
+    gmg.dist_connect(all_gather_bytes(handle))
+
+
+def partition_probe(rank, world, csr, owner):
+    """Host-only: the local matrix / halo maps rank `rank` would build (see csrc/partition.h)."""
+    lib = load_library()
+    csr = csr.tocsr()
+    rp = np.ascontiguousarray(csr.indptr, dtype=np.int64)
+    col, val, owner = _i32(csr.indices), _f64(csr.data), _i32(owner)
+    n_owned, n_halo = C.c_int32(), C.c_int32()
+    l_rp, l_col, l_val = _pi64(), _pi32(), _pd()
+    og, hg, sc, si, sb = _pi32(), _pi32(), _pi32(), _pi32(), _pi32()
+    rc = lib.gmg_partition_probe(rank, world, csr.shape[0], rp.ctypes.data_as(_pi64), col.ctypes.data_as(_pi32), _pd_of(val),
+                                 owner.ctypes.data_as(_pi32), C.byref(n_owned), C.byref(n_halo), C.byref(l_rp), C.byref(l_col),
+                                 C.byref(l_val), C.byref(og), C.byref(hg), C.byref(sc), C.byref(si), C.byref(sb))
+    if rc != 0:
+        raise GmgError(rc, "gmg_partition_probe failed")
+    no, nh = n_owned.value, n_halo.value
+    take = lambda p, n, dt: np.ctypeslib.as_array(p, shape=(max(n, 1),)).astype(dt)[:n].copy()
+    rowptr = take(l_rp, no + 1, np.int64)
+    nnz = int(rowptr[-1])
+    out = dict(n_owned=no, n_halo=nh, rowptr=rowptr, col=take(l_col, nnz, np.int32), val=take(l_val, nnz, np.float64),
+               owned_global=take(og, no, np.int32), halo_global=take(hg, nh, np.int32), send_count=take(sc, world, np.int32),
+               send_dst_base=take(sb, world, np.int32))
+    out["send_idx"] = take(si, int(out["send_count"].sum()), np.int32)
+    for p in (l_rp, l_col, l_val, og, hg, sc, si, sb):
+        lib.gmg_free_host(C.cast(p, C.c_void_p))
+    return out

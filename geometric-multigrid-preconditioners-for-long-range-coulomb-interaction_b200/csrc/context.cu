@@ -6,6 +6,7 @@
 
 #include "context.h"
 #include "kernels.cuh"
+#include "dist.cuh"
 
 using namespace gmg;
 
@@ -513,7 +514,19 @@ static int fetch_coarse_its(gmg_context *h) {
   return GMG_OK;
 }
 
-static Sell *pick(gmg_context *h, int which, int level) {
+static int dist_setup(gmg_context *h);
+static int dist_pcg(gmg_context *h, const double *b_global, double *x_global, int max_it, double tol, int *iters,
+                    double *res0_out, double *res_out);
+static int dist_vcycle(gmg_context *h, const double *src, double *dst);
+static void dist_free(gmg_context *h);
+static int dist_gather(gmg_context *h, const GatherPlan &G, const double *src, int channel);
+
+static Sell *pick(gmg_context *h, int which, int level, bool local_ok = false) {
+  if (h->dist.on && (which == GMG_SYSTEM || (which == GMG_LEVEL && level == 0))) {
+    if (!local_ok) return nullptr;  // row-partitioned: only the rank-local block exists on this device
+    Sell *s = which == GMG_SYSTEM ? &h->dist.S.A : &h->dist.A0.A;
+    return s->valid ? s : nullptr;
+  }
   if (which == GMG_SYSTEM) return h->S.valid ? &h->S : nullptr;
   if (level < 0 || level >= h->n_levels) return nullptr;
   Level &L = h->levels[level];
@@ -652,12 +665,20 @@ int gmg_set_matrix(gmg_handle h, int which, int level, int32_t n_rows, int32_t n
   h->is_setup = false;
   if (which == GMG_SYSTEM) {
     h->n_sys = n_rows;
+    if (h->dist.on) {
+      h->dist.hS = make_host(n_rows, n_cols, rowptr, col, val);
+      return GMG_OK;
+    }
     return upload_csr(h, n_rows, n_cols, rowptr, col, val, h->rawS);
   }
   if (level < 0 || level >= h->n_levels) return fail(h, GMG_EINVAL, "level out of range (call gmg_set_num_levels)");
   Level &L = h->levels[level];
   if (which == GMG_LEVEL) {
     L.n = n_rows;
+    if (h->dist.on && level == 0) {
+      h->dist.hA0 = make_host(n_rows, n_cols, rowptr, col, val);
+      return GMG_OK;
+    }
     if (level >= 1) L.hA = make_host(n_rows, n_cols, rowptr, col, val);
     return upload_csr(h, n_rows, n_cols, rowptr, col, val, L.rawA);
   }
@@ -676,6 +697,12 @@ int gmg_set_copy_indices(gmg_handle h, int level, int32_t n, const int32_t *gi, 
   if (!h || level < 0 || level >= h->n_levels || n < 0) return GMG_EINVAL;
   gmg::enter(h);
   Level &L = h->levels[level];
+  if (h->dist.on) {
+    h->dist.h_copy_g.resize(h->n_levels);
+    h->dist.h_copy_l.resize(h->n_levels);
+    h->dist.h_copy_g[level].assign(gi, gi + n);
+    h->dist.h_copy_l[level].assign(li, li + n);
+  }
   dfree(L.copy_g);
   dfree(L.copy_l);
   L.n_copy = n;
@@ -732,8 +759,10 @@ int gmg_setup(gmg_handle h) {
     }
   }
   int cg_n = 0;
+  const bool dist = h->dist.on;
   for (int l = 0; l < h->n_levels; ++l) {
     Level &L = h->levels[l];
+    if (dist && l == 0) continue;  // level 0 is row-partitioned: built by dist_setup
     TraceScope tr_l("  level total");
     if (L.rawA.rowptr) {
       TraceScope tr("    A -> sell");
@@ -833,8 +862,13 @@ int gmg_setup(gmg_handle h) {
       return fail(h, GMG_EINVAL, "prolongation from level " + std::to_string(l) + " missing");
     }
   }
+  if (dist) {
+    dfree(h->hh);
+    GMG_CUDA(h, dalloc(&h->hh, h->n_sys));
+    if ((rc = dist_setup(h))) return rc;
+  }
   // the coarse CG may also be called on the system matrix (tests / single-level)
-  cg_n = std::max(cg_n, h->n_sys);
+  cg_n = dist ? 0 : std::max(cg_n, h->n_sys);
   if (cg_n > h->cg_n) {
     dfree(h->cg_g);
     dfree(h->cg_d);
@@ -852,11 +886,13 @@ int gmg_setup(gmg_handle h) {
 // ------------------------------------------------------------------------------------ solve path
 int gmg_pcg_solve_dev(gmg_handle h, const double *b, double *x, int max_it, double abs_tol, int *iters, double *res0,
                       double *res_final) {
-  if (!h || !h->is_setup || !h->S.valid || h->n_levels < 1) return h ? fail(h, GMG_EINVAL, "not set up") : GMG_EINVAL;
+  if (!h || !h->is_setup || (!h->S.valid && !h->dist.on) || h->n_levels < 1)
+    return h ? fail(h, GMG_EINVAL, "not set up") : GMG_EINVAL;
   gmg::enter(h);
   int it = 0;
   double r0 = 0, r1 = 0;
-  int rc = pcg(h, PRECOND_GMG, 0.0, b, x, max_it, abs_tol, &it, &r0, &r1);
+  int rc = h->dist.on ? dist_pcg(h, b, x, max_it, abs_tol, &it, &r0, &r1)
+                      : pcg(h, PRECOND_GMG, 0.0, b, x, max_it, abs_tol, &it, &r0, &r1);
   if (iters) *iters = it;
   if (res0) *res0 = r0;
   if (res_final) *res_final = r1;
@@ -887,7 +923,7 @@ int gmg_pcg_solve(gmg_handle h, const double *b, double *x, int max_it, double a
 
 int gmg_pcg_solve_jacobi(gmg_handle h, const double *b, double *x, double omega, int max_it, double abs_tol, int *iters,
                          double *res0, double *res_final) {
-  if (!h || !b || !x || !h->S.valid) return GMG_EINVAL;
+  if (!h || !b || !x || !h->S.valid) return h ? fail(h, GMG_EINVAL, "Jacobi-preconditioned CG needs the single-GPU system matrix") : GMG_EINVAL;
   gmg::enter(h);
   const int n = h->n_sys;
   if (int rc = with_host_vectors(h, n, b, n, x, true)) return rc;
@@ -906,6 +942,16 @@ int gmg_vcycle_apply_dev(gmg_handle h, const double *src, double *dst) {
   if (!h || !h->is_setup) return GMG_EINVAL;
   gmg::enter(h);
   h->cg_solve_begin = h->cg_cursor;
+  if (h->dist.on) {  // global-length vectors in, full result out on every rank
+    DistData &d = h->dist;
+    const int n = d.n_sys_owned;
+    vec_take<<<cdiv(std::max(n, 1), 256), 256, 0, h->stream>>>(n, d.sys_owned_global, src, d.g);
+    GMG_LAUNCH_CHECK(h);
+    if (int rc = dist_vcycle(h, d.g, d.hh)) return rc;
+    if (int rc = dist_gather(h, d.gather_x, d.hh, CH_GATHER_X)) return rc;
+    GMG_CUDA(h, gmg::copy(h, dst, d.buf + d.gather_x.region, sizeof(double) * d.n_sys, cudaMemcpyDeviceToDevice));
+    return GMG_OK;
+  }
   return vcycle(h, src, dst);
 }
 
@@ -1091,7 +1137,7 @@ int gmg_transfer_bytes(gmg_handle h, int reset, int64_t *h2d, int64_t *d2h) {
 
 int gmg_matrix_traffic(gmg_handle h, int which, int level, double out[3]) {
   if (!h || !out) return GMG_EINVAL;
-  Sell *A = pick(h, which, level);
+  Sell *A = pick(h, which, level, true);  // multi-GPU: the rank-local block
   if (!A) return fail(h, GMG_EINVAL, "matrix not available");
   const double nnz = (double)A->stored_nnz, n = (double)A->v.n_rows;
   out[0] = nnz;
@@ -1116,3 +1162,5 @@ int gmg_coarse_profile(gmg_handle h, int reset, double *ms, int64_t *launches, i
 }
 
 }  // extern "C"
+
+#include "dist.inl"

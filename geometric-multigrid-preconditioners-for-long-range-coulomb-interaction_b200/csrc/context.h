@@ -10,6 +10,7 @@
 
 #include "../../include/gmg_b200.h"
 #include "common.cuh"
+#include "partition.h"
 
 namespace gmg {
 
@@ -58,6 +59,55 @@ struct Level {
   std::vector<ColorSet> colors;      // multicolour SSOR
   std::vector<ColorSet> wave_fwd, wave_bwd;  // level-scheduled lexicographic SSOR
   double lambda_max = 0.0;           // Chebyshev
+};
+
+// one distributed (row-partitioned) matrix: local SELL over [owned | halo] columns + its halo send lists
+struct DistMat {
+  Sell A;
+  int n_owned = 0, n_halo = 0, n_send = 0;
+  int *send_src = nullptr, *send_dst = nullptr;
+  unsigned char *send_peer = nullptr;
+  uint32_t dst_mask = 0, src_mask = 0;
+};
+
+// "push my owned entries of a list to every rank" (all-gather over peer memory)
+struct GatherPlan {
+  int n_total = 0, n_send = 0;  // n_send = owned entries x world
+  int *send_src = nullptr, *send_dst = nullptr;
+  unsigned char *send_peer = nullptr;
+  size_t region = 0;
+};
+
+struct DistData {
+  bool on = false;
+  int rank = 0, world = 1;
+  char *buf = nullptr;
+  char *peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t bytes = 0, bump = 0;
+  uint64_t seq[32] = {0};
+  uint64_t launch_id = 0;
+  int *d_error = nullptr;
+  std::vector<int32_t> sys_owner, l0_owner;
+  HostCsr hS, hA0;
+  std::vector<std::vector<int32_t>> h_copy_g, h_copy_l;  // copy indices as handed over (global numbering)
+  DistMat S, A0;
+  size_t reg_cg_d = 0, reg_pcg_d = 0, reg_pcg_x = 0;
+  int n_sys_owned = 0, n_l0_owned = 0, n_sys = 0, n_l0 = 0;
+  int *sys_owned_global = nullptr;      // device: global index of each owned system dof
+  // copy_to_mg / copy_from_mg
+  int n_copy0 = 0;
+  int *copy0_sys = nullptr, *copy0_l0 = nullptr;  // owned pairs on level 0 (local indices)
+  GatherPlan gather_g;                            // defect entries of the replicated levels
+  std::vector<int> gather_g_offset;               // per level >= 1: offset into the gathered list
+  std::vector<int> n_from;                        // per level >= 1: owned pairs for copy_from_mg
+  std::vector<int *> from_sys, from_lvl;
+  // level 0 <-> level 1 transfer
+  Sell R0, P0F;
+  GatherPlan gather_c;
+  GatherPlan gather_x;  // solution all-gather (global positions)
+  double *l0_defect = nullptr, *l0_sol = nullptr, *cg_g = nullptr, *cg_h = nullptr;
+  double *g = nullptr, *hh = nullptr;  // outer PCG owned vectors
+  double *cg_partials = nullptr;
 };
 
 }  // namespace gmg
@@ -117,6 +167,7 @@ struct gmg_context {
   int *list_atoms = nullptr;
   int n_lists = 0;
   struct RhsState *rhs = nullptr;
+  gmg::DistData dist;
 };
 
 namespace gmg {

@@ -1,0 +1,575 @@
+// Multi-GPU host side (included by context.cu): symmetric peer buffer, partitioned set-up, distributed
+// V-cycle / PCG.  Decomposition: level 0 and the system matrix are row-partitioned by the
+// ownership arrays the host hands over (z-slabs of the base lattice); the small patch levels (>= 1) are
+// replicated on every GPU so they need no communication; what crosses NVLink is (i) halo rows of the
+// PCG / coarse-CG direction vectors, (ii) W x W scalar all-reduces, (iii) two small all-gathers per V-cycle
+// (patch defect entries, level-0 values under the patch).
+
+namespace gmg {
+
+static DistPeers peers_of(const gmg_context *h) {
+  DistPeers P;
+  P.rank = h->dist.rank;
+  P.world = h->dist.world;
+  for (int q = 0; q < DIST_MAX_RANKS; ++q) P.peer[q] = h->dist.peer[q];
+  return P;
+}
+
+static int sym_alloc(gmg_context *h, size_t bytes, size_t &off) {
+  DistData &d = h->dist;
+  off = (d.bump + 255) & ~(size_t)255;
+  if (off + bytes > d.bytes) return fail(h, GMG_EINVAL, "symmetric communication buffer too small (gmg_dist_init comm_bytes)");
+  d.bump = off + bytes;
+  return GMG_OK;
+}
+
+template <class T>
+static int to_device(gmg_context *h, T *&dst, const std::vector<T> &src) {
+  dfree(dst);
+  GMG_CUDA(h, dalloc(&dst, (int64_t)src.size()));
+  if (!src.empty()) GMG_CUDA(h, copy_sync(h, dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+  return GMG_OK;
+}
+
+static int dist_check_error(gmg_context *h) {
+  int e = 0;
+  GMG_CUDA(h, copy_sync(h, &e, h->dist.d_error, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e) return fail(h, GMG_ENCCL, "multi-GPU: a wait on a peer flag timed out (a rank is missing or failed)");
+  return GMG_OK;
+}
+
+static int dist_allreduce1(gmg_context *h, double *v, int k = 1) {
+  DistData &d = h->dist;
+  dist_allreduce<<<1, 32, 0, h->stream>>>(peers_of(h), v, k, ++d.seq[CH_RED], d.d_error);
+  GMG_LAUNCH_CHECK(h);
+  return GMG_OK;
+}
+
+// push (src -> peers' region) + wait for every source rank on `channel`
+static int dist_exchange(gmg_context *h, int n_send, const int *send_src, const unsigned char *send_peer,
+                         const int *send_dst, size_t region, const double *src, int channel, uint32_t dst_mask,
+                         uint32_t src_mask) {
+  DistData &d = h->dist;
+  const uint64_t seq = ++d.seq[channel];
+  dist_push<<<std::max(cdiv(n_send, 256), 1), 256, 0, h->stream>>>(peers_of(h), n_send, send_src, send_peer, send_dst, region,
+                                                                  src, channel, seq, dst_mask, h->counter + 1);
+  GMG_LAUNCH_CHECK(h);
+  dist_wait<<<1, 32, 0, h->stream>>>(peers_of(h), channel, seq, src_mask, d.d_error);
+  GMG_LAUNCH_CHECK(h);
+  return GMG_OK;
+}
+
+static int dist_halo(gmg_context *h, const DistMat &M, size_t region, int channel) {
+  const double *src = reinterpret_cast<const double *>(h->dist.buf + region);
+  return dist_exchange(h, M.n_send, M.send_src, M.send_peer, M.send_dst, region, src, channel, M.dst_mask, M.src_mask);
+}
+
+static int dist_gather(gmg_context *h, const GatherPlan &G, const double *src, int channel) {
+  const uint32_t all = (1u << h->dist.world) - 1u;
+  return dist_exchange(h, G.n_send, G.send_src, G.send_peer, G.send_dst, G.region, src, channel, all, all);
+}
+
+static void free_distmat(DistMat &M) {
+  free_sell(M.A);
+  dfree(M.send_src);
+  dfree(M.send_dst);
+  dfree(M.send_peer);
+  M = DistMat{};
+}
+static void free_gather(GatherPlan &G) {
+  dfree(G.send_src);
+  dfree(G.send_dst);
+  dfree(G.send_peer);
+  G = GatherPlan{};
+}
+
+static int build_distmat(gmg_context *h, const HostCsr &g, const std::vector<int32_t> &owner, DistMat &M, LocalMatrix &lm,
+                         ExchangePlan &plan) {
+  DistData &d = h->dist;
+  partition_matrix(d.rank, d.world, g.n_rows, g.n_cols, g.rowptr.data(), g.col.data(), g.val.data(), owner.data(),
+                   owner.data(), lm, plan);
+  HostCsr loc;
+  loc.n_rows = lm.n_owned;
+  loc.n_cols = lm.n_owned + lm.n_halo;
+  loc.rowptr = lm.rowptr;
+  loc.col = lm.col;
+  loc.val = lm.val;
+  free_distmat(M);
+  if (int rc = build_sell_host(h, loc, h->drop_tol, M.A)) return rc;
+  M.n_owned = lm.n_owned;
+  M.n_halo = lm.n_halo;
+  std::vector<int> ssrc, sdst;
+  std::vector<unsigned char> speer;
+  for (int q = 0; q < d.world; ++q) {
+    if (q == d.rank) continue;
+    if (!plan.send_idx[q].empty()) M.dst_mask |= 1u << q;
+    if (plan.recv_count[q] > 0) M.src_mask |= 1u << q;
+    for (size_t k = 0; k < plan.send_idx[q].size(); ++k) {
+      ssrc.push_back(plan.send_idx[q][k]);
+      sdst.push_back(plan.send_dst_base[q] + (int)k);
+      speer.push_back((unsigned char)q);
+    }
+  }
+  M.n_send = (int)ssrc.size();
+  if (int rc = to_device(h, M.send_src, ssrc)) return rc;
+  if (int rc = to_device(h, M.send_dst, sdst)) return rc;
+  return to_device(h, M.send_peer, speer);
+}
+
+// owned entries (local src index, destination position) pushed to every rank, self included
+static int build_gather(gmg_context *h, const std::vector<int> &src_local, const std::vector<int> &dst_pos, int n_total,
+                        GatherPlan &G) {
+  DistData &d = h->dist;
+  free_gather(G);
+  std::vector<int> ssrc, sdst;
+  std::vector<unsigned char> speer;
+  for (int q = 0; q < d.world; ++q)
+    for (size_t k = 0; k < src_local.size(); ++k) {
+      ssrc.push_back(src_local[k]);
+      sdst.push_back(dst_pos[k]);
+      speer.push_back((unsigned char)q);
+    }
+  G.n_total = n_total;
+  G.n_send = (int)ssrc.size();
+  if (int rc = sym_alloc(h, sizeof(double) * (size_t)std::max(n_total, 1), G.region)) return rc;
+  if (int rc = to_device(h, G.send_src, ssrc)) return rc;
+  if (int rc = to_device(h, G.send_dst, sdst)) return rc;
+  return to_device(h, G.send_peer, speer);
+}
+
+static int dist_setup(gmg_context *h) {
+  DistData &d = h->dist;
+  if (d.hS.empty() || d.hA0.empty() || d.sys_owner.empty() || d.l0_owner.empty())
+    return fail(h, GMG_EINVAL, "multi-GPU: system / level-0 matrices and their ownership must be set before gmg_setup");
+  if ((int)d.sys_owner.size() != d.hS.n_rows || (int)d.l0_owner.size() != d.hA0.n_rows)
+    return fail(h, GMG_EINVAL, "multi-GPU: ownership array size mismatch");
+  d.bump = DIST_HEADER_BYTES;
+  d.n_sys = d.hS.n_rows;
+  d.n_l0 = d.hA0.n_rows;
+  h->n_sys = d.n_sys;
+  LocalMatrix lmS, lmA;
+  ExchangePlan plS, plA;
+  int rc;
+  {
+    TraceScope tr("  dist: system matrix");
+    if ((rc = build_distmat(h, d.hS, d.sys_owner, d.S, lmS, plS))) return rc;
+  }
+  {
+    TraceScope tr("  dist: level-0 matrix");
+    if ((rc = build_distmat(h, d.hA0, d.l0_owner, d.A0, lmA, plA))) return rc;
+  }
+  d.n_sys_owned = lmS.n_owned;
+  d.n_l0_owned = lmA.n_owned;
+  // symmetric extended vectors: size = max over ranks of owned + halo (every rank knows every size)
+  int ext_sys = 0, ext_l0 = 0;
+  for (int q = 0; q < d.world; ++q) {
+    ext_sys = std::max(ext_sys, plS.n_owned_of[q] + plS.n_halo_of[q]);
+    ext_l0 = std::max(ext_l0, plA.n_owned_of[q] + plA.n_halo_of[q]);
+  }
+  if ((rc = sym_alloc(h, sizeof(double) * (size_t)ext_sys, d.reg_pcg_x))) return rc;
+  if ((rc = sym_alloc(h, sizeof(double) * (size_t)ext_sys, d.reg_pcg_d))) return rc;
+  if ((rc = sym_alloc(h, sizeof(double) * (size_t)ext_l0, d.reg_cg_d))) return rc;
+  if ((rc = to_device(h, d.sys_owned_global, lmS.owned_global))) return rc;
+  std::vector<int> sys_g2l(d.n_sys, -1), l0_g2l(d.n_l0, -1);
+  for (int i = 0; i < lmS.n_owned; ++i) sys_g2l[lmS.owned_global[i]] = i;
+  for (int i = 0; i < lmA.n_owned; ++i) l0_g2l[lmA.owned_global[i]] = i;
+
+  // ---- copy indices
+  const int nl = h->n_levels;
+  if ((int)d.h_copy_g.size() != nl) return fail(h, GMG_EINVAL, "multi-GPU: copy indices missing");
+  {
+    std::vector<int> cs, cl;
+    for (size_t k = 0; k < d.h_copy_g[0].size(); ++k) {
+      const int g = d.h_copy_g[0][k], lv = d.h_copy_l[0][k];
+      if (d.sys_owner[g] != d.rank) continue;
+      if (d.l0_owner[lv] != d.rank) return fail(h, GMG_EINVAL, "multi-GPU: a system dof and its level-0 twin have different owners");
+      cs.push_back(sys_g2l[g]);
+      cl.push_back(l0_g2l[lv]);
+    }
+    d.n_copy0 = (int)cs.size();
+    if ((rc = to_device(h, d.copy0_sys, cs))) return rc;
+    if ((rc = to_device(h, d.copy0_l0, cl))) return rc;
+  }
+  {
+    std::vector<int> src, pos;
+    d.gather_g_offset.assign(nl + 1, 0);
+    for (auto p : d.from_sys) dfree(p);
+    for (auto p : d.from_lvl) dfree(p);
+    d.from_sys.assign(nl, nullptr);
+    d.from_lvl.assign(nl, nullptr);
+    d.n_from.assign(nl, 0);
+    int total = 0;
+    for (int l = 1; l < nl; ++l) {
+      d.gather_g_offset[l] = total;
+      std::vector<int> fs, fl;
+      for (size_t k = 0; k < d.h_copy_g[l].size(); ++k) {
+        const int g = d.h_copy_g[l][k];
+        if (d.sys_owner[g] == d.rank) {
+          src.push_back(sys_g2l[g]);
+          pos.push_back(total + (int)k);
+          fs.push_back(sys_g2l[g]);
+          fl.push_back(d.h_copy_l[l][k]);
+        }
+      }
+      total += (int)d.h_copy_g[l].size();
+      d.n_from[l] = (int)fs.size();
+      if ((rc = to_device(h, d.from_sys[l], fs))) return rc;
+      if ((rc = to_device(h, d.from_lvl[l], fl))) return rc;
+    }
+    d.gather_g_offset[nl] = total;
+    if ((rc = build_gather(h, src, pos, total, d.gather_g))) return rc;
+  }
+  // ---- level 0 <-> level 1 transfers
+  free_sell(d.R0);
+  free_sell(d.P0F);
+  free_gather(d.gather_c);
+  if (nl > 1) {
+    const HostCsr &P = h->levels[0].hP;
+    if (P.empty()) return fail(h, GMG_EINVAL, "prolongation from level 0 missing");
+    // restriction: rows = my level-0 dofs, columns = level-1 dofs (replicated input)
+    HostCsr R = transpose(P);
+    HostCsr Rl;
+    Rl.n_cols = R.n_cols;
+    extract_owned_rows(d.rank, R.n_rows, R.rowptr.data(), R.col.data(), R.val.data(), d.l0_owner.data(), Rl.rowptr, Rl.col,
+                       Rl.val);
+    Rl.n_rows = (int)Rl.rowptr.size() - 1;
+    if ((rc = build_sell_host(h, Rl, 0.0, d.R0))) return rc;
+    // prolongation through the footprint F = level-0 dofs that are parents of level-1 dofs
+    std::vector<int> F(P.col.begin(), P.col.end());
+    std::sort(F.begin(), F.end());
+    F.erase(std::unique(F.begin(), F.end()), F.end());
+    std::vector<int> posF(d.n_l0, -1);
+    for (size_t k = 0; k < F.size(); ++k) posF[F[k]] = (int)k;
+    HostCsr PF = P;
+    PF.n_cols = (int)F.size();
+    for (auto &c : PF.col) c = posF[c];
+    if ((rc = build_sell_host(h, PF, 0.0, d.P0F))) return rc;
+    std::vector<int> src, pos;
+    for (size_t k = 0; k < F.size(); ++k)
+      if (d.l0_owner[F[k]] == d.rank) {
+        src.push_back(l0_g2l[F[k]]);
+        pos.push_back((int)k);
+      }
+    if ((rc = build_gather(h, src, pos, (int)F.size(), d.gather_c))) return rc;
+  }
+  // ---- solution all-gather (global positions)
+  {
+    std::vector<int> src(lmS.n_owned), pos(lmS.owned_global.begin(), lmS.owned_global.end());
+    for (int i = 0; i < lmS.n_owned; ++i) src[i] = i;
+    if ((rc = build_gather(h, src, pos, d.n_sys, d.gather_x))) return rc;
+  }
+  // ---- work vectors
+  for (double **p : {&d.l0_defect, &d.l0_sol, &d.cg_g, &d.cg_h}) {
+    dfree(*p);
+    GMG_CUDA(h, dalloc(p, d.n_l0_owned));
+    GMG_CUDA(h, cudaMemsetAsync(*p, 0, sizeof(double) * std::max(d.n_l0_owned, 1), h->stream));
+  }
+  for (double **p : {&d.g, &d.hh}) {
+    dfree(*p);
+    GMG_CUDA(h, dalloc(p, d.n_sys_owned));
+  }
+  dfree(d.cg_partials);
+  GMG_CUDA(h, dalloc(&d.cg_partials, h->cg_grid));
+  GMG_CUDA(h, cudaMemsetAsync(d.buf + DIST_HEADER_BYTES, 0, d.bump - DIST_HEADER_BYTES, h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return GMG_OK;
+}
+
+static int dist_coarse_cg(gmg_context *h, const double *b, double *x) {
+  DistData &d = h->dist;
+  const int slot = h->cg_cursor % h->cg_ring;
+  h->cg_cursor++;
+  CgResult *res = h->cg_results + slot;
+  SellView v = d.A0.A.v;
+  DistCgArgs D;
+  D.P = peers_of(h);
+  D.n_send = d.A0.n_send;
+  D.send_src = d.A0.send_src;
+  D.send_peer = d.A0.send_peer;
+  D.send_dst = d.A0.send_dst;
+  D.region_d = d.reg_cg_d;
+  D.dst_mask = d.A0.dst_mask;
+  D.src_mask = d.A0.src_mask;
+  D.seq_base = (++d.launch_id) << 32;
+  int max_it = h->coarse_max_it;
+  double tol = h->coarse_tol;
+  int grid = h->cg_grid;
+  void *args[] = {&v, (void *)&b, &x, &d.cg_g, &d.cg_h, &d.cg_partials, &max_it, &tol, &res, &D, &d.d_error};
+  int ev = -1;
+  if (h->ev_used < (int)h->ev_begin.size()) {
+    ev = h->ev_used++;
+    cudaEventRecord(h->ev_begin[ev], h->stream);
+  }
+  GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_dist<512>, dim3(grid), dim3(512), args, 0, h->stream));
+  h->launches++;
+  if (ev >= 0) {
+    cudaEventRecord(h->ev_end[ev], h->stream);
+    h->ev_result_slot[ev] = slot;
+  }
+  return GMG_OK;
+}
+
+// PreconditionMG::vmult, distributed: src / dst are owned-only system vectors
+static int dist_vcycle(gmg_context *h, const double *src, double *dst) {
+  DistData &d = h->dist;
+  const int nl = h->n_levels;
+  // copy_to_mg
+  GMG_CUDA(h, cudaMemsetAsync(d.l0_defect, 0, sizeof(double) * std::max(d.n_l0_owned, 1), h->stream));
+  if (d.n_copy0) {
+    vec_gather<<<cdiv(d.n_copy0, 256), 256, 0, h->stream>>>(d.n_copy0, d.copy0_l0, d.copy0_sys, src, d.l0_defect);
+    GMG_LAUNCH_CHECK(h);
+  }
+  if (nl > 1) {
+    if (int rc = dist_gather(h, d.gather_g, src, CH_GATHER_G)) return rc;
+    const double *gg = reinterpret_cast<const double *>(d.buf + d.gather_g.region);
+    for (int l = 1; l < nl; ++l) {
+      Level &L = h->levels[l];
+      GMG_CUDA(h, cudaMemsetAsync(L.defect, 0, sizeof(double) * std::max(L.n, 1), h->stream));
+      if (L.n_copy) {
+        vec_gather_from<<<cdiv(L.n_copy, 256), 256, 0, h->stream>>>(L.n_copy, L.copy_l, gg + d.gather_g_offset[l], L.defect);
+        GMG_LAUNCH_CHECK(h);
+      }
+    }
+  }
+  for (int l = nl - 1; l >= 1; --l) {
+    Level &L = h->levels[l];
+    if (int rc = smooth(h, L, L.sol, L.defect, true)) return rc;
+    if (int rc = spmv<EPI_RESID, DOT_NONE>(h, L.AI, L.sol, L.t, L.defect)) return rc;
+    if (l > 1) {
+      if (int rc = spmv<EPI_ADD, DOT_NONE>(h, h->levels[l - 1].R, L.t, h->levels[l - 1].defect)) return rc;
+    } else {
+      if (int rc = spmv<EPI_ADD, DOT_NONE>(h, d.R0, L.t, d.l0_defect)) return rc;
+    }
+  }
+  if (int rc = dist_coarse_cg(h, d.l0_defect, d.l0_sol)) return rc;
+  for (int l = 1; l < nl; ++l) {
+    Level &L = h->levels[l];
+    if (l > 1) {
+      if (int rc = spmv<EPI_ADD, DOT_NONE>(h, h->levels[l - 1].P, h->levels[l - 1].sol, L.sol)) return rc;
+    } else {
+      if (int rc = dist_gather(h, d.gather_c, d.l0_sol, CH_GATHER_C)) return rc;
+      const double *c = reinterpret_cast<const double *>(d.buf + d.gather_c.region);
+      if (int rc = spmv<EPI_ADD, DOT_NONE>(h, d.P0F, c, L.sol)) return rc;
+    }
+    if (L.IT.valid && L.IT.stored_nnz > 0)
+      if (int rc = spmv<EPI_SUB, DOT_NONE>(h, L.IT, L.sol, L.defect)) return rc;
+    if (int rc = smooth(h, L, L.sol, L.defect, false)) return rc;
+  }
+  // copy_from_mg
+  GMG_CUDA(h, cudaMemsetAsync(dst, 0, sizeof(double) * std::max(d.n_sys_owned, 1), h->stream));
+  if (d.n_copy0) {
+    vec_gather<<<cdiv(d.n_copy0, 256), 256, 0, h->stream>>>(d.n_copy0, d.copy0_sys, d.copy0_l0, d.l0_sol, dst);
+    GMG_LAUNCH_CHECK(h);
+  }
+  for (int l = 1; l < nl; ++l)
+    if (d.n_from[l]) {
+      vec_gather<<<cdiv(d.n_from[l], 256), 256, 0, h->stream>>>(d.n_from[l], d.from_sys[l], d.from_lvl[l], h->levels[l].sol, dst);
+      GMG_LAUNCH_CHECK(h);
+    }
+  return GMG_OK;
+}
+
+// distributed SolverCG with the GMG preconditioner; b, x are GLOBAL-length device vectors (every rank holds
+// the same b and receives the full solution)
+static int dist_pcg(gmg_context *h, const double *b_global, double *x_global, int max_it, double tol, int *iters,
+                    double *res0_out, double *res_out) {
+  DistData &d = h->dist;
+  const int n = d.n_sys_owned;
+  h->cg_solve_begin = h->cg_cursor;
+  double *x = reinterpret_cast<double *>(d.buf + d.reg_pcg_x);
+  double *dd = reinterpret_cast<double *>(d.buf + d.reg_pcg_d);
+  double *bl = h->hh;  // owned part of b (h->hh has global length >= owned)
+  PcgScalars hs;
+  const int tg = cdiv(std::max(n, 1), 256);
+  vec_take<<<tg, 256, 0, h->stream>>>(n, d.sys_owned_global, b_global, bl);
+  GMG_LAUNCH_CHECK(h);
+  vec_take<<<tg, 256, 0, h->stream>>>(n, d.sys_owned_global, x_global, x);
+  GMG_LAUNCH_CHECK(h);
+  const int rg = reduce_grid(h, n);
+  auto sync_scalars = [&]() -> int {
+    GMG_CUDA(h, copy(h, &hs, h->scalars, sizeof(hs), cudaMemcpyDeviceToHost));
+    GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return dist_check_error(h);
+  };
+  auto finish = [&]() -> int {
+    if (int rc = dist_gather(h, d.gather_x, x, CH_GATHER_X)) return rc;
+    GMG_CUDA(h, copy(h, x_global, d.buf + d.gather_x.region, sizeof(double) * d.n_sys, cudaMemcpyDeviceToDevice));
+    GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return dist_check_error(h);
+  };
+  if (int rc = dist_halo(h, d.S, d.reg_pcg_x, CH_HALO_SYS_X)) return rc;
+  if (int rc = spmv<EPI_NRESID, DOT_YY>(h, d.S.A, x, d.g, bl, nullptr, 0.0, &h->scalars->res2)) return rc;
+  if (int rc = dist_allreduce1(h, &h->scalars->res2)) return rc;
+  if (int rc = sync_scalars()) return rc;
+  double res = std::sqrt(hs.res2);
+  *res0_out = res;
+  *res_out = res;
+  *iters = 0;
+  if (res <= tol) return finish();
+  int slot = 0;
+  if (int rc = dist_vcycle(h, d.g, d.hh)) return rc;
+  pcg_init_direction<<<rg, 256, 0, h->stream>>>(n, d.g, d.hh, dd, h->scalars, slot, h->partials, h->counter);
+  GMG_LAUNCH_CHECK(h);
+  if (int rc = dist_allreduce1(h, &h->scalars->gh[slot])) return rc;
+  int it = 0;
+  while (true) {
+    ++it;
+    if (int rc = dist_halo(h, d.S, d.reg_pcg_d, CH_HALO_SYS_D)) return rc;
+    if (int rc = spmv<EPI_ASSIGN, DOT_XY>(h, d.S.A, dd, d.hh, nullptr, nullptr, 0.0, &h->scalars->dh)) return rc;
+    if (int rc = dist_allreduce1(h, &h->scalars->dh)) return rc;
+    pcg_update<<<rg, 256, 0, h->stream>>>(n, x, d.g, dd, d.hh, h->scalars, slot, h->partials, h->counter);
+    GMG_LAUNCH_CHECK(h);
+    if (int rc = dist_allreduce1(h, &h->scalars->res2)) return rc;
+    if (int rc = sync_scalars()) return rc;
+    {
+      CgResult r;
+      GMG_CUDA(h, copy_sync(h, &r, h->cg_results + ((h->cg_cursor - 1) % h->cg_ring), sizeof(r), cudaMemcpyDeviceToHost));
+      if (r.status == 1)
+        return fail(h, GMG_ENOCONVERGENCE, "coarse-grid CG: convergence failure in step " + std::to_string(r.iterations));
+      if (r.status == 2) return fail(h, GMG_ENCCL, "multi-GPU coarse CG aborted: a peer did not arrive");
+    }
+    res = std::sqrt(hs.res2);
+    *res_out = res;
+    *iters = it;
+    if (res <= tol) break;
+    if (it >= max_it || std::isnan(res))
+      return fail(h, GMG_ENOCONVERGENCE, "Iterative method reported convergence failure in step " + std::to_string(it));
+    if (int rc = dist_vcycle(h, d.g, d.hh)) return rc;
+    vec_dot<<<rg, 256, 0, h->stream>>>(n, d.g, d.hh, &h->scalars->gh[slot ^ 1], h->partials, h->counter);
+    GMG_LAUNCH_CHECK(h);
+    if (int rc = dist_allreduce1(h, &h->scalars->gh[slot ^ 1])) return rc;
+    slot ^= 1;
+    pcg_new_direction<<<cdiv(std::max(n, 1), 256), 256, 0, h->stream>>>(n, dd, d.hh, h->scalars, slot);
+    GMG_LAUNCH_CHECK(h);
+  }
+  return finish();
+}
+
+static void dist_free(gmg_context *h) {
+  DistData &d = h->dist;
+  free_distmat(d.S);
+  free_distmat(d.A0);
+  free_gather(d.gather_g);
+  free_gather(d.gather_c);
+  free_gather(d.gather_x);
+  free_sell(d.R0);
+  free_sell(d.P0F);
+  dfree(d.sys_owned_global);
+  dfree(d.copy0_sys);
+  dfree(d.copy0_l0);
+  for (auto p : d.from_sys) dfree(p);
+  for (auto p : d.from_lvl) dfree(p);
+  dfree(d.l0_defect);
+  dfree(d.l0_sol);
+  dfree(d.cg_g);
+  dfree(d.cg_h);
+  dfree(d.g);
+  dfree(d.hh);
+  dfree(d.cg_partials);
+  dfree(d.d_error);
+  for (int q = 0; q < d.world; ++q)
+    if (q != d.rank && d.peer[q]) cudaIpcCloseMemHandle(d.peer[q]);
+  if (d.buf) cudaFree(d.buf);
+  d = DistData{};
+}
+
+}  // namespace gmg
+
+extern "C" {
+
+int gmg_dist_init(gmg_handle h, int rank, int world, int64_t comm_bytes, void *ipc_handle_out) {
+  if (!h || world < 1 || world > DIST_MAX_RANKS || rank < 0 || rank >= world || !ipc_handle_out) return GMG_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  gmg::enter(h);
+  DistData &d = h->dist;
+  if (d.buf) return fail(h, GMG_EINVAL, "gmg_dist_init called twice");
+  d.rank = rank;
+  d.world = world;
+  d.bytes = (size_t)std::max<int64_t>(comm_bytes, (int64_t)DIST_HEADER_BYTES * 2);
+  GMG_CUDA(h, cudaMalloc((void **)&d.buf, d.bytes));  // plain cudaMalloc: pool memory cannot be IPC-exported
+  GMG_CUDA(h, cudaMemset(d.buf, 0, d.bytes));
+  GMG_CUDA(h, cudaDeviceSynchronize());
+  cudaIpcMemHandle_t hd;
+  GMG_CUDA(h, cudaIpcGetMemHandle(&hd, d.buf));
+  std::memcpy(ipc_handle_out, &hd, sizeof(hd));
+  GMG_CUDA(h, dalloc(&d.d_error, 1));
+  GMG_CUDA(h, cudaMemsetAsync(d.d_error, 0, sizeof(int), h->stream));
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  d.bump = DIST_HEADER_BYTES;
+  return GMG_OK;
+}
+
+int gmg_dist_connect(gmg_handle h, const void *all_handles) {
+  if (!h || !all_handles || !h->dist.buf) return GMG_EINVAL;
+  gmg::enter(h);
+  DistData &d = h->dist;
+  for (int q = 0; q < d.world; ++q) {
+    if (q == d.rank) {
+      d.peer[q] = d.buf;
+      continue;
+    }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, (const char *)all_handles + 64 * (size_t)q, sizeof(hd));
+    void *p = nullptr;
+    GMG_CUDA(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    d.peer[q] = (char *)p;
+  }
+  d.on = d.world > 1;
+  return GMG_OK;
+}
+
+int gmg_set_ownership(gmg_handle h, int which, int level, int32_t n, const int32_t *owner) {
+  if (!h || !owner || n < 0) return GMG_EINVAL;
+  if (which == GMG_SYSTEM) h->dist.sys_owner.assign(owner, owner + n);
+  else if (which == GMG_LEVEL && level == 0) h->dist.l0_owner.assign(owner, owner + n);
+  else return fail(h, GMG_EINVAL, "ownership is defined for the system matrix and level 0 (patch levels are replicated)");
+  h->is_setup = false;
+  return GMG_OK;
+}
+
+int gmg_dist_rank(gmg_handle h, int *rank, int *world) {
+  if (!h) return GMG_EINVAL;
+  if (rank) *rank = h->dist.rank;
+  if (world) *world = h->dist.world;
+  return GMG_OK;
+}
+
+// CPU-only probe of the partitioner (tests): local CSR + maps of `rank` in malloc'ed arrays (gmg_free_host)
+int gmg_partition_probe(int rank, int world, int32_t n_rows, const int64_t *rowptr, const int32_t *col, const double *val,
+                        const int32_t *owner, int32_t *n_owned, int32_t *n_halo, int64_t **l_rowptr, int32_t **l_col,
+                        double **l_val, int32_t **owned_global, int32_t **halo_global, int32_t **send_count,
+                        int32_t **send_idx, int32_t **send_dst_base) {
+  try {
+    LocalMatrix lm;
+    ExchangePlan pl;
+    partition_matrix(rank, world, n_rows, n_rows, rowptr, col, val, owner, owner, lm, pl);
+    auto dup = [](const auto &v, auto **out) {
+      using T = typename std::remove_reference<decltype(v[0])>::type;
+      using U = typename std::remove_const<T>::type;
+      *out = (U *)std::malloc(sizeof(U) * std::max<size_t>(v.size(), 1));
+      std::copy(v.begin(), v.end(), *out);
+    };
+    *n_owned = lm.n_owned;
+    *n_halo = lm.n_halo;
+    dup(lm.rowptr, l_rowptr);
+    dup(lm.col, l_col);
+    dup(lm.val, l_val);
+    dup(lm.owned_global, owned_global);
+    dup(lm.halo_global, halo_global);
+    std::vector<int32_t> cnt(world), flat;
+    for (int q = 0; q < world; ++q) {
+      cnt[q] = (int32_t)pl.send_idx[q].size();
+      flat.insert(flat.end(), pl.send_idx[q].begin(), pl.send_idx[q].end());
+    }
+    dup(cnt, send_count);
+    dup(flat, send_idx);
+    dup(pl.send_dst_base, send_dst_base);
+  } catch (std::exception &) {
+    return GMG_EINVAL;
+  }
+  return GMG_OK;
+}
+
+void gmg_free_host(void *p) { std::free(p); }
+
+}  // extern "C"

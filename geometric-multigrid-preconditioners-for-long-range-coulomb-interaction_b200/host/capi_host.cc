@@ -246,7 +246,8 @@ class BenchProblem : public Step50::LaplaceProblem<3> {
   double *b_dev = nullptr, *x_dev = nullptr, *x0_dev = nullptr;
   double tol = 0.0;
 
-  void prepare() {
+  // phase 1: all cycles but the last (single GPU per process), the last up to solve()
+  void prepare_cycles() {
     set_output(sink);
     begin_run();
     const unsigned int n = number_of_adaptive_refinement_cycles;
@@ -257,6 +258,9 @@ class BenchProblem : public Step50::LaplaceProblem<3> {
     }
     cycle_until_solve(n - 1);
     x0 = solution;  // transferred initial guess of the last cycle
+  }
+  // phase 2 (after the caller connected the ranks, if any): hierarchy of the last cycle onto the device(s)
+  void prepare() {
     hand_over_hierarchy();
     const int64_t nd = (int64_t)solution.size();
     gmg_check(gmg_vec_alloc(gmg, nd, &b_dev), "gmg_vec_alloc");
@@ -361,12 +365,18 @@ void *step50_bench_create(const char *prm_text) {
     prm.leave_subsection();
     bh->problem.reset(new BenchProblem(degree, prm, problem, pre, atoms, bc, left, right, hsize, vac, nref, cycles, rc,
                                        cutoff, f_rhs, false, false, false, false, qrhs));
-    bh->problem->prepare();
+    bh->problem->prepare_cycles();
     return bh;
   } catch (std::exception &e) {
     g_err = e.what();
     return nullptr;
   }
+}
+int step50_bench_finish_setup(void *p) {
+  try {
+    ((BenchHolder *)p)->problem->prepare();
+  } catch (std::exception &e) { g_err = e.what(); return -1; }
+  return 0;
 }
 void step50_bench_destroy(void *p) { delete (BenchHolder *)p; }
 void *step50_bench_gmg(void *p) { return (void *)((BenchHolder *)p)->problem->device(); }
@@ -393,6 +403,10 @@ int step50_bench_mesh(void *p, double *lo, double *H, int *reps) {
   BenchProblem &b = *((BenchHolder *)p)->problem;
   *lo = b.mesh_lo(); *H = b.mesh_H(); *reps = b.mesh_reps();
   return 0;
+}
+int step50_bench_download_x(void *p, double *out) {
+  BenchProblem &b = *((BenchHolder *)p)->problem;
+  return gmg_vec_download(b.device(), out, b.x_dev, (int64_t)b.sol().size());
 }
 int step50_bench_vectors(void *p, double *solution_out, double *rhs_out) {
   BenchProblem &b = *((BenchHolder *)p)->problem;

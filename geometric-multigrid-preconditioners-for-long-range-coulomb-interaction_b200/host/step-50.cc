@@ -425,6 +425,21 @@ void LaplaceProblem<dim>::hand_over_hierarchy() {
   const bool mg = PreconditionerType == "GMG";
   const int nl = mg ? triangulation->n_levels() : 1;
   gmg_check(gmg_set_num_levels(gmg, nl), "gmg_set_num_levels");
+  // multi-GPU: rows follow the z-slab of the base lattice their vertex lies in (the reference: p4est
+  // subdomains); a system dof and its level-0 twin share coordinates, hence the owner.  Patch levels are replicated.
+  int dist_rank = 0, dist_world = 1;
+  gmg_dist_rank(gmg, &dist_rank, &dist_world);
+  if (dist_world > 1) {
+    if (!mg) throw ExcMessage("the multi-GPU path implements the GMG preconditioner");
+    const int res = triangulation->resolution();
+    const int planes = triangulation->reps + 1;
+    auto slab = [&](int z_fine) { return std::min(dist_world - 1, (int)(((long)(z_fine >> res)) * dist_world / planes)); };
+    std::vector<int32_t> own_sys(d.n), own_l0(d.level_n[0]);
+    for (int i = 0; i < d.n; ++i) own_sys[i] = slab(d.xyz[i][2]);
+    for (int i = 0; i < d.level_n[0]; ++i) own_l0[i] = slab(d.level_xyz[0][i][2]);
+    gmg_check(gmg_set_ownership(gmg, GMG_SYSTEM, 0, d.n, own_sys.data()), "gmg_set_ownership");
+    gmg_check(gmg_set_ownership(gmg, GMG_LEVEL, 0, d.level_n[0], own_l0.data()), "gmg_set_ownership");
+  }
   auto set = [&](int which, int l, const Csr &m) {
     gmg_check(gmg_set_matrix(gmg, which, l, m.n_rows, m.n_cols, m.rowptr.data(), m.col.data(), m.val.data()),
               "gmg_set_matrix");

@@ -41,6 +41,8 @@ def lib():
         L.step50_bench_create.restype = C.c_void_p
         L.step50_bench_create.argtypes = [C.c_char_p]
         L.step50_bench_destroy.argtypes = [C.c_void_p]
+        L.step50_bench_finish_setup.argtypes = [C.c_void_p]
+        L.step50_bench_download_x.argtypes = [C.c_void_p, C.c_void_p]
         L.step50_bench_gmg.restype = C.c_void_p
         L.step50_bench_gmg.argtypes = [C.c_void_p]
         L.step50_bench_info.argtypes = [C.c_void_p, C.c_void_p]
@@ -158,20 +160,25 @@ def run_problem(prm_text):
 class BenchProblem:
     """LaplaceProblem advanced to the last refinement cycle, hierarchy on the device, ready to repeat the hot path."""
 
-    def __init__(self, prm_text):
+    def __init__(self, prm_text, connect=None):
+        """connect(gmg): optional callable that joins this rank's device context to its peers (multi-GPU) before the
+        hierarchy of the last cycle is handed over."""
         self.L = lib()
         self.p = self.L.step50_bench_create(prm_text.encode())
         if not self.p:
             raise HostError(self.L.ms_last_error().decode())
+        self.gmg = capi.Gmg.__new__(capi.Gmg)  # view of the problem's own device context (not owned)
+        self.gmg.lib = capi.load_library()
+        self.gmg.h = C.c_void_p(self.L.step50_bench_gmg(self.p))
+        self.gmg.close = lambda: None
+        if connect is not None:
+            connect(self.gmg)
+        _ck(self.L.step50_bench_finish_setup(self.p))
         info = np.zeros(16, dtype=np.int64)
         self.L.step50_bench_info(self.p, info.ctypes.data)
         self.n_dofs, self.n_cells, self.n_levels = int(info[0]), int(info[1]), int(info[2])
         self.level_n = [int(v) for v in info[3:3 + self.n_levels]]
         self.n_atoms, self.n_pairs, self.sys_nnz, self.nq = int(info[11]), int(info[12]), int(info[13]), int(info[14])
-        self.gmg = capi.Gmg.__new__(capi.Gmg)  # view of the problem's own device context (not owned)
-        self.gmg.lib = capi.load_library()
-        self.gmg.h = C.c_void_p(self.L.step50_bench_gmg(self.p))
-        self.gmg.close = lambda: None
 
     def close(self):
         if self.p:
@@ -187,6 +194,12 @@ class BenchProblem:
         its, res = C.c_int(0), C.c_double(0)
         _ck(self.L.step50_bench_step_host(self.p, int(with_hierarchy), C.byref(its), C.byref(res)))
         return its.value, res.value
+
+    def download_x(self):
+        """Solution of the last step_device() (device -> host)."""
+        out = np.zeros(self.n_dofs)
+        _ck(self.L.step50_bench_download_x(self.p, out.ctypes.data))
+        return out
 
     def get(self, name, level=0):
         return _fetch(self.L.step50_bench_get, self.p, name, level)

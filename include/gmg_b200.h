@@ -128,6 +128,26 @@ int gmg_coarse_profile(gmg_handle h, int reset, double *ms, int64_t *launches, i
 /* number of kernel launches issued by this handle since creation */
 int64_t gmg_launch_count(gmg_handle h);
 
+/* ---- multi-GPU (one process per GPU) -------------------------------------------------
+ * The reference distributes rows over MPI ranks (p4est subdomains; Epetra Import/Export halos,
+ * MPI_Allreduce dots).  Here every rank maps every peer's communication buffer (CUDA IPC over NVLink):
+ *   gmg_dist_init   allocate this rank's buffer, return its 64-byte IPC handle
+ *   (caller all-gathers the handles, e.g. torch.distributed / MPI)
+ *   gmg_dist_connect  map the peers
+ *   gmg_set_ownership owner rank of every row of the system matrix / of level 0 (patch levels >= 1 are
+ *                   replicated); then gmg_set_matrix / gmg_set_copy_indices / gmg_setup as usual with the
+ *                   GLOBAL matrices on every rank; gmg_pcg_solve(_dev) takes and returns global vectors. */
+int gmg_dist_init(gmg_handle h, int rank, int world, int64_t comm_bytes, void *ipc_handle_out /*64 B*/);
+int gmg_dist_connect(gmg_handle h, const void *all_handles /*world x 64 B*/);
+int gmg_set_ownership(gmg_handle h, int which, int level, int32_t n, const int32_t *owner);
+int gmg_dist_rank(gmg_handle h, int *rank, int *world);
+/* host-only probe of the row partitioner (CPU tests of the N > 1 logic); outputs malloc'ed, gmg_free_host */
+int gmg_partition_probe(int rank, int world, int32_t n_rows, const int64_t *rowptr, const int32_t *col,
+                        const double *val, const int32_t *owner, int32_t *n_owned, int32_t *n_halo,
+                        int64_t **l_rowptr, int32_t **l_col, double **l_val, int32_t **owned_global,
+                        int32_t **halo_global, int32_t **send_count, int32_t **send_idx, int32_t **send_dst_base);
+void gmg_free_host(void *p);
+
 /* ---- the RHS path ----------------------------------------------------------------------------- */
 /* rhs_assembly_optimization (src/step-50.cc:260-306): cell c lists atom i iff some vertex v of the
  * axis-aligned cube [lo_c, lo_c + h_c]^3 has ||X_i - v||_2 < radius (strict).  Output CSR with
