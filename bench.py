@@ -149,6 +149,8 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # control plane only (barriers, handle exchange, max over ranks of the timings): the data path is peer memory
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     P = pkg()
     P.load_library()

@@ -65,9 +65,10 @@ struct Level {
 struct DistMat {
   Sell A;
   int n_owned = 0, n_halo = 0, n_send = 0;
-  int *send_src = nullptr, *send_dst = nullptr;
+  int *send_src = nullptr, *send_dst = nullptr, *send_hpos = nullptr;
   unsigned char *send_peer = nullptr;
   uint32_t dst_mask = 0, src_mask = 0;
+  std::vector<int> h_send_src;  // host copy (sorted by source row)
 };
 
 // "push my owned entries of a list to every rank" (all-gather over peer memory)
@@ -91,7 +92,7 @@ struct DistData {
   HostCsr hS, hA0;
   std::vector<std::vector<int32_t>> h_copy_g, h_copy_l;  // copy indices as handed over (global numbering)
   DistMat S, A0;
-  size_t reg_cg_d = 0, reg_pcg_d = 0, reg_pcg_x = 0;
+  size_t reg_cg_d = 0, reg_cg_ll = 0, reg_pcg_d = 0, reg_pcg_x = 0;
   int n_sys_owned = 0, n_l0_owned = 0, n_sys = 0, n_l0 = 0;
   int *sys_owned_global = nullptr;      // device: global index of each owned system dof
   // copy_to_mg / copy_from_mg
@@ -108,6 +109,7 @@ struct DistData {
   double *l0_defect = nullptr, *l0_sol = nullptr, *cg_g = nullptr, *cg_h = nullptr;
   double *g = nullptr, *hh = nullptr;  // outer PCG owned vectors
   double *cg_partials = nullptr;
+  int *cg_send_block_ptr = nullptr;
 };
 
 }  // namespace gmg

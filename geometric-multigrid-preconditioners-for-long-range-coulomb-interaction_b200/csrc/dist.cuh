@@ -29,9 +29,11 @@ struct DistPeers {
 __device__ __forceinline__ void flag_store(uint64_t *p, uint64_t v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// polling uses relaxed loads: an acquire load at system scope is a load + a system-wide fence, and hundreds of
+// spinning warps issuing fences starve the very store they wait for; one fence follows the successful poll
 __device__ __forceinline__ uint64_t flag_load(const uint64_t *p) {
   uint64_t v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ uint64_t *dist_flag(char *base, int channel, int src_rank) {
@@ -45,9 +47,24 @@ __device__ __forceinline__ bool wait_flag(const uint64_t *p, uint64_t seq) {
   const long long t0 = clock64();
   while (flag_load(p) < seq) {
     if (clock64() - t0 > 40000000000LL) return false;  // ~20 s
-    __nanosleep(20);
+    __nanosleep(40);
   }
   return true;
+}
+// warp-collective: lanes q < world with bit q of `mask` wait for flag[channel][q] >= seq in the local buffer;
+// lane 0 then re-reads the flags and issues the acquire fence for the block (follow with __syncthreads/__syncwarp)
+__device__ __forceinline__ bool warp_wait_flags(char *mine, int channel, uint64_t seq, uint32_t mask, int world) {
+  const int lane = threadIdx.x & 31;
+  bool ok = true;
+  if (lane < world && (mask >> lane & 1u)) ok = wait_flag(dist_flag(mine, channel, lane), seq);
+  ok = __all_sync(0xffffffffu, ok);
+  if (lane == 0) {
+    for (int q = 0; q < world; ++q)
+      if (mask >> q & 1u) (void)flag_load(dist_flag(mine, channel, q));
+    __threadfence_system();
+  }
+  __syncwarp();
+  return ok;
 }
 
 // payload[t] -> peer's region ; then flags to every rank in dst_mask (even when there is no payload)
@@ -59,9 +76,9 @@ __global__ void __launch_bounds__(256) dist_push(DistPeers P, int n, const int *
   __shared__ bool last;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) reinterpret_cast<double *>(P.peer[dst_peer[t]] + region_off)[dst_idx[t]] = src[src_idx[t]];
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();  // release of this block's stores (cumulative over the barrier), gpu scope
     const unsigned int c = atomicInc(counter, gridDim.x - 1);
     last = (c == gridDim.x - 1);
   }
@@ -73,9 +90,7 @@ __global__ void __launch_bounds__(256) dist_push(DistPeers P, int n, const int *
 }
 
 __global__ void dist_wait(DistPeers P, int channel, uint64_t seq, uint32_t src_mask, int *error) {
-  const int q = threadIdx.x;
-  if (q < P.world && (src_mask >> q & 1u))
-    if (!wait_flag(dist_flag(P.peer[P.rank], channel, q), seq)) *error = 1;
+  if (!warp_wait_flags(P.peer[P.rank], channel, seq, src_mask, P.world) && threadIdx.x == 0) *error = 1;
 }
 
 // in-place sum over ranks of k <= 4 consecutive doubles at v (rank order: identical bits everywhere)
@@ -87,9 +102,8 @@ __global__ void dist_allreduce(DistPeers P, double *v, int k, uint64_t seq, int 
     for (int i = 0; i < k; ++i) slot[i] = v[i];
     __threadfence_system();
     flag_store(dist_flag(P.peer[q], CH_RED, P.rank), seq);
-    if (!wait_flag(dist_flag(P.peer[P.rank], CH_RED, q), seq)) *error = 1;
   }
-  __syncwarp();
+  if (!warp_wait_flags(P.peer[P.rank], CH_RED, seq, (1u << P.world) - 1u, P.world) && q == 0) *error = 1;
   if (q == 0)
     for (int i = 0; i < k; ++i) {
       double s = 0.0;
@@ -109,20 +123,46 @@ __global__ void vec_take(int n, const int *__restrict__ idx, const double *__res
   if (i < n) dst[i] = src[idx[i]];
 }
 
+// ---- "LL" words (as in NCCL's low-latency protocol): 8-byte stores carry 4 bytes of payload and a 4-byte tag,
+// so the payload needs no fence and no separate flag: a double travels as two tagged words in one 16-byte store.
+constexpr size_t DIST_OFF_LLRED = 4096;  // uint64 llred[2][8][2] in the header
+__device__ __forceinline__ void ll_store(uint64_t *p /*16-byte aligned pair*/, double v, uint32_t tag) {
+  const uint64_t bits = (uint64_t)__double_as_longlong(v);
+  const uint64_t w0 = ((uint64_t)tag << 32) | (bits & 0xffffffffull);
+  const uint64_t w1 = ((uint64_t)tag << 32) | (bits >> 32);
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
+}
+// spin until both words carry `tag`; false on timeout
+__device__ __forceinline__ bool ll_load(const uint64_t *p, uint32_t tag, double &v) {
+  const long long t0 = clock64();
+  uint64_t w0, w1;
+  while (true) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag) break;
+    if (clock64() - t0 > 40000000000LL) return false;
+  }
+  v = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+  return true;
+}
+
 struct DistCgArgs {
   DistPeers P;
+  int n_owned, n_halo;
   int n_send;
-  const int *send_src;
+  const int *send_src;          // sorted by source row
   const unsigned char *send_peer;
-  const int *send_dst;
+  const int *send_hpos;         // position in the destination's halo
+  const int *send_block_ptr;    // gridDim.x + 1: entries whose source row belongs to each block's slice range
   size_t region_d;     // symmetric offset of the extended direction vector d = [owned | halo]
-  uint32_t dst_mask, src_mask;
-  uint64_t seq_base;   // (launch id << 32): sequence numbers used inside the kernel are seq_base + counter
+  size_t region_ll;    // symmetric offset of the LL receive area: 16 bytes per halo entry
+  uint32_t tag_base;   // launch id * 2^20: tags used inside the kernel are tag_base + counter (never 0)
 };
 
 // ------------------------------------------------------------------------------------------------
 // distributed persistent CG: the single-GPU cg_persistent plus, inside the same cooperative kernel,
-// the halo push of d to the neighbours' extended vectors and the cross-GPU all-reduces of d.h and g.g.
+// the halo rows of d pushed straight into the neighbours (by the block that just updated them) and the
+// cross-GPU all-reduces of d.h and g.g, all as tagged LL words over NVLink: no fences, no flags, no extra
+// exchange kernels.  Per iteration: 3 grid.sync() exactly as on one GPU.
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) cg_persistent_dist(SellView A, const double *__restrict__ b, double *x, double *g,
@@ -131,7 +171,7 @@ __global__ void __launch_bounds__(BLOCK) cg_persistent_dist(SellView A, const do
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   __shared__ double red[32];
-  __shared__ int s_abort;
+  __shared__ double s_bc;
   const int nb = gridDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int WPB = BLOCK / 32;
@@ -139,60 +179,58 @@ __global__ void __launch_bounds__(BLOCK) cg_persistent_dist(SellView A, const do
   const int s_end = (int)(((int64_t)A.n_slices * (blockIdx.x + 1)) / nb);
   char *mine = D.P.peer[D.P.rank];
   double *d = reinterpret_cast<double *>(mine + D.region_d);
-  volatile double *gsum = reinterpret_cast<volatile double *>(mine + DIST_OFF_GSUM);
+  const uint64_t *ll_in = reinterpret_cast<const uint64_t *>(mine + D.region_ll);
+  uint32_t nred = 0, nhalo = 0;
+  // A wait that times out sets *error; control flow changes only at the check right after the NEXT grid.sync(),
+  // where every block reads the same value: no block ever leaves a barrier the others still need.
+  bool aborted = false;
   volatile int *abort_flag = error;
-  uint64_t nred = 0, nhalo = 0;
 
-  // sum over the grid and over the ranks; 2 grid syncs
+  // sum over the grid and over the ranks: 1 grid sync; block 0 publishes the local total to every rank,
+  // every block reads all ranks' totals (local memory) and adds them in rank order
   auto all_sum = [&](double block_value) -> double {
     if (threadIdx.x == 0) partials[blockIdx.x] = block_value;
     grid.sync();
+    if (*abort_flag) aborted = true;
+    if (aborted) return 0.0;
     ++nred;
-    const int slot = (int)(nred % 3);
-    if (blockIdx.x == 0 && warp == 0) {
-      const double s = warp_sum_partials(partials, nb);
-      const uint64_t seq = D.seq_base + nred;
-      const int par = (int)(seq & 1);
+    const uint32_t tag = D.tag_base + nred;
+    const int par = (int)(nred & 1);
+    if (warp == 0) {
+      if (blockIdx.x == 0) {
+        const double s = warp_sum_partials(partials, nb);
+        if (lane < D.P.world)
+          ll_store(reinterpret_cast<uint64_t *>(D.P.peer[lane] + DIST_OFF_LLRED) + (par * 8 + D.P.rank) * 2, s, tag);
+      }
+      double v = 0.0;
       bool ok = true;
-      if (lane < D.P.world) {
-        dist_red(D.P.peer[lane], par, D.P.rank, 1)[0] = s;
-        __threadfence_system();
-        flag_store(dist_flag(D.P.peer[lane], CH_CG_RED, D.P.rank), seq);
-        ok = wait_flag(dist_flag(mine, CH_CG_RED, lane), seq);
-      }
-      if (!ok) *abort_flag = 1;
-      __syncwarp();
-      if (lane == 0) {
-        double tot = 0.0;
-        for (int r = 0; r < D.P.world; ++r) tot += dist_red(mine, par, r, 1)[0];
-        gsum[slot] = tot;
-        __threadfence();
-      }
+      if (lane < D.P.world)
+        ok = ll_load(reinterpret_cast<const uint64_t *>(mine + DIST_OFF_LLRED) + (par * 8 + lane) * 2, tag, v);
+      if (!__all_sync(0xffffffffu, ok) && lane == 0) *abort_flag = 1;
+      double tot = 0.0;
+      for (int r = 0; r < D.P.world; ++r) tot += __shfl_sync(0xffffffffu, v, r);  // rank order
+      if (lane == 0) s_bc = tot;
     }
-    grid.sync();
-    return gsum[slot];
+    __syncthreads();
+    const double r = s_bc;
+    __syncthreads();
+    return r;
   };
-  // push my boundary values of d into the neighbours' halos and wait for theirs; 2 grid syncs
-  auto halo = [&]() {
+  // after this block's rows of d are written: push its boundary rows, then help unpacking the incoming halo
+  auto exchange_halo = [&]() {
     ++nhalo;
-    const uint64_t seq = D.seq_base + nhalo;
-    for (int t = blockIdx.x * BLOCK + threadIdx.x; t < D.n_send; t += nb * BLOCK)
-      reinterpret_cast<double *>(D.P.peer[D.send_peer[t]] + D.region_d)[D.send_dst[t]] = d[D.send_src[t]];
-    __threadfence_system();
-    grid.sync();
-    if (blockIdx.x == 0 && warp == 0 && lane < D.P.world) {
-      if (D.dst_mask >> lane & 1u) flag_store(dist_flag(D.P.peer[lane], CH_CG_HALO, D.P.rank), seq);
-      if (D.src_mask >> lane & 1u)
-        if (!wait_flag(dist_flag(mine, CH_CG_HALO, lane), seq)) *abort_flag = 1;
+    const uint32_t tag = D.tag_base + (1u << 19) + nhalo;
+    __syncthreads();
+    for (int t = D.send_block_ptr[blockIdx.x] + threadIdx.x; t < D.send_block_ptr[blockIdx.x + 1]; t += BLOCK)
+      ll_store(reinterpret_cast<uint64_t *>(D.P.peer[D.send_peer[t]] + D.region_ll) + 2 * (size_t)D.send_hpos[t],
+               d[D.send_src[t]], tag);
+    bool ok = true;
+    for (int k = blockIdx.x * BLOCK + threadIdx.x; k < D.n_halo; k += nb * BLOCK) {
+      double v;
+      if (ll_load(ll_in + 2 * (size_t)k, tag, v)) d[D.n_owned + k] = v;
+      else ok = false;
     }
-    grid.sync();
-  };
-  auto aborted = [&]() -> bool {
-    if (threadIdx.x == 0) s_abort = *abort_flag;
-    __syncthreads();
-    const int a = s_abort;
-    __syncthreads();
-    return a != 0;
+    if (!ok) *abort_flag = 1;
   };
 
   double acc = 0.0;
@@ -206,16 +244,16 @@ __global__ void __launch_bounds__(BLOCK) cg_persistent_dist(SellView A, const do
       acc += bv * bv;
     }
   }
+  exchange_halo();
   acc = block_sum(acc, red);
-  double res2 = all_sum(acc);
+  double res2 = all_sum(acc);  // its grid sync also publishes d (owned + halo) to every block
   double res = sqrt(res2);
   const double res0 = res;
   int it = 0, status = 0;
-  if (res > tol && !aborted()) {
+  if (aborted) status = 2;
+  if (res > tol && !aborted) {
     double gh = res * res;
-    halo();
     while (true) {
-      if (aborted()) { status = 2; break; }
       ++it;
       acc = 0.0;
       for (int s = s_begin + warp; s < s_end; s += WPB) {
@@ -228,6 +266,7 @@ __global__ void __launch_bounds__(BLOCK) cg_persistent_dist(SellView A, const do
       }
       acc = block_sum(acc, red);
       const double alpha = gh / all_sum(acc);
+      if (aborted) { status = 2; break; }
       acc = 0.0;
       for (int s = s_begin + warp; s < s_end; s += WPB) {
         const int r = s * 32 + lane;
@@ -241,6 +280,7 @@ __global__ void __launch_bounds__(BLOCK) cg_persistent_dist(SellView A, const do
       acc = block_sum(acc, red);
       res2 = all_sum(acc);
       res = sqrt(res2);
+      if (aborted) { status = 2; break; }
       if (res <= tol) break;
       if (it >= max_it) { status = 1; break; }
       const double beta = res2 / gh;
@@ -249,8 +289,10 @@ __global__ void __launch_bounds__(BLOCK) cg_persistent_dist(SellView A, const do
         const int r = s * 32 + lane;
         if (r < A.n_rows) d[r] = beta * d[r] - g[r];
       }
-      grid.sync();  // all of d written before anyone pushes / reads it
-      halo();
+      exchange_halo();
+      grid.sync();  // d (owned rows and unpacked halo) visible to every block
+      if (*abort_flag) aborted = true;
+      if (aborted) { status = 2; break; }
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {

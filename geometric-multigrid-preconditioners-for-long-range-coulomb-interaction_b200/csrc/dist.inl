@@ -74,6 +74,7 @@ static void free_distmat(DistMat &M) {
   dfree(M.send_src);
   dfree(M.send_dst);
   dfree(M.send_peer);
+  dfree(M.send_hpos);
   M = DistMat{};
 }
 static void free_gather(GatherPlan &G) {
@@ -110,6 +111,27 @@ static int build_distmat(gmg_context *h, const HostCsr &g, const std::vector<int
       speer.push_back((unsigned char)q);
     }
   }
+  {  // sort by source row: the persistent CG lets the block that owns a row push it
+    std::vector<int> order(ssrc.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ssrc[a] < ssrc[b]; });
+    std::vector<int> s2(ssrc.size()), d2(ssrc.size());
+    std::vector<unsigned char> p2(ssrc.size());
+    for (size_t i = 0; i < order.size(); ++i) {
+      s2[i] = ssrc[order[i]];
+      d2[i] = sdst[order[i]];
+      p2[i] = speer[order[i]];
+    }
+    ssrc.swap(s2);
+    sdst.swap(d2);
+    speer.swap(p2);
+  }
+  {
+    std::vector<int> hpos(ssrc.size());
+    for (size_t i = 0; i < hpos.size(); ++i) hpos[i] = sdst[i] - plan.n_owned_of[speer[i]];
+    if (int rc = to_device(h, M.send_hpos, hpos)) return rc;
+  }
+  M.h_send_src = ssrc;
   M.n_send = (int)ssrc.size();
   if (int rc = to_device(h, M.send_src, ssrc)) return rc;
   if (int rc = to_device(h, M.send_dst, sdst)) return rc;
@@ -160,6 +182,18 @@ static int dist_setup(gmg_context *h) {
   }
   d.n_sys_owned = lmS.n_owned;
   d.n_l0_owned = lmA.n_owned;
+  {  // send-list ranges per block of the persistent CG (same slice partition as the kernel)
+    const int nb = h->cg_grid, n_slices = d.A0.A.v.n_slices;
+    std::vector<int> bp(nb + 1, 0);
+    size_t t = 0;
+    for (int b = 0; b < nb; ++b) {
+      const int row_end = (int)(((int64_t)n_slices * (b + 1)) / nb) * 32;
+      while (t < d.A0.h_send_src.size() && d.A0.h_send_src[t] < row_end) ++t;
+      bp[b + 1] = (int)t;
+    }
+    bp[nb] = (int)d.A0.h_send_src.size();
+    if ((rc = to_device(h, d.cg_send_block_ptr, bp))) return rc;
+  }
   // symmetric extended vectors: size = max over ranks of owned + halo (every rank knows every size)
   int ext_sys = 0, ext_l0 = 0;
   for (int q = 0; q < d.world; ++q) {
@@ -169,6 +203,11 @@ static int dist_setup(gmg_context *h) {
   if ((rc = sym_alloc(h, sizeof(double) * (size_t)ext_sys, d.reg_pcg_x))) return rc;
   if ((rc = sym_alloc(h, sizeof(double) * (size_t)ext_sys, d.reg_pcg_d))) return rc;
   if ((rc = sym_alloc(h, sizeof(double) * (size_t)ext_l0, d.reg_cg_d))) return rc;
+  {
+    int halo_max = 0;
+    for (int q = 0; q < d.world; ++q) halo_max = std::max(halo_max, plA.n_halo_of[q]);
+    if ((rc = sym_alloc(h, 16 * (size_t)std::max(halo_max, 1), d.reg_cg_ll))) return rc;
+  }
   if ((rc = to_device(h, d.sys_owned_global, lmS.owned_global))) return rc;
   std::vector<int> sys_g2l(d.n_sys, -1), l0_g2l(d.n_l0, -1);
   for (int i = 0; i < lmS.n_owned; ++i) sys_g2l[lmS.owned_global[i]] = i;
@@ -283,14 +322,17 @@ static int dist_coarse_cg(gmg_context *h, const double *b, double *x) {
   SellView v = d.A0.A.v;
   DistCgArgs D;
   D.P = peers_of(h);
+  D.n_owned = d.A0.n_owned;
+  D.n_halo = d.A0.n_halo;
   D.n_send = d.A0.n_send;
   D.send_src = d.A0.send_src;
   D.send_peer = d.A0.send_peer;
-  D.send_dst = d.A0.send_dst;
+  D.send_hpos = d.A0.send_hpos;
+  D.send_block_ptr = d.cg_send_block_ptr;
   D.region_d = d.reg_cg_d;
-  D.dst_mask = d.A0.dst_mask;
-  D.src_mask = d.A0.src_mask;
-  D.seq_base = (++d.launch_id) << 32;
+  D.region_ll = d.reg_cg_ll;
+  D.tag_base = (uint32_t)(((++d.launch_id) & 0xfffu) << 20);  // tags stay unique for 4095 launches in a row, never 0
+  if (D.tag_base == 0) D.tag_base = (uint32_t)(((++d.launch_id) & 0xfffu) << 20);
   int max_it = h->coarse_max_it;
   double tol = h->coarse_tol;
   int grid = h->cg_grid;
@@ -466,6 +508,7 @@ static void dist_free(gmg_context *h) {
   dfree(d.g);
   dfree(d.hh);
   dfree(d.cg_partials);
+  dfree(d.cg_send_block_ptr);
   dfree(d.d_error);
   for (int q = 0; q < d.world; ++q)
     if (q != d.rank && d.peer[q]) cudaIpcCloseMemHandle(d.peer[q]);
