@@ -37,6 +37,7 @@ SIGNATURES = {
     "gmg_set_smoother": (_i, [_h, _i, _d, _i]),
     "gmg_set_coarse": (_i, [_h, _i, _d]),
     "gmg_set_drop_tolerance": (_i, [_h, _d]),
+    "gmg_set_compression": (_i, [_h, _i]),
     "gmg_setup": (_i, [_h]),
     "gmg_pcg_solve": (_i, [_h, _pd, _pd, _i, _d, C.POINTER(_i), _pd, _pd]),
     "gmg_pcg_solve_jacobi": (_i, [_h, _pd, _pd, _d, _i, _d, C.POINTER(_i), _pd, _pd]),
@@ -168,6 +169,9 @@ class Gmg:
     def set_coarse(self, max_it=1000, tol=1e-10):
         self._ck(self.lib.gmg_set_coarse(self.h, max_it, tol))
 
+    def set_compression(self, on):
+        self._ck(self.lib.gmg_set_compression(self.h, int(on)))
+
     def set_drop_tolerance(self, tol):
         self._ck(self.lib.gmg_set_drop_tolerance(self.h, tol))
 
@@ -271,9 +275,10 @@ class Gmg:
         return it.value, r.value
 
     def matrix_traffic(self, which, level=0):
-        out = np.zeros(3)
+        out = np.zeros(6)
         self._ck(self.lib.gmg_matrix_traffic(self.h, which, level, _pd_of(out)))
-        return dict(nnz=out[0], spmv_bytes=out[1], cg_iter_bytes=out[2])
+        return dict(nnz=out[0], spmv_bytes=out[1], cg_iter_bytes=out[2], csr_spmv_bytes=out[3], csr_cg_iter_bytes=out[4],
+                    compressed=bool(out[5]))
 
     def coarse_profile(self, reset=True):
         ms, n, it = _d(0), _i64(0), _i64(0)
@@ -403,8 +408,9 @@ def partition_probe(rank, world, csr, owner):
     rowptr = take(l_rp, no + 1, np.int64)
     nnz = int(rowptr[-1])
     out = dict(n_owned=no, n_halo=nh, rowptr=rowptr, col=take(l_col, nnz, np.int32), val=take(l_val, nnz, np.float64),
-               owned_global=take(og, no, np.int32), halo_global=take(hg, nh, np.int32), send_count=take(sc, world, np.int32),
-               send_dst_base=take(sb, world, np.int32))
+               owned_global=take(og, no, np.int32), halo_global=take(hg, nh, np.int32), send_dst_base=take(sb, world, np.int32))
+    sc_all = take(sc, world + 1, np.int32)
+    out["send_count"], out["n_halo_lo"] = sc_all[:world], int(sc_all[world])
     out["send_idx"] = take(si, int(out["send_count"].sum()), np.int32)
     for p in (l_rp, l_col, l_val, og, hg, sc, si, sb):
         lib.gmg_free_host(C.cast(p, C.c_void_p))

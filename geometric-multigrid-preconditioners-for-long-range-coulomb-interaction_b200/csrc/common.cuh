@@ -101,6 +101,18 @@ struct SellView {
   const int *col;
 };
 
+// Compressed sliced ELL ("CSELL"): lossless 4-byte entries = 16-bit dictionary code of the fp64 value
+// + signed 16-bit column offset from the row.  FE matrices on (mostly) uniform levels have a handful of
+// distinct values and a bounded bandwidth, so 12 bytes per entry shrink to 4.  Same slice layout as SELL
+// but 4 entries per 128-bit lane load: lane L reads chunk p at ent4[slice_ptr/4 + 32 p + L].
+struct CsellView {
+  int n_rows, n_cols, n_slices;
+  const int64_t *slice_ptr;   // n_slices + 1 entry offsets (multiples of 128)
+  const uint32_t *ent;        // (code << 16) | (uint16)(col - row)
+  const double *dict;
+  int dict_n;
+};
+
 struct PcgScalars {
   double gh[2];   // g.h, double-buffered (beta = gh[new] / gh[old])
   double dh;      // d.(A d)

@@ -6,6 +6,7 @@
 
 #include "context.h"
 #include "kernels.cuh"
+// (dist.cuh uses RowDot / CSELL_SMEM_DICT from kernels.cuh)
 #include "dist.cuh"
 
 using namespace gmg;
@@ -25,6 +26,9 @@ static void free_sell(Sell &s) {
   dfree(s.slice_ptr);
   dfree(s.val);
   dfree(s.col);
+  dfree(s.cslice_ptr);
+  dfree(s.ent);
+  dfree(s.dict);
   s = Sell{};
 }
 static void free_csr(DevCsr &c) {
@@ -103,7 +107,98 @@ static int build_sell(gmg_context *h, const DevCsr &c, double drop_tol, Sell &ou
   dfree(width);
   dfree(row_nnz);
   out.v = SellView{c.n_rows, c.n_cols, n_slices, out.slice_ptr, out.val, out.col};
+  out.h_slice_ptr = sp;
   out.valid = true;
+  return GMG_OK;
+}
+
+// Lossless compressed copy (CSELL) of a square SELL matrix: value dictionary + 16-bit column offsets.
+// Leaves s.compressed == false when the matrix does not qualify (too many distinct values / too wide).
+static int build_csell(gmg_context *h, Sell &s) {
+  s.compressed = false;
+  if (!s.valid || s.v.n_rows > s.v.n_cols || s.v.n_slices == 0) return GMG_OK;  // (rank-local blocks: n_cols = owned + halo)
+  TraceScope tr("    csell");
+  constexpr int LOG_TABLE = 17, LIMIT = 60000;
+  const int mask = (1 << LOG_TABLE) - 1;
+  unsigned long long *table = nullptr;
+  int *d_count = nullptr;
+  unsigned short *slot_code = nullptr;
+  GMG_CUDA(h, dalloc(&table, (int64_t)mask + 1));
+  GMG_CUDA(h, dalloc(&d_count, 2));
+  GMG_CUDA(h, cudaMemsetAsync(table, 0, sizeof(unsigned long long) * ((size_t)mask + 1), h->stream));
+  GMG_CUDA(h, cudaMemsetAsync(d_count, 0, 2 * sizeof(int), h->stream));
+  value_set_insert<<<cdiv(s.padded, 256), 256, 0, h->stream>>>(s.padded, s.val, table, mask, d_count, LIMIT);
+  GMG_LAUNCH_CHECK(h);
+  int count = 0;
+  GMG_CUDA(h, copy_sync(h, &count, d_count, sizeof(int), cudaMemcpyDeviceToHost));
+  auto cleanup = [&]() {
+    dfree(table);
+    dfree(d_count);
+    dfree(slot_code);
+  };
+  if (count > LIMIT) {
+    cleanup();
+    return GMG_OK;
+  }
+  std::vector<unsigned long long> ht((size_t)mask + 1);
+  GMG_CUDA(h, copy_sync(h, ht.data(), table, sizeof(unsigned long long) * ht.size(), cudaMemcpyDeviceToHost));
+  std::vector<std::pair<double, int>> vals;  // (value, slot)
+  for (int i = 0; i <= mask; ++i)
+    if (ht[i] != 0ull) {
+      const unsigned long long bits = ht[i] - 1ull;
+      double v;
+      std::memcpy(&v, &bits, sizeof v);
+      vals.emplace_back(v, i);
+    }
+  std::sort(vals.begin(), vals.end(), [](auto &a, auto &b) {
+    unsigned long long x, y;
+    std::memcpy(&x, &a.first, 8);
+    std::memcpy(&y, &b.first, 8);
+    return x < y;
+  });
+  std::vector<double> dict(vals.size());
+  std::vector<unsigned short> codes((size_t)mask + 1, 0);
+  int zero_code = -1;
+  for (size_t k = 0; k < vals.size(); ++k) {
+    dict[k] = vals[k].first;
+    codes[vals[k].second] = (unsigned short)k;
+    unsigned long long bits;
+    std::memcpy(&bits, &vals[k].first, 8);
+    if (bits == 0ull) zero_code = (int)k;
+  }
+  if (zero_code < 0) {
+    zero_code = (int)dict.size();
+    dict.push_back(0.0);
+  }
+  // slice widths rounded up to 4 entries per row
+  const int ns = s.v.n_slices;
+  std::vector<int64_t> csp(ns + 1, 0);
+  for (int i = 0; i < ns; ++i) {
+    const int64_t w = (s.h_slice_ptr[i + 1] - s.h_slice_ptr[i]) / SLICE;
+    csp[i + 1] = csp[i] + ((w + 3) / 4) * 4 * SLICE;
+  }
+  s.cpadded = csp[ns];
+  GMG_CUDA(h, dalloc(&slot_code, (int64_t)codes.size()));
+  GMG_CUDA(h, copy(h, slot_code, codes.data(), sizeof(unsigned short) * codes.size(), cudaMemcpyHostToDevice));
+  GMG_CUDA(h, dalloc(&s.cslice_ptr, ns + 1));
+  GMG_CUDA(h, copy(h, s.cslice_ptr, csp.data(), sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice));
+  GMG_CUDA(h, dalloc(&s.dict, (int64_t)dict.size()));
+  GMG_CUDA(h, copy(h, s.dict, dict.data(), sizeof(double) * dict.size(), cudaMemcpyHostToDevice));
+  GMG_CUDA(h, dalloc(&s.ent, s.cpadded));
+  sell_to_csell<<<cdiv((int64_t)ns * 32, 256), 256, 0, h->stream>>>(s.v, s.cslice_ptr, table, slot_code, mask,
+                                                                    (unsigned short)zero_code, s.ent, d_count + 1);
+  GMG_LAUNCH_CHECK(h);
+  int flags[2] = {0, 0};
+  GMG_CUDA(h, copy_sync(h, flags, d_count, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+  cleanup();
+  if (flags[1] != 0) {  // a column offset does not fit 16 bits: keep the plain format
+    dfree(s.cslice_ptr);
+    dfree(s.ent);
+    dfree(s.dict);
+    return GMG_OK;
+  }
+  s.cv = CsellView{s.v.n_rows, s.v.n_cols, ns, s.cslice_ptr, s.ent, s.dict, (int)dict.size()};
+  s.compressed = true;
   return GMG_OK;
 }
 
@@ -287,13 +382,21 @@ static int coarse_cg(gmg_context *h, const Sell &A, const double *b, double *x, 
   h->cg_cursor++;
   CgResult *res = h->cg_results + slot;
   SellView v = A.v;
-  void *args[] = {&v, (void *)&b, &x, &h->cg_g, &h->cg_d, &h->cg_h, &h->cg_partials, &max_it, &tol, &res};
+  CsellView cv = A.cv;
+  const bool comp = A.compressed && h->compress;
+  void *args[] = {comp ? (void *)&cv : (void *)&v, (void *)&b, &x, &h->cg_g, &h->cg_d, &h->cg_h, &h->cg_partials, &max_it,
+                  &tol, &res};
   int ev = -1;
   if (h->ev_used < (int)h->ev_begin.size()) {
     ev = h->ev_used++;
     cudaEventRecord(h->ev_begin[ev], h->stream);
   }
-  GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent<512>, dim3(h->cg_grid), dim3(512), args, 0, h->stream));
+  if (comp)
+    GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent<512, CsellView>, dim3(h->cg_grid_c), dim3(512), args, 0,
+                                            h->stream));
+  else
+    GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent<512, SellView>, dim3(h->cg_grid), dim3(512), args, 0,
+                                            h->stream));
   h->launches++;
   if (ev >= 0) {
     cudaEventRecord(h->ev_end[ev], h->stream);
@@ -575,9 +678,14 @@ int gmg_create(int device, gmg_handle *out) {
     cudaMemset(h->scalars, 0, sizeof(PcgScalars));
     cudaMemset(h->cg_results, 0, sizeof(CgResult) * h->cg_ring);
     int per_sm = 0;
-    ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent<512>, 512, 0) == cudaSuccess && per_sm > 0;
+    ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent<512, SellView>, 512, 0) == cudaSuccess &&
+         per_sm > 0;
     h->cg_grid = h->sm_count * std::max(per_sm, 1);
-    ok = ok && dalloc(&h->cg_partials, 3 * h->cg_grid) == cudaSuccess;
+    int per_sm_c = 0;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, cg_persistent<512, CsellView>, 512, 0) == cudaSuccess &&
+         per_sm_c > 0;
+    h->cg_grid_c = h->sm_count * std::max(per_sm_c, 1);
+    ok = ok && dalloc(&h->cg_partials, 3 * std::max(h->cg_grid, h->cg_grid_c)) == cudaSuccess;
     h->ev_begin.resize(512);
     h->ev_end.resize(512);
     h->ev_result_slot.resize(512);
@@ -729,6 +837,12 @@ int gmg_set_coarse(gmg_handle h, int max_it, double abs_tol) {
   return GMG_OK;
 }
 
+int gmg_set_compression(gmg_handle h, int on) {
+  if (!h) return GMG_EINVAL;
+  h->compress = on != 0;
+  return GMG_OK;
+}
+
 int gmg_set_drop_tolerance(gmg_handle h, double drop_tol) {
   if (!h) return GMG_EINVAL;
   h->drop_tol = drop_tol;
@@ -776,6 +890,8 @@ int gmg_setup(gmg_handle h) {
       }
     }
     if (!L.A.valid) return fail(h, GMG_EINVAL, "level matrix missing on level " + std::to_string(l));
+    if (l == 0 && h->compress && !L.A.compressed)
+      if ((rc = build_csell(h, L.A))) return rc;
     TraceScope trv("    vectors");
     for (double **p : {&L.defect, &L.sol, &L.t, &L.tmp}) {
       dfree(*p);
@@ -1141,8 +1257,16 @@ int gmg_matrix_traffic(gmg_handle h, int which, int level, double out[3]) {
   if (!A) return fail(h, GMG_EINVAL, "matrix not available");
   const double nnz = (double)A->stored_nnz, n = (double)A->v.n_rows;
   out[0] = nnz;
-  out[1] = 12.0 * nnz + 4.0 * (n + 1.0) + 16.0 * n;  // CSR-equivalent algorithmic bytes
-  out[2] = out[1] + 72.0 * n;                         // + x,d,g,h reads and x,g,d writes of one CG iteration
+  out[3] = 12.0 * nnz + 4.0 * (n + 1.0) + 16.0 * n;  // CSR-equivalent algorithmic bytes of one SpMV
+  out[4] = out[3] + 72.0 * n;                         // + x,d,g,h reads and x,g,d writes of one CG iteration
+  out[5] = (A->compressed && h->compress) ? 1.0 : 0.0;
+  if (out[5] != 0.0) {  // bytes of the format actually streamed: 4-byte entries (padded to 4 per row) + slice pointers
+    out[1] = 4.0 * (double)A->cpadded + 8.0 * (A->v.n_slices + 1.0) + 8.0 * A->cv.dict_n + 16.0 * n;
+    out[2] = out[1] + 72.0 * n;
+  } else {
+    out[1] = out[3];
+    out[2] = out[4];
+  }
   return GMG_OK;
 }
 

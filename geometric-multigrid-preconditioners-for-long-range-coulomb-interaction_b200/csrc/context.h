@@ -39,6 +39,14 @@ struct Sell {
   int64_t stored_nnz = 0;  // entries kept from the CSR (explicit zeros included unless dropped)
   int64_t padded = 0;      // elements in the sliced-ELL arrays
   bool valid = false;
+  std::vector<int64_t> h_slice_ptr;
+  // optional lossless compressed copy (CsellView): 4 bytes per entry
+  bool compressed = false;
+  CsellView cv{};
+  int64_t *cslice_ptr = nullptr;
+  uint32_t *ent = nullptr;
+  double *dict = nullptr;
+  int64_t cpadded = 0;
 };
 
 struct ColorSet {
@@ -64,7 +72,7 @@ struct Level {
 // one distributed (row-partitioned) matrix: local SELL over [owned | halo] columns + its halo send lists
 struct DistMat {
   Sell A;
-  int n_owned = 0, n_halo = 0, n_send = 0;
+  int n_owned = 0, n_halo = 0, n_halo_lo = 0, n_send = 0;
   int *send_src = nullptr, *send_dst = nullptr, *send_hpos = nullptr;
   unsigned char *send_peer = nullptr;
   uint32_t dst_mask = 0, src_mask = 0;
@@ -110,6 +118,7 @@ struct DistData {
   double *g = nullptr, *hh = nullptr;  // outer PCG owned vectors
   double *cg_partials = nullptr;
   int *cg_send_block_ptr = nullptr;
+  int cg_grid = 0;
 };
 
 }  // namespace gmg
@@ -141,6 +150,8 @@ struct gmg_context {
   int coarse_max_it = 1000;
   double coarse_tol = 1e-10;
   double drop_tol = -1.0;
+  bool compress = true;  // build the compressed copy of the coarse-level matrix when it qualifies
+  int cg_grid_c = 0;     // cooperative grid of the compressed-format CG kernel
   bool is_setup = false;
 
   // reductions

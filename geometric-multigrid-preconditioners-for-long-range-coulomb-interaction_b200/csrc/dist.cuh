@@ -147,13 +147,13 @@ __device__ __forceinline__ bool ll_load(const uint64_t *p, uint32_t tag, double 
 
 struct DistCgArgs {
   DistPeers P;
-  int n_owned, n_halo;
+  int n_owned, n_halo, n_halo_lo;
   int n_send;
   const int *send_src;          // sorted by source row
   const unsigned char *send_peer;
   const int *send_hpos;         // position in the destination's halo
   const int *send_block_ptr;    // gridDim.x + 1: entries whose source row belongs to each block's slice range
-  size_t region_d;     // symmetric offset of the extended direction vector d = [owned | halo]
+  size_t region_d;     // symmetric offset of the extended direction vector [lower halo | owned | upper halo]
   size_t region_ll;    // symmetric offset of the LL receive area: 16 bytes per halo entry
   uint32_t tag_base;   // launch id * 2^20: tags used inside the kernel are tag_base + counter (never 0)
 };
@@ -164,21 +164,25 @@ struct DistCgArgs {
 // cross-GPU all-reduces of d.h and g.g, all as tagged LL words over NVLink: no fences, no flags, no extra
 // exchange kernels.  Per iteration: 3 grid.sync() exactly as on one GPU.
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) cg_persistent_dist(SellView A, const double *__restrict__ b, double *x, double *g,
+template <int BLOCK, class MAT>
+__global__ void __launch_bounds__(BLOCK) cg_persistent_dist(MAT A, const double *__restrict__ b, double *x, double *g,
                                                             double *h, double *partials, int max_it, double tol,
                                                             CgResult *result, DistCgArgs D, int *error) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   __shared__ double red[32];
   __shared__ double s_bc;
+  __shared__ double sdict[std::is_same<MAT, CsellView>::value ? CSELL_SMEM_DICT : 1];
+  RowDot<MAT> row_dot;
+  row_dot.init(A, sdict);
   const int nb = gridDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int WPB = BLOCK / 32;
   const int s_begin = (int)(((int64_t)A.n_slices * blockIdx.x) / nb);
   const int s_end = (int)(((int64_t)A.n_slices * (blockIdx.x + 1)) / nb);
   char *mine = D.P.peer[D.P.rank];
-  double *d = reinterpret_cast<double *>(mine + D.region_d);
+  double *d_ext = reinterpret_cast<double *>(mine + D.region_d);
+  double *d = d_ext + D.n_halo_lo;  // first owned entry; lower-rank halo entries sit at negative indices
   const uint64_t *ll_in = reinterpret_cast<const uint64_t *>(mine + D.region_ll);
   uint32_t nred = 0, nhalo = 0;
   // A wait that times out sets *error; control flow changes only at the check right after the NEXT grid.sync(),
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(BLOCK) cg_persistent_dist(SellView A, const do
     bool ok = true;
     for (int k = blockIdx.x * BLOCK + threadIdx.x; k < D.n_halo; k += nb * BLOCK) {
       double v;
-      if (ll_load(ll_in + 2 * (size_t)k, tag, v)) d[D.n_owned + k] = v;
+      if (ll_load(ll_in + 2 * (size_t)k, tag, v)) d_ext[k < D.n_halo_lo ? k : k + D.n_owned] = v;
       else ok = false;
     }
     if (!ok) *abort_flag = 1;
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(BLOCK) cg_persistent_dist(SellView A, const do
       ++it;
       acc = 0.0;
       for (int s = s_begin + warp; s < s_end; s += WPB) {
-        const double ad = sell_row_dot<false>(A, s, lane, d);
+        const double ad = row_dot(A, s, lane, d);
         const int r = s * 32 + lane;
         if (r < A.n_rows) {
           h[r] = ad;

@@ -60,7 +60,7 @@ static int dist_exchange(gmg_context *h, int n_send, const int *send_src, const 
 }
 
 static int dist_halo(gmg_context *h, const DistMat &M, size_t region, int channel) {
-  const double *src = reinterpret_cast<const double *>(h->dist.buf + region);
+  const double *src = reinterpret_cast<const double *>(h->dist.buf + region) + M.n_halo_lo;  // owned part
   return dist_exchange(h, M.n_send, M.send_src, M.send_peer, M.send_dst, region, src, channel, M.dst_mask, M.src_mask);
 }
 
@@ -99,6 +99,7 @@ static int build_distmat(gmg_context *h, const HostCsr &g, const std::vector<int
   if (int rc = build_sell_host(h, loc, h->drop_tol, M.A)) return rc;
   M.n_owned = lm.n_owned;
   M.n_halo = lm.n_halo;
+  M.n_halo_lo = lm.n_halo_lo;
   std::vector<int> ssrc, sdst;
   std::vector<unsigned char> speer;
   for (int q = 0; q < d.world; ++q) {
@@ -128,7 +129,8 @@ static int build_distmat(gmg_context *h, const HostCsr &g, const std::vector<int
   }
   {
     std::vector<int> hpos(ssrc.size());
-    for (size_t i = 0; i < hpos.size(); ++i) hpos[i] = sdst[i] - plan.n_owned_of[speer[i]];
+    for (size_t i = 0; i < hpos.size(); ++i)
+      hpos[i] = sdst[i] - (d.rank > (int)speer[i] ? plan.n_owned_of[speer[i]] : 0);
     if (int rc = to_device(h, M.send_hpos, hpos)) return rc;
   }
   M.h_send_src = ssrc;
@@ -182,8 +184,18 @@ static int dist_setup(gmg_context *h) {
   }
   d.n_sys_owned = lmS.n_owned;
   d.n_l0_owned = lmA.n_owned;
+  if (h->compress)
+    if ((rc = build_csell(h, d.A0.A))) return rc;  // note: offsets into [owned | halo] must fit 16 bits, else plain SELL
+  {
+    int per_sm = 0;
+    const bool comp = d.A0.A.compressed && h->compress;
+    cudaError_t e = comp ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_dist<512, CsellView>, 512, 0)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_dist<512, SellView>, 512, 0);
+    if (e != cudaSuccess || per_sm < 1) return fail(h, GMG_ECUDA, "occupancy query of the distributed CG kernel failed");
+    d.cg_grid = h->sm_count * per_sm;
+  }
   {  // send-list ranges per block of the persistent CG (same slice partition as the kernel)
-    const int nb = h->cg_grid, n_slices = d.A0.A.v.n_slices;
+    const int nb = d.cg_grid, n_slices = d.A0.A.v.n_slices;
     std::vector<int> bp(nb + 1, 0);
     size_t t = 0;
     for (int b = 0; b < nb; ++b) {
@@ -308,7 +320,7 @@ static int dist_setup(gmg_context *h) {
     GMG_CUDA(h, dalloc(p, d.n_sys_owned));
   }
   dfree(d.cg_partials);
-  GMG_CUDA(h, dalloc(&d.cg_partials, h->cg_grid));
+  GMG_CUDA(h, dalloc(&d.cg_partials, d.cg_grid));
   GMG_CUDA(h, cudaMemsetAsync(d.buf + DIST_HEADER_BYTES, 0, d.bump - DIST_HEADER_BYTES, h->stream));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return GMG_OK;
@@ -320,10 +332,13 @@ static int dist_coarse_cg(gmg_context *h, const double *b, double *x) {
   h->cg_cursor++;
   CgResult *res = h->cg_results + slot;
   SellView v = d.A0.A.v;
+  CsellView cv = d.A0.A.cv;
+  const bool comp = d.A0.A.compressed && h->compress;
   DistCgArgs D;
   D.P = peers_of(h);
   D.n_owned = d.A0.n_owned;
   D.n_halo = d.A0.n_halo;
+  D.n_halo_lo = d.A0.n_halo_lo;
   D.n_send = d.A0.n_send;
   D.send_src = d.A0.send_src;
   D.send_peer = d.A0.send_peer;
@@ -335,14 +350,20 @@ static int dist_coarse_cg(gmg_context *h, const double *b, double *x) {
   if (D.tag_base == 0) D.tag_base = (uint32_t)(((++d.launch_id) & 0xfffu) << 20);
   int max_it = h->coarse_max_it;
   double tol = h->coarse_tol;
-  int grid = h->cg_grid;
-  void *args[] = {&v, (void *)&b, &x, &d.cg_g, &d.cg_h, &d.cg_partials, &max_it, &tol, &res, &D, &d.d_error};
+  int grid = d.cg_grid;
+  void *args[] = {comp ? (void *)&cv : (void *)&v, (void *)&b, &x, &d.cg_g, &d.cg_h, &d.cg_partials, &max_it, &tol, &res, &D,
+                  &d.d_error};
   int ev = -1;
   if (h->ev_used < (int)h->ev_begin.size()) {
     ev = h->ev_used++;
     cudaEventRecord(h->ev_begin[ev], h->stream);
   }
-  GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_dist<512>, dim3(grid), dim3(512), args, 0, h->stream));
+  if (comp)
+    GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_dist<512, CsellView>, dim3(grid), dim3(512), args, 0,
+                                            h->stream));
+  else
+    GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_dist<512, SellView>, dim3(grid), dim3(512), args, 0,
+                                            h->stream));
   h->launches++;
   if (ev >= 0) {
     cudaEventRecord(h->ev_end[ev], h->stream);
@@ -418,8 +439,9 @@ static int dist_pcg(gmg_context *h, const double *b_global, double *x_global, in
   DistData &d = h->dist;
   const int n = d.n_sys_owned;
   h->cg_solve_begin = h->cg_cursor;
-  double *x = reinterpret_cast<double *>(d.buf + d.reg_pcg_x);
-  double *dd = reinterpret_cast<double *>(d.buf + d.reg_pcg_d);
+  // extended vectors [lower halo | owned | upper halo]; kernels address them from the first owned entry
+  double *x = reinterpret_cast<double *>(d.buf + d.reg_pcg_x) + d.S.n_halo_lo;
+  double *dd = reinterpret_cast<double *>(d.buf + d.reg_pcg_d) + d.S.n_halo_lo;
   double *bl = h->hh;  // owned part of b (h->hh has global length >= owned)
   PcgScalars hs;
   const int tg = cdiv(std::max(n, 1), 256);
@@ -599,11 +621,12 @@ int gmg_partition_probe(int rank, int world, int32_t n_rows, const int64_t *rowp
     dup(lm.val, l_val);
     dup(lm.owned_global, owned_global);
     dup(lm.halo_global, halo_global);
-    std::vector<int32_t> cnt(world), flat;
+    std::vector<int32_t> cnt(world + 1), flat;  // cnt[world] = n_halo_lo
     for (int q = 0; q < world; ++q) {
       cnt[q] = (int32_t)pl.send_idx[q].size();
       flat.insert(flat.end(), pl.send_idx[q].begin(), pl.send_idx[q].end());
     }
+    cnt[world] = lm.n_halo_lo;
     dup(cnt, send_count);
     dup(flat, send_idx);
     dup(pl.send_dst_base, send_dst_base);

@@ -6,6 +6,8 @@
 // pair p at  val2[slice_ptr/2 + p*32 + L]  -- every warp-wide load is one fully coalesced 512 B
 // (values) / 256 B (columns) transaction, 128-bit per lane.  Padding entries have value 0.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace gmg {
@@ -53,6 +55,103 @@ __device__ __forceinline__ double sell_row_dot(const SellView &A, int slice, int
     acc = fma(v.y, ldx<NC>(x, c.y), acc);
   }
   return acc;
+}
+
+// ---- compressed format ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// sum_j a_rj x_j for row (slice, lane) of a CSELL matrix; `dict` points at the value dictionary (shared or global).
+// Same entry order and the same FMA chain as sell_row_dot: bit-identical results.
+template <bool NC>
+__device__ __forceinline__ double csell_row_dot(const CsellView &A, int slice, int lane, const double *__restrict__ x,
+                                                const double *__restrict__ dict) {
+  const int64_t b = A.slice_ptr[slice];
+  const int nchunks = (int)((A.slice_ptr[slice + 1] - b) >> 7);
+  const uint4 *e4 = reinterpret_cast<const uint4 *>(A.ent) + (b >> 2) + lane;
+  const int row = slice * 32 + lane;
+  if (row >= A.n_rows) return 0.0;  // lanes past the last row of the last slice: their offsets are relative to nothing
+  double acc = 0.0;
+  int p = 0;
+  for (; p + 2 <= nchunks; p += 2) {
+    const uint4 e0 = ld_stream_u4(e4 + p * 32);
+    const uint4 e1 = ld_stream_u4(e4 + (p + 1) * 32);
+    const uint32_t w[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+    double xv[8], av[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      xv[u] = ldx<NC>(x, row + (int)(short)(w[u] & 0xffffu));
+      av[u] = dict[w[u] >> 16];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc = fma(av[u], xv[u], acc);
+  }
+  for (; p < nchunks; ++p) {
+    const uint4 e0 = ld_stream_u4(e4 + p * 32);
+    const uint32_t w[4] = {e0.x, e0.y, e0.z, e0.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc = fma(dict[w[u] >> 16], ldx<NC>(x, row + (int)(short)(w[u] & 0xffffu)), acc);
+  }
+  return acc;
+}
+
+// open-addressing set of fp64 bit patterns (distinct matrix values); table size is a power of two
+__global__ void value_set_insert(int64_t n, const double *__restrict__ val, unsigned long long *table, int mask,
+                                 int *count, int limit) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = (unsigned long long)__double_as_longlong(val[i]) + 1ull;  // 0 = empty slot
+  unsigned int hsh = (unsigned int)((key * 0x9E3779B97F4A7C15ull) >> 40) & mask;
+  for (int probe = 0; probe <= mask; ++probe) {
+    const unsigned long long cur = table[hsh];
+    if (cur == key) return;
+    if (cur == 0ull) {
+      if (*(volatile int *)count > limit) return;
+      const unsigned long long old = atomicCAS(table + hsh, 0ull, key);
+      if (old == 0ull) {
+        atomicAdd(count, 1);
+        return;
+      }
+      if (old == key) return;
+    }
+    hsh = (hsh + 1) & mask;
+  }
+}
+
+// SELL (pair layout) -> CSELL; slot_code maps hash-table slots to dictionary codes.  flags[0] |= 1 on failure.
+__global__ void sell_to_csell(SellView A, const int64_t *__restrict__ cslice_ptr, const unsigned long long *__restrict__ table,
+                              const unsigned short *__restrict__ slot_code, int mask, unsigned short zero_code,
+                              uint32_t *__restrict__ ent, int *flags) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slice = r >> 5, lane = r & 31;
+  if (slice >= A.n_slices) return;
+  const int64_t b = A.slice_ptr[slice];
+  const int w = (int)((A.slice_ptr[slice + 1] - b) >> 5);
+  const int64_t cb = cslice_ptr[slice];
+  const int cw = (int)((cslice_ptr[slice + 1] - cb) >> 5);
+  for (int j = 0; j < cw; ++j) {
+    uint32_t word = ((uint32_t)zero_code << 16);
+    if (j < w && r < A.n_rows) {
+      const int64_t at = b + (int64_t)(j >> 1) * 64 + lane * 2 + (j & 1);
+      const int delta = A.col[at] - r;
+      if (delta < -32768 || delta > 32767) atomicOr(flags, 1);
+      const unsigned long long key = (unsigned long long)__double_as_longlong(A.val[at]) + 1ull;
+      unsigned int hsh = (unsigned int)((key * 0x9E3779B97F4A7C15ull) >> 40) & mask;
+      int probe = 0;
+      while (table[hsh] != key && probe <= mask) {
+        hsh = (hsh + 1) & mask;
+        ++probe;
+      }
+      if (probe > mask) atomicOr(flags, 1);
+      word = ((uint32_t)slot_code[hsh] << 16) | (uint32_t)(unsigned short)(short)delta;
+    }
+    ent[cb + (int64_t)(j >> 2) * 128 + lane * 4 + (j & 3)] = word;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -326,14 +425,45 @@ __device__ __forceinline__ double grid_total(const double *partials, int nblocks
   return r;
 }
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) cg_persistent(SellView A, const double *__restrict__ b, double *x, double *g,
+constexpr int CSELL_SMEM_DICT = 2048;  // dictionary entries staged in shared memory (16 KB)
+
+template <class MAT>
+struct RowDot;
+template <>
+struct RowDot<SellView> {
+  __device__ __forceinline__ void init(const SellView &, double *) {}
+  __device__ __forceinline__ double operator()(const SellView &A, int s, int lane, const double *x) const {
+    return sell_row_dot<false>(A, s, lane, x);
+  }
+};
+template <>
+struct RowDot<CsellView> {
+  const double *dict;
+  __device__ __forceinline__ void init(const CsellView &A, double *sdict) {
+    if (A.dict_n <= CSELL_SMEM_DICT) {
+      for (int i = threadIdx.x; i < A.dict_n; i += blockDim.x) sdict[i] = A.dict[i];
+      __syncthreads();
+      dict = sdict;
+    } else {
+      dict = A.dict;
+    }
+  }
+  __device__ __forceinline__ double operator()(const CsellView &A, int s, int lane, const double *x) const {
+    return csell_row_dot<false>(A, s, lane, x, dict);
+  }
+};
+
+template <int BLOCK, class MAT>
+__global__ void __launch_bounds__(BLOCK) cg_persistent(MAT A, const double *__restrict__ b, double *x, double *g,
                                                        double *d, double *h, double *partials /* 3 * gridDim.x */,
                                                        int max_it, double tol, CgResult *result) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   __shared__ double red[32];
   __shared__ double bc;
+  __shared__ double sdict[std::is_same<MAT, CsellView>::value ? CSELL_SMEM_DICT : 1];
+  RowDot<MAT> row_dot;
+  row_dot.init(A, sdict);
   const int nb = gridDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int WPB = BLOCK / 32;
@@ -368,7 +498,7 @@ __global__ void __launch_bounds__(BLOCK) cg_persistent(SellView A, const double 
       // h = A d ; dh = d.h
       acc = 0.0;
       for (int s = s_begin + warp; s < s_end; s += WPB) {
-        const double ad = sell_row_dot<false>(A, s, lane, d);
+        const double ad = row_dot(A, s, lane, d);
         const int r = s * 32 + lane;
         if (r < A.n_rows) {
           h[r] = ad;

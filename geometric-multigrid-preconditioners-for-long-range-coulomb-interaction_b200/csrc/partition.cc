@@ -58,14 +58,24 @@ void partition_matrix(int rank, int world, int32_t n_rows, int32_t n_cols, const
     }
   }
   out.n_halo = (int)out.halo_global.size();
+  out.n_halo_lo = 0;
+  for (int o = 0; o < rank; ++o) out.n_halo_lo += plan.recv_count[o];
+  // local column of a halo entry: relative to the first owned entry
+  for (int k = 0; k < out.n_halo; ++k)
+    g2l[out.halo_global[k]] = (k < out.n_halo_lo) ? k - out.n_halo_lo : out.n_owned + (k - out.n_halo_lo);
+  plan.n_halo_lo_of.assign(world, 0);
+  for (int q = 0; q < world; ++q)
+    for (int o = 0; o < q; ++o) plan.n_halo_lo_of[q] += halo_cnt[q][o];
   // what I send to q: q's halo segment for owner == rank, in ascending global order
   plan.send_idx.assign(world, {});
   plan.send_dst_base.assign(world, 0);
+  plan.send_hpos_base.assign(world, 0);
   for (int q = 0; q < world; ++q) {
     if (q == rank) continue;
-    int32_t off = plan.n_owned_of[q];
+    int32_t off = 0;
     for (int o = 0; o < rank; ++o) off += halo_cnt[q][o];
-    plan.send_dst_base[q] = off;
+    plan.send_hpos_base[q] = off;
+    plan.send_dst_base[q] = off + (rank > q ? plan.n_owned_of[q] : 0);
   }
   for (int32_t j = 0; j < n_cols; ++j) {
     if (col_owner[j] != rank) continue;

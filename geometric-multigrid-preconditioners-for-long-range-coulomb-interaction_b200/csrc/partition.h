@@ -2,9 +2,12 @@
 // so the N > 1 host logic is testable on the CPU).  Mirrors what Epetra's Import/Export objects set up
 // for the reference's distributed matrices: owned rows, ghost (halo) columns, send lists.
 //
-// Local numbering on rank r: owned entries first, in ascending global order; halo entries after them,
-// ordered by (owner rank, global index).  What rank r sends to rank q is exactly q's halo segment for
-// owner r, in q's halo order, so a halo exchange is "q.halo[seg(r) + k] = r.owned[send_idx[k]]".
+// Halo entries are ordered by (owner rank, global index); the extended vector of rank r is laid out as
+//     [ halo entries owned by lower ranks | owned entries (ascending global order) | halo entries of higher ranks ]
+// and local column indices are relative to the first OWNED entry (so lower-rank halo columns are negative).
+// With slab-like partitions every row then reaches its neighbours at small column offsets, which keeps the
+// 16-bit offsets of the compressed matrix format valid.  What rank r sends to rank q is exactly q's halo
+// segment for owner r, in q's halo order.
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -12,9 +15,9 @@
 namespace gmg {
 
 struct LocalMatrix {
-  int n_owned = 0, n_halo = 0;
+  int n_owned = 0, n_halo = 0, n_halo_lo = 0;  // n_halo_lo: halo entries owned by lower ranks
   std::vector<int64_t> rowptr;      // n_owned + 1
-  std::vector<int32_t> col;         // local column indices in [0, n_owned + n_halo)
+  std::vector<int32_t> col;         // local column indices in [-n_halo_lo, n_owned + n_halo - n_halo_lo)
   std::vector<double> val;
   std::vector<int32_t> owned_global;  // global row/col index of each owned entry
   std::vector<int32_t> halo_global;   // global index of each halo entry
@@ -25,7 +28,9 @@ struct ExchangePlan {
   int rank = 0, world = 1;
   // per peer q: local (owned) indices to send, and where they land in q's extended vector
   std::vector<std::vector<int32_t>> send_idx;   // [world][..]
-  std::vector<int32_t> send_dst_base;           // [world]: n_owned(q) + offset of my segment in q's halo
+  std::vector<int32_t> send_dst_base;           // [world]: index in q's extended vector where my segment starts
+  std::vector<int32_t> send_hpos_base;          // [world]: position of my segment in q's halo list
+  std::vector<int32_t> n_halo_lo_of;            // [world]
   std::vector<int32_t> recv_count;              // [world]: entries received from each peer
   std::vector<int32_t> n_owned_of, n_halo_of;   // [world]
 };

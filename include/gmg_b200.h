@@ -76,6 +76,10 @@ int gmg_set_smoother(gmg_handle h, int kind, double omega, int steps);
 int gmg_set_coarse(gmg_handle h, int max_it, double abs_tol);
 /* Drop stored entries with |a_ij| <= drop_tol when building the device format (default: keep all). */
 int gmg_set_drop_tolerance(gmg_handle h, double drop_tol);
+/* Lossless compression of the coarse-level matrix on the device (16-bit value dictionary codes + 16-bit column
+ * offsets, 4 bytes per entry instead of 12; results are bit-identical).  Default on; falls back to the plain
+ * sliced-ELL format when a matrix has more than 60000 distinct values or a half bandwidth >= 32768. */
+int gmg_set_compression(gmg_handle h, int on);
 /* Build device formats (sliced ELL), transposes, colourings, eigenvalue bounds. */
 int gmg_setup(gmg_handle h);
 
@@ -119,9 +123,10 @@ int gmg_vcycle_apply_dev(gmg_handle h, const double *src_dev, double *dst_dev);
 int gmg_spmv_dev(gmg_handle h, int which, int level, const double *x_dev, double *y_dev);
 int gmg_cg_solve_dev(gmg_handle h, int which, int level, const double *b_dev, double *x_dev,
                      int max_it, double abs_tol, int *iters, double *res_final);
-/* bytes one SpMV / one coarse-CG iteration with this matrix moves algorithmically
- * (SURVEY.md section 8d): out[0] = stored nnz, out[1] = SpMV bytes, out[2] = CG-iteration bytes */
-int gmg_matrix_traffic(gmg_handle h, int which, int level, double out[3]);
+/* bytes one SpMV / one coarse-CG iteration with this matrix moves algorithmically:
+ * out[0] = stored nnz, out[1] = SpMV bytes and out[2] = CG-iteration bytes of the format actually stored,
+ * out[3], out[4] = the same for plain CSR (12 B per entry), out[5] = 1 if the compressed format is in use */
+int gmg_matrix_traffic(gmg_handle h, int which, int level, double out[6]);
 /* accumulated device time (ms, CUDA events on the handle's stream) and launch count of the
  * persistent coarse-CG kernel since the last reset; inner iterations summed in *iters. */
 int gmg_coarse_profile(gmg_handle h, int reset, double *ms, int64_t *launches, int64_t *iters);

@@ -82,6 +82,24 @@ def test_coarse_cg_lattice8_matches_reference_log(capi, lattice8, goldens):
     g.close()
 
 
+def test_compressed_coarse_matrix_is_lossless(capi, lattice8):
+    """The 4-byte-per-entry compressed level-0 format (value dictionary + 16-bit column offsets) decodes to the same
+    fp64 numbers in the same order: the coarse CG is bit-identical with and without it."""
+    P = lattice8
+    out = {}
+    for comp in (False, True):
+        g = capi.Gmg()
+        g.set_compression(comp)
+        hand_over(P, g)
+        tr = g.matrix_traffic(capi.GMG_LEVEL, 0)
+        assert tr["compressed"] == comp
+        out[comp] = g.cg_solve(capi.GMG_LEVEL, 0, P.b, 1000, 1e-10) + (tr,)
+        g.close()
+    assert out[True][1] == out[False][1] == 97
+    assert np.array_equal(out[True][0], out[False][0]) and out[True][2] == out[False][2]
+    assert out[True][3]["cg_iter_bytes"] < 0.55 * out[False][3]["cg_iter_bytes"]
+
+
 @pytest.mark.parametrize("kind", ["jacobi", "lex_ssor"])
 def test_smoother_steps_match_oracle(capi, P3, kind):
     from oracle import solver

@@ -30,7 +30,9 @@ def test_partition_maps_cover_and_match_single_process():
         parts = [capi.partition_probe(r, world, A, owner) for r in range(world)]
         assert sum(p["n_owned"] for p in parts) == A.shape[0]
         x = np.random.default_rng(0).standard_normal(A.shape[0])
-        ext = [np.concatenate([x[p["owned_global"]], np.zeros(p["n_halo"])]) for p in parts]
+        # extended vectors: [lower-rank halo | owned | higher-rank halo]
+        ext = [np.concatenate([np.zeros(p["n_halo_lo"]), x[p["owned_global"]], np.zeros(p["n_halo"] - p["n_halo_lo"])])
+               for p in parts]
         # emulate the pushes: r -> q
         for r, p in enumerate(parts):
             off = 0
@@ -38,11 +40,12 @@ def test_partition_maps_cover_and_match_single_process():
                 c = p["send_count"][q]
                 idx = p["send_idx"][off:off + c]
                 off += c
-                ext[q][p["send_dst_base"][q] + np.arange(c)] = ext[r][idx]
+                ext[q][p["send_dst_base"][q] + np.arange(c)] = ext[r][p["n_halo_lo"] + idx]
         y = np.zeros(A.shape[0])
         for p, xe in zip(parts, ext):
-            assert np.array_equal(xe[p["n_owned"]:], x[p["halo_global"]])
-            L = sp.csr_matrix((p["val"], p["col"], p["rowptr"]), shape=(p["n_owned"], p["n_owned"] + p["n_halo"]))
+            lo = p["n_halo_lo"]
+            assert np.array_equal(np.concatenate([xe[:lo], xe[lo + p["n_owned"]:]]), x[p["halo_global"]])
+            L = sp.csr_matrix((p["val"], p["col"] + lo, p["rowptr"]), shape=(p["n_owned"], p["n_owned"] + p["n_halo"]))
             y[p["owned_global"]] = L @ xe
         assert np.abs(y - A @ x).max() < 1e-13
 
@@ -56,30 +59,32 @@ def _worker(rank, world, port, q):
     A = laplace27(8)
     owner = slab_owner(8, world)
     p = capi.partition_probe(rank, world, A, owner)
-    L = sp.csr_matrix((p["val"], p["col"], p["rowptr"]), shape=(p["n_owned"], p["n_owned"] + p["n_halo"]))
+    lo, no = p["n_halo_lo"], p["n_owned"]
+    L = sp.csr_matrix((p["val"], p["col"] + lo, p["rowptr"]), shape=(no, no + p["n_halo"]))
     rng = np.random.default_rng(1)
     b = rng.standard_normal(A.shape[0])
     # distributed CG (deal.II recurrences), halos by send/recv, dots by all_reduce
     x = np.zeros(p["n_owned"])
     g = -b[p["owned_global"]]
-    d = np.concatenate([-g, np.zeros(p["n_halo"])])
+    d = np.concatenate([np.zeros(lo), -g, np.zeros(p["n_halo"] - lo)])  # [lower halo | owned | upper halo]
 
     def halo(v):
         off, reqs, bufs = 0, [], {}
         for qq in range(world):
             c = int(p["send_count"][qq])
             if c:
-                reqs.append(dist.isend(torch.from_numpy(v[p["send_idx"][off:off + c]].copy()), qq))
+                reqs.append(dist.isend(torch.from_numpy(v[lo + p["send_idx"][off:off + c]].copy()), qq))
             off += c
         other = [parts_n for parts_n in range(world) if parts_n != rank]
-        pos = p["n_owned"]
+        k = 0  # position in the halo list (ordered by owner)
         for qq in range(world):
             cnt = int((owner[p["halo_global"]] == qq).sum())
             if cnt:
                 t = torch.zeros(cnt, dtype=torch.float64)
                 dist.recv(t, qq)
+                pos = k if qq < rank else no + k
                 v[pos:pos + cnt] = t.numpy()
-                pos += cnt
+                k += cnt
         for r in reqs:
             r.wait()
 
@@ -94,11 +99,11 @@ def _worker(rank, world, port, q):
         its += 1
         halo(d)
         h = L @ d
-        alpha = gh / allsum(d[:p["n_owned"]] @ h)
-        x += alpha * d[:p["n_owned"]]
+        alpha = gh / allsum(d[lo:lo + no] @ h)
+        x += alpha * d[lo:lo + no]
         g += alpha * h
         new = allsum(g @ g)
-        d[:p["n_owned"]] = (new / gh) * d[:p["n_owned"]] - g
+        d[lo:lo + no] = (new / gh) * d[lo:lo + no] - g
         gh = new
     full = np.zeros(A.shape[0])
     full[p["owned_global"]] = x
