@@ -36,6 +36,8 @@ SIGNATURES = {
     "gmg_set_copy_indices": (_i, [_h, _i, C.c_int32, _pi32, _pi32]),
     "gmg_set_smoother": (_i, [_h, _i, _d, _i]),
     "gmg_set_coarse": (_i, [_h, _i, _d]),
+    "gmg_set_level_coloring": (_i, [_h, _i, C.c_int32, _pi32]),
+    "gmg_set_graphs": (_i, [_h, _i]),
     "gmg_set_drop_tolerance": (_i, [_h, _d]),
     "gmg_set_compression": (_i, [_h, _i]),
     "gmg_setup": (_i, [_h]),
@@ -69,6 +71,7 @@ SIGNATURES = {
                                  C.POINTER(_pi64), C.POINTER(_pi32), C.POINTER(_pd), C.POINTER(_pi32), C.POINTER(_pi32),
                                  C.POINTER(_pi32), C.POINTER(_pi32), C.POINTER(_pi32)]),
     "gmg_free_host": (None, [C.c_void_p]),
+    "gmg_dist_pingpong": (_i, [_h, _i, _i, _pd]),
     "gmg_bin_atoms": (_i, [_h, C.c_int32, _pd, _pd, C.c_int32, _pd, _d, _pi64, _pi32]),
     "gmg_set_atom_lists": (_i, [_h, C.c_int32, _pi64, _pi32]),
     "gmg_set_atoms": (_i, [_h, C.c_int32, _pd, _pd]),
@@ -165,6 +168,13 @@ class Gmg:
 
     def set_smoother(self, kind, omega=0.5, steps=2):
         self._ck(self.lib.gmg_set_smoother(self.h, kind, omega, steps))
+
+    def set_level_coloring(self, level, color):
+        color = _i32(color)
+        self._ck(self.lib.gmg_set_level_coloring(self.h, level, len(color), color.ctypes.data_as(_pi32)))
+
+    def set_graphs(self, on):
+        self._ck(self.lib.gmg_set_graphs(self.h, int(on)))
 
     def set_coarse(self, max_it=1000, tol=1e-10):
         self._ck(self.lib.gmg_set_coarse(self.h, max_it, tol))
@@ -303,6 +313,11 @@ class Gmg:
     def dist_connect(self, all_handles):
         blob = b"".join(all_handles)
         self._ck(self.lib.gmg_dist_connect(self.h, C.cast(C.c_char_p(blob), C.c_void_p)))
+
+    def pingpong(self, iters=1000, mode=0):
+        us = _d(0)
+        self._ck(self.lib.gmg_dist_pingpong(self.h, iters, mode, C.byref(us)))
+        return us.value
 
     def set_ownership(self, which, level, owner):
         owner = _i32(owner)

@@ -53,10 +53,21 @@ __device__ __forceinline__ double block_max(double v, double *red) {
 
 // Sum `n` partials in a fixed order with one warp (lane-strided serial sums, then a shuffle tree):
 // every block that calls this on the same data obtains the same bits.
-__device__ __forceinline__ double warp_sum_partials(const volatile double *p, int n) {
+// Loads are ld.global.cg (L2, never a stale L1 line) and independent, so they overlap: with volatile loads the
+// ~10 serial L2 round trips of this loop cost ~6 us per reduction inside the persistent CG.
+__device__ __forceinline__ double warp_sum_partials(const double *p, int n) {
   const int lane = threadIdx.x & 31;
+  double v[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int i = lane + 32 * u;
+    v[u] = (i < n) ? __ldcg(p + i) : 0.0;
+  }
   double s = 0.0;
-  for (int i = lane; i < n; i += 32) s += p[i];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) s += v[u];  // same order as the serial loop
+  for (int i = lane + 512; i < n; i += 32) s += __ldcg(p + i);
+
   return warp_sum(s);
 }
 

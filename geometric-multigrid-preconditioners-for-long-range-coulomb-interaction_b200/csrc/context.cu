@@ -303,6 +303,17 @@ static std::vector<int> greedy_coloring(const HostCsr &a, int &n_colors) {
   return color;
 }
 
+static bool coloring_is_valid(const HostCsr &a, const std::vector<int32_t> &color, int &n_colors) {
+  n_colors = 0;
+  for (int r = 0; r < a.n_rows; ++r) {
+    if (color[r] < 0 || color[r] > 255) return false;
+    n_colors = std::max(n_colors, color[r] + 1);
+    for (int64_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k)
+      if (a.col[k] != r && a.val[k] != 0.0 && color[a.col[k]] == color[r]) return false;
+  }
+  return true;
+}
+
 // wavefront ("level") schedule of the forward / backward Gauss-Seidel sweeps in natural row order
 static std::vector<std::vector<int>> wavefronts(const HostCsr &a, bool forward) {
   std::vector<int> lev(a.n_rows, 0);
@@ -497,8 +508,8 @@ static int smooth(gmg_context *h, Level &L, double *&u, const double *rhs, bool 
   return fail(h, GMG_EINVAL, "unknown smoother");
 }
 
-// PreconditionMG::vmult on device vectors
-static int vcycle(gmg_context *h, const double *src, double *dst) {
+// PreconditionMG::vmult on device vectors: down sweep, coarse solve, up sweep
+static int vcycle_down(gmg_context *h, const double *src) {
   const int nl = h->n_levels;
   for (int l = 0; l < nl; ++l) {
     Level &L = h->levels[l];
@@ -508,7 +519,6 @@ static int vcycle(gmg_context *h, const double *src, double *dst) {
       GMG_LAUNCH_CHECK(h);
     }
   }
-  // down
   for (int l = nl - 1; l >= 1; --l) {
     Level &L = h->levels[l];
     Level &C = h->levels[l - 1];
@@ -518,12 +528,11 @@ static int vcycle(gmg_context *h, const double *src, double *dst) {
     // defect[l-1] += P^T t
     if (int rc = spmv<EPI_ADD, DOT_NONE>(h, C.R, L.t, C.defect)) return rc;
   }
-  // coarse
-  {
-    Level &L0 = h->levels[0];
-    if (int rc = coarse_cg(h, L0.A, L0.defect, L0.sol, h->coarse_max_it, h->coarse_tol)) return rc;
-  }
-  // up
+  return GMG_OK;
+}
+
+static int vcycle_up(gmg_context *h, double *dst) {
+  const int nl = h->n_levels;
   for (int l = 1; l < nl; ++l) {
     Level &L = h->levels[l];
     Level &C = h->levels[l - 1];
@@ -541,6 +550,75 @@ static int vcycle(gmg_context *h, const double *src, double *dst) {
     }
   }
   return GMG_OK;
+}
+
+static void drop_vc_graphs(gmg_context *h) {
+  for (auto &g : h->vc_graphs) {
+    if (g.down) cudaGraphExecDestroy(g.down);
+    if (g.up) cudaGraphExecDestroy(g.up);
+  }
+  h->vc_graphs.clear();
+}
+
+// capture `body` (stream-ordered launches only) into an executable graph
+template <class F>
+static int capture_graph(gmg_context *h, F &&body, cudaGraphExec_t &exec, int64_t &n_launches) {
+  const int64_t before = h->launches;
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return GMG_ECUDA;
+  const int rc = body();
+  const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  n_launches = h->launches - before;
+  h->launches = before;
+  if (rc != GMG_OK || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return rc != GMG_OK ? rc : GMG_ECUDA;
+  }
+  const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  return e2 == cudaSuccess ? GMG_OK : GMG_ECUDA;
+}
+
+static int vcycle(gmg_context *h, const double *src, double *dst) {
+  // The fine-level parts are hundreds of tiny launches on the patch levels (latency-bound): replay them as CUDA
+  // graphs.  Jacobi swaps its ping-pong buffers, so its launch sequence is not replayable as captured.
+  const bool graphs = h->use_graphs && h->n_levels > 1 && h->smoother != GMG_SMOOTHER_JACOBI;
+  gmg_context::VcGraph *g = nullptr;
+  if (graphs) {
+    for (auto &c : h->vc_graphs)
+      if (c.src == src && c.dst == dst) g = &c;
+    if (!g && h->vc_graphs.size() < 8) {
+      gmg_context::VcGraph ng;
+      ng.src = src;
+      ng.dst = dst;
+      if (capture_graph(h, [&]() { return vcycle_down(h, src); }, ng.down, ng.n_down) == GMG_OK &&
+          capture_graph(h, [&]() { return vcycle_up(h, dst); }, ng.up, ng.n_up) == GMG_OK) {
+        h->vc_graphs.push_back(ng);
+        g = &h->vc_graphs.back();
+      } else {
+        if (ng.down) cudaGraphExecDestroy(ng.down);
+        if (ng.up) cudaGraphExecDestroy(ng.up);
+        h->use_graphs = false;  // capture unsupported here: fall back to direct launches for good
+      }
+    }
+  }
+  if (g) {
+    GMG_CUDA(h, cudaGraphLaunch(g->down, h->stream));
+    h->launches += g->n_down;
+  } else if (int rc = vcycle_down(h, src)) {
+    return rc;
+  }
+  {
+    Level &L0 = h->levels[0];
+    if (int rc = coarse_cg(h, L0.A, L0.defect, L0.sol, h->coarse_max_it, h->coarse_tol)) return rc;
+  }
+  if (g) {
+    GMG_CUDA(h, cudaGraphLaunch(g->up, h->stream));
+    h->launches += g->n_up;
+    return GMG_OK;
+  }
+  return vcycle_up(h, dst);
 }
 
 enum { PRECOND_GMG = 0, PRECOND_JACOBI = 1 };
@@ -706,6 +784,7 @@ int gmg_destroy(gmg_handle h) {
   if (!h) return GMG_OK;
   gmg::enter(h);
   cudaDeviceSynchronize();
+  drop_vc_graphs(h);
   for (auto &L : h->levels) free_level(L);
   free_csr(h->rawS);
   free_sell(h->S);
@@ -757,6 +836,8 @@ int64_t gmg_launch_count(gmg_handle h) { return h ? h->launches : 0; }
 
 int gmg_set_num_levels(gmg_handle h, int n_levels) {
   if (!h || n_levels < 1) return GMG_EINVAL;
+  gmg::enter(h);
+  drop_vc_graphs(h);
   for (auto &L : h->levels) free_level(L);
   h->levels.assign(n_levels, Level{});
   h->n_levels = n_levels;
@@ -850,9 +931,24 @@ int gmg_set_drop_tolerance(gmg_handle h, double drop_tol) {
   return GMG_OK;
 }
 
+int gmg_set_level_coloring(gmg_handle h, int level, int32_t n, const int32_t *color) {
+  if (!h || level < 0 || level >= h->n_levels || n < 0 || (n && !color)) return GMG_EINVAL;
+  h->levels[level].user_color.assign(color, color + n);
+  h->is_setup = false;
+  return GMG_OK;
+}
+
+int gmg_set_graphs(gmg_handle h, int on) {
+  if (!h) return GMG_EINVAL;
+  h->use_graphs = on != 0;
+  drop_vc_graphs(h);
+  return GMG_OK;
+}
+
 int gmg_setup(gmg_handle h) {
   if (!h) return GMG_EINVAL;
   gmg::enter(h);
+  drop_vc_graphs(h);
   TraceScope tr_all("gmg_setup total");
   int rc;
   if (h->rawS.rowptr) {
@@ -921,7 +1017,11 @@ int gmg_setup(gmg_handle h) {
       }
       if (h->smoother == GMG_SMOOTHER_MC_SSOR) {
         int nc = 0;
-        std::vector<int> color = greedy_coloring(L.hA, nc);
+        std::vector<int> color;
+        if ((int)L.user_color.size() == L.n && coloring_is_valid(L.hA, L.user_color, nc))
+          color.assign(L.user_color.begin(), L.user_color.end());
+        else
+          color = greedy_coloring(L.hA, nc);
         std::vector<std::vector<int>> rows(nc);
         for (int r = 0; r < L.n; ++r) rows[color[r]].push_back(r);
         L.colors.resize(nc);

@@ -67,6 +67,7 @@ struct Level {
   std::vector<ColorSet> colors;      // multicolour SSOR
   std::vector<ColorSet> wave_fwd, wave_bwd;  // level-scheduled lexicographic SSOR
   double lambda_max = 0.0;           // Chebyshev
+  std::vector<int32_t> user_color;   // optional colouring handed over by the host (gmg_set_level_coloring)
 };
 
 // one distributed (row-partitioned) matrix: local SELL over [owned | halo] columns + its halo send lists
@@ -181,6 +182,15 @@ struct gmg_context {
   int n_lists = 0;
   struct RhsState *rhs = nullptr;
   gmg::DistData dist;
+  // CUDA graphs of the fine-level parts of the V-cycle (down sweep / up sweep), keyed by (src, dst)
+  struct VcGraph {
+    const double *src = nullptr;
+    double *dst = nullptr;
+    cudaGraphExec_t down = nullptr, up = nullptr;
+    int64_t n_down = 0, n_up = 0;
+  };
+  std::vector<VcGraph> vc_graphs;
+  bool use_graphs = true;
 };
 
 namespace gmg {

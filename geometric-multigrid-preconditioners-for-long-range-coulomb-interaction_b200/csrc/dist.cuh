@@ -145,6 +145,29 @@ __device__ __forceinline__ bool ll_load(const uint64_t *p, uint32_t tag, double 
   return true;
 }
 
+// latency probe: rank 0 sends tag i to rank 1, which echoes it; cycles for `iters` round trips -> out[0].
+// mode 0: tagged LL store only; mode 1: LL store followed by __threadfence_system()
+__global__ void dist_pingpong(DistPeers P, size_t region, int iters, int mode, uint32_t tag_base, long long *out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint64_t *mine = reinterpret_cast<uint64_t *>(P.peer[P.rank] + region);
+  uint64_t *other = reinterpret_cast<uint64_t *>(P.peer[P.rank ^ 1] + region);
+  double v;
+  const long long t0 = clock64();
+  for (int i = 1; i <= iters; ++i) {
+    const uint32_t tag = tag_base + i;
+    if (P.rank == 0) {
+      ll_store(other, (double)i, tag);
+      if (mode == 1) __threadfence_system();
+      if (!ll_load(mine, tag, v)) break;
+    } else {
+      if (!ll_load(mine, tag, v)) break;
+      ll_store(other, v, tag);
+      if (mode == 1) __threadfence_system();
+    }
+  }
+  out[0] = clock64() - t0;
+}
+
 struct DistCgArgs {
   DistPeers P;
   int n_owned, n_halo, n_halo_lo;
@@ -165,7 +188,7 @@ struct DistCgArgs {
 // exchange kernels.  Per iteration: 3 grid.sync() exactly as on one GPU.
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK, class MAT>
-__global__ void __launch_bounds__(BLOCK) cg_persistent_dist(MAT A, const double *__restrict__ b, double *x, double *g,
+__global__ void __launch_bounds__(BLOCK, 2) cg_persistent_dist(MAT A, const double *__restrict__ b, double *x, double *g,
                                                             double *h, double *partials, int max_it, double tol,
                                                             CgResult *result, DistCgArgs D, int *error) {
   namespace cg = cooperative_groups;
@@ -261,6 +284,7 @@ __global__ void __launch_bounds__(BLOCK) cg_persistent_dist(MAT A, const double 
       ++it;
       acc = 0.0;
       for (int s = s_begin + warp; s < s_end; s += WPB) {
+        if (s + WPB < s_end) row_dot.prefetch(A, s + WPB, lane);
         const double ad = row_dot(A, s, lane, d);
         const int r = s * 32 + lane;
         if (r < A.n_rows) {

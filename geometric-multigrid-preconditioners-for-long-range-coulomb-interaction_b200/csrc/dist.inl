@@ -638,4 +638,27 @@ int gmg_partition_probe(int rank, int world, int32_t n_rows, const int64_t *rowp
 
 void gmg_free_host(void *p) { std::free(p); }
 
+// developer probe: NVLink round-trip latency of tagged LL words between ranks 0 and 1 (both ranks must call)
+int gmg_dist_pingpong(gmg_handle h, int iters, int mode, double *us_per_round_trip) {
+  if (!h || !h->dist.on || h->dist.world < 2) return GMG_EINVAL;
+  gmg::enter(h);
+  DistData &d = h->dist;
+  if (d.rank > 1) { if (us_per_round_trip) *us_per_round_trip = 0.0; return GMG_OK; }
+  static size_t region = 0;
+  if (region == 0) { region = DIST_HEADER_BYTES - 64; }
+  long long *out = nullptr;
+  GMG_CUDA(h, dalloc(&out, 1));
+  static uint32_t tb = 0x40000000u;
+  tb += 0x100000u;
+  dist_pingpong<<<1, 32, 0, h->stream>>>(peers_of(h), region, iters, mode, tb, out);
+  GMG_LAUNCH_CHECK(h);
+  long long cyc = 0;
+  GMG_CUDA(h, copy_sync(h, &cyc, out, sizeof(cyc), cudaMemcpyDeviceToHost));
+  dfree(out);
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+  if (us_per_round_trip) *us_per_round_trip = (double)cyc / (khz * 1e-3) / iters;
+  return GMG_OK;
+}
+
 }  // extern "C"

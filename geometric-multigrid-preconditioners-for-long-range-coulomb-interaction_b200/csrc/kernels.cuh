@@ -77,27 +77,39 @@ __device__ __forceinline__ double csell_row_dot(const CsellView &A, int slice, i
   const int row = slice * 32 + lane;
   if (row >= A.n_rows) return 0.0;  // lanes past the last row of the last slice: their offsets are relative to nothing
   double acc = 0.0;
-  int p = 0;
-  for (; p + 2 <= nchunks; p += 2) {
-    const uint4 e0 = ld_stream_u4(e4 + p * 32);
-    const uint4 e1 = ld_stream_u4(e4 + (p + 1) * 32);
-    const uint32_t w[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-    double xv[8], av[8];
+  // Latency-bound on the entry stream (ncu: about half of all stall samples sat on the first use of an entry word):
+  // entries are consumed in groups of 4 chunks (16 entries) whose loads are all issued first, and the caller
+  // prefetches the next slice of this warp into L2 (csell_prefetch_slice) while this one is processed.
+  for (int p0 = 0; p0 < nchunks; p0 += 4) {
+    uint4 e[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      xv[u] = ldx<NC>(x, row + (int)(short)(w[u] & 0xffffu));
-      av[u] = dict[w[u] >> 16];
+    for (int u = 0; u < 4; ++u)
+      e[u] = (p0 + u < nchunks) ? ld_stream_u4(e4 + (p0 + u) * 32) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (p0 + u < nchunks) {
+        const uint32_t w[4] = {e[u].x, e[u].y, e[u].z, e[u].w};
+        double xv[4], av[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          xv[t] = ldx<NC>(x, row + (int)(short)(w[t] & 0xffffu));
+          av[t] = dict[w[t] >> 16];
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc = fma(av[t], xv[t], acc);
+      }
     }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) acc = fma(av[u], xv[u], acc);
-  }
-  for (; p < nchunks; ++p) {
-    const uint4 e0 = ld_stream_u4(e4 + p * 32);
-    const uint32_t w[4] = {e0.x, e0.y, e0.z, e0.w};
-#pragma unroll
-    for (int u = 0; u < 4; ++u) acc = fma(dict[w[u] >> 16], ldx<NC>(x, row + (int)(short)(w[u] & 0xffffu)), acc);
   }
   return acc;
+}
+
+// one 128-byte line per lane: the whole entry block of a slice (<= 32 lines = 4 KB) goes to L2 with one instruction
+__device__ __forceinline__ void csell_prefetch_slice(const CsellView &A, int slice, int lane) {
+  if (slice >= A.n_slices) return;
+  const int64_t b = A.slice_ptr[slice];
+  const int64_t bytes = (A.slice_ptr[slice + 1] - b) * 4;
+  const char *p = reinterpret_cast<const char *>(A.ent) + b * 4 + (int64_t)lane * 128;
+  if ((int64_t)lane * 128 < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // open-addressing set of fp64 bit patterns (distinct matrix values); table size is a power of two
@@ -432,6 +444,7 @@ struct RowDot;
 template <>
 struct RowDot<SellView> {
   __device__ __forceinline__ void init(const SellView &, double *) {}
+  __device__ __forceinline__ void prefetch(const SellView &, int, int) const {}
   __device__ __forceinline__ double operator()(const SellView &A, int s, int lane, const double *x) const {
     return sell_row_dot<false>(A, s, lane, x);
   }
@@ -448,13 +461,14 @@ struct RowDot<CsellView> {
       dict = A.dict;
     }
   }
+  __device__ __forceinline__ void prefetch(const CsellView &A, int s, int lane) const { csell_prefetch_slice(A, s, lane); }
   __device__ __forceinline__ double operator()(const CsellView &A, int s, int lane, const double *x) const {
     return csell_row_dot<false>(A, s, lane, x, dict);
   }
 };
 
 template <int BLOCK, class MAT>
-__global__ void __launch_bounds__(BLOCK) cg_persistent(MAT A, const double *__restrict__ b, double *x, double *g,
+__global__ void __launch_bounds__(BLOCK, 2) cg_persistent(MAT A, const double *__restrict__ b, double *x, double *g,
                                                        double *d, double *h, double *partials /* 3 * gridDim.x */,
                                                        int max_it, double tol, CgResult *result) {
   namespace cg = cooperative_groups;
@@ -498,6 +512,7 @@ __global__ void __launch_bounds__(BLOCK) cg_persistent(MAT A, const double *__re
       // h = A d ; dh = d.h
       acc = 0.0;
       for (int s = s_begin + warp; s < s_end; s += WPB) {
+        if (s + WPB < s_end) row_dot.prefetch(A, s + WPB, lane);
         const double ad = row_dot(A, s, lane, d);
         const int r = s * 32 + lane;
         if (r < A.n_rows) {

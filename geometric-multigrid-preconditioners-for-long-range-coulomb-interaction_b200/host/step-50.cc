@@ -453,6 +453,16 @@ void LaplaceProblem<dim>::hand_over_hierarchy() {
       gmg_check(gmg_set_copy_indices(gmg, l, (int)d.copy_global[l].size(), d.copy_global[l].data(),
                                      d.copy_level[l].data()),
                 "gmg_set_copy_indices");
+      if (l >= 1) {
+        // vertex-parity colouring of the level: neighbours in a Q1 stencil differ in at least one coordinate by one
+        const int sh = triangulation->resolution() - l;
+        std::vector<int32_t> color(d.level_n[l]);
+        for (int i = 0; i < d.level_n[l]; ++i) {
+          const Int3 &q = d.level_xyz[l][i];
+          color[i] = ((q[0] >> sh) & 1) | (((q[1] >> sh) & 1) << 1) | (((q[2] >> sh) & 1) << 2);
+        }
+        gmg_check(gmg_set_level_coloring(gmg, l, d.level_n[l], color.data()), "gmg_set_level_coloring");
+      }
     }
   } else {
     set(GMG_LEVEL, 0, system_matrix);  // unused by the Jacobi-preconditioned solve

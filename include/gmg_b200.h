@@ -72,6 +72,11 @@ int gmg_set_copy_indices(gmg_handle h, int level, int32_t n, const int32_t *glob
                          const int32_t *level_idx);
 /* MGSmootherPrecondition<...>::initialize(mg_matrices, AdditionalData(omega)); set_steps(steps). */
 int gmg_set_smoother(gmg_handle h, int kind, double omega, int steps);
+/* Optional colouring of a level's rows for the multicolour SSOR (e.g. the 8 vertex-parity colours of a Q1
+ * mesh level); validated against the matrix graph, the library falls back to its greedy colouring. */
+int gmg_set_level_coloring(gmg_handle h, int level, int32_t n, const int32_t *color);
+/* Replay the fine-level parts of the V-cycle as CUDA graphs (default on). */
+int gmg_set_graphs(gmg_handle h, int on);
 /* SolverControl coarse_solver_control(max_it, abs_tol) + SolverCG + PreconditionIdentity. */
 int gmg_set_coarse(gmg_handle h, int max_it, double abs_tol);
 /* Drop stored entries with |a_ij| <= drop_tol when building the device format (default: keep all). */
@@ -152,6 +157,8 @@ int gmg_partition_probe(int rank, int world, int32_t n_rows, const int64_t *rowp
                         int64_t **l_rowptr, int32_t **l_col, double **l_val, int32_t **owned_global,
                         int32_t **halo_global, int32_t **send_count, int32_t **send_idx, int32_t **send_dst_base);
 void gmg_free_host(void *p);
+/* developer probe: NVLink round-trip latency (us) of tagged 16-byte words between ranks 0 and 1 */
+int gmg_dist_pingpong(gmg_handle h, int iters, int mode, double *us_per_round_trip);
 
 /* ---- the RHS path ----------------------------------------------------------------------------- */
 /* rhs_assembly_optimization (src/step-50.cc:260-306): cell c lists atom i iff some vertex v of the
