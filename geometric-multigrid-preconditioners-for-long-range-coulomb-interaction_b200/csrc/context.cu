@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include "context.h"
 #include "kernels.cuh"
@@ -23,6 +24,10 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 thread_local cudaStream_t tl_stream = nullptr;
 
 static void free_sell(Sell &s) {
+  if (s.shares_structure) {
+    s.slice_ptr = nullptr;
+    s.col = nullptr;
+  }
   dfree(s.slice_ptr);
   dfree(s.val);
   dfree(s.col);
@@ -48,6 +53,49 @@ int ensure_stage(gmg_context *h, int64_t n) {
   return GMG_OK;
 }
 
+// Large host->device copies from pageable memory: chunks are copied into a ring of pinned buffers by a few host
+// threads (one memcpy thread tops out near 10 GB/s) while the previous chunk is in flight on the copy engine.
+static int staged_h2d(gmg_context *h, void *dst, const void *src, size_t bytes) {
+  constexpr size_t CHUNK = 32u << 20;
+  constexpr int NBUF = 4, NTHREADS = 6;
+  if (bytes < (8u << 20)) {
+    GMG_CUDA(h, copy(h, dst, src, bytes, cudaMemcpyHostToDevice));
+    return GMG_OK;
+  }
+  if (!h->pin[0]) {
+    for (int i = 0; i < NBUF; ++i) {
+      GMG_CUDA(h, cudaHostAlloc((void **)&h->pin[i], CHUNK, cudaHostAllocDefault));
+      GMG_CUDA(h, cudaEventCreateWithFlags(&h->pin_free[i], cudaEventDisableTiming));
+    }
+    h->pin_bytes = CHUNK;
+  }
+  h->h2d_bytes += (int64_t)bytes;
+  size_t off = 0;
+  int buf = 0;
+  while (off < bytes) {
+    const size_t n = std::min(CHUNK, bytes - off);
+    GMG_CUDA(h, cudaEventSynchronize(h->pin_free[buf]));  // previous DMA out of this buffer has finished
+    {
+      const char *s = (const char *)src + off;
+      char *d = h->pin[buf];
+      std::thread th[NTHREADS];
+      const size_t part = (n + NTHREADS - 1) / NTHREADS;
+      for (int t = 0; t < NTHREADS; ++t) {
+        const size_t a = std::min(n, part * t), b = std::min(n, part * (t + 1));
+        th[t] = std::thread([=]() {
+          if (b > a) std::memcpy(d + a, s + a, b - a);
+        });
+      }
+      for (auto &t : th) t.join();
+    }
+    GMG_CUDA(h, cudaMemcpyAsync((char *)dst + off, h->pin[buf], n, cudaMemcpyHostToDevice, h->stream));
+    GMG_CUDA(h, cudaEventRecord(h->pin_free[buf], h->stream));
+    off += n;
+    buf = (buf + 1) % NBUF;
+  }
+  return GMG_OK;
+}
+
 static int upload_csr(gmg_context *h, int n_rows, int n_cols, const int64_t *rowptr, const int32_t *col,
                       const double *val, DevCsr &out) {
   free_csr(out);
@@ -57,9 +105,9 @@ static int upload_csr(gmg_context *h, int n_rows, int n_cols, const int64_t *row
   GMG_CUDA(h, dalloc(&out.rowptr, n_rows + 1));
   GMG_CUDA(h, dalloc(&out.col, out.nnz));
   GMG_CUDA(h, dalloc(&out.val, out.nnz));
-  GMG_CUDA(h, gmg::copy(h, out.rowptr, rowptr, sizeof(int64_t) * (n_rows + 1), cudaMemcpyHostToDevice));
-  GMG_CUDA(h, gmg::copy(h, out.col, col, sizeof(int) * out.nnz, cudaMemcpyHostToDevice));
-  GMG_CUDA(h, gmg::copy(h, out.val, val, sizeof(double) * out.nnz, cudaMemcpyHostToDevice));
+  if (int rc = staged_h2d(h, out.rowptr, rowptr, sizeof(int64_t) * (n_rows + 1))) return rc;
+  if (int rc = staged_h2d(h, out.col, col, sizeof(int) * out.nnz)) return rc;
+  if (int rc = staged_h2d(h, out.val, val, sizeof(double) * out.nnz)) return rc;
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));  // the host buffers are only borrowed
   return GMG_OK;
 }
@@ -68,45 +116,44 @@ static int upload_host_csr(gmg_context *h, const HostCsr &m, DevCsr &out) {
   return upload_csr(h, m.n_rows, m.n_cols, m.rowptr.data(), m.col.data(), m.val.data(), out);
 }
 
-// CSR (device) -> sliced ELL (device)
-static int build_sell(gmg_context *h, const DevCsr &c, double drop_tol, Sell &out) {
+// CSR (device) -> sliced ELL (device); `rows` (device, optional) selects / orders a subset of the CSR rows
+static int build_sell(gmg_context *h, const DevCsr &c, double drop_tol, Sell &out, const int *rows = nullptr, int n_sub = -1) {
   free_sell(out);
-  const int n_slices = cdiv(c.n_rows, SLICE);
+  const int n_rows = rows ? n_sub : c.n_rows;
+  const int n_slices = cdiv(n_rows, SLICE);
   TraceScope trb("        build_sell");
-  int *width = nullptr, *row_nnz = nullptr;
+  int *width = nullptr;
+  unsigned long long *total = nullptr;
   GMG_CUDA(h, dalloc(&width, n_slices));
-  GMG_CUDA(h, dalloc(&row_nnz, c.n_rows));
+  GMG_CUDA(h, dalloc(&total, 1));
+  GMG_CUDA(h, cudaMemsetAsync(total, 0, sizeof(unsigned long long), h->stream));
   if (n_slices > 0) {
-    csr_slice_widths<<<cdiv((int64_t)n_slices * 32, 256), 256, 0, h->stream>>>(c.n_rows, n_slices, c.rowptr, c.val,
-                                                                               drop_tol, width, row_nnz);
+    csr_slice_widths<<<cdiv((int64_t)n_slices * 32, 256), 256, 0, h->stream>>>(n_rows, n_slices, rows, c.rowptr, c.val,
+                                                                               drop_tol, width, total);
     GMG_LAUNCH_CHECK(h);
   }
-  std::vector<int> hw(n_slices), hn(c.n_rows);
-  GMG_CUDA(h, gmg::copy(h, hw.data(), width, sizeof(int) * n_slices, cudaMemcpyDeviceToHost));
-  GMG_CUDA(h, gmg::copy(h, hn.data(), row_nnz, sizeof(int) * c.n_rows, cudaMemcpyDeviceToHost));
+  std::vector<int> hw(n_slices);
+  unsigned long long htotal = 0;
+  GMG_CUDA(h, copy(h, hw.data(), width, sizeof(int) * n_slices, cudaMemcpyDeviceToHost));
+  GMG_CUDA(h, copy(h, &htotal, total, sizeof(htotal), cudaMemcpyDeviceToHost));
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   std::vector<int64_t> sp(n_slices + 1, 0);
-  int maxw = 0;
-  for (int s = 0; s < n_slices; ++s) {
-    sp[s + 1] = sp[s] + (int64_t)hw[s] * SLICE;
-    maxw = std::max(maxw, hw[s]);
-  }
-  out.stored_nnz = 0;
-  for (int r = 0; r < c.n_rows; ++r) out.stored_nnz += hn[r];
+  for (int s = 0; s < n_slices; ++s) sp[s + 1] = sp[s] + (int64_t)hw[s] * SLICE;
+  out.stored_nnz = (int64_t)htotal;
   out.padded = sp[n_slices];
   GMG_CUDA(h, dalloc(&out.slice_ptr, n_slices + 1));
   GMG_CUDA(h, dalloc(&out.val, out.padded));
   GMG_CUDA(h, dalloc(&out.col, out.padded));
-  GMG_CUDA(h, gmg::copy(h, out.slice_ptr, sp.data(), sizeof(int64_t) * (n_slices + 1), cudaMemcpyHostToDevice));
+  GMG_CUDA(h, copy(h, out.slice_ptr, sp.data(), sizeof(int64_t) * (n_slices + 1), cudaMemcpyHostToDevice));
   if (n_slices > 0) {
-    csr_to_sell<<<cdiv((int64_t)n_slices * 32, 256), 256, 0, h->stream>>>(c.n_rows, c.n_cols, c.rowptr, c.col, c.val,
+    csr_to_sell<<<cdiv((int64_t)n_slices * 32, 256), 256, 0, h->stream>>>(n_rows, c.n_cols, rows, c.rowptr, c.col, c.val,
                                                                           drop_tol, out.slice_ptr, out.val, out.col);
     GMG_LAUNCH_CHECK(h);
   }
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   dfree(width);
-  dfree(row_nnz);
-  out.v = SellView{c.n_rows, c.n_cols, n_slices, out.slice_ptr, out.val, out.col};
+  dfree(total);
+  out.v = SellView{n_rows, c.n_cols, n_slices, out.slice_ptr, out.val, out.col};
   out.h_slice_ptr = sp;
   out.valid = true;
   return GMG_OK;
@@ -202,6 +249,39 @@ static int build_csell(gmg_context *h, Sell &s) {
   return GMG_OK;
 }
 
+// AI = A + I on the device: same structure as A (shared), values = A's plus I's entries
+static int build_sum_on_device(gmg_context *h, const Sell &A, const HostCsr &I, Sell &out, bool &ok) {
+  ok = false;
+  free_sell(out);
+  out.shares_structure = true;
+  out.slice_ptr = A.slice_ptr;
+  out.col = A.col;
+  out.stored_nnz = A.stored_nnz;
+  out.padded = A.padded;
+  out.h_slice_ptr = A.h_slice_ptr;
+  GMG_CUDA(h, dalloc(&out.val, A.padded));
+  GMG_CUDA(h, copy(h, out.val, A.val, sizeof(double) * A.padded, cudaMemcpyDeviceToDevice));
+  out.v = SellView{A.v.n_rows, A.v.n_cols, A.v.n_slices, out.slice_ptr, out.val, out.col};
+  out.valid = true;
+  if (I.empty() || I.nnz() == 0) {
+    ok = true;
+    return GMG_OK;
+  }
+  DevCsr dI;
+  int *flag = nullptr;
+  if (int rc = upload_host_csr(h, I, dI)) return rc;
+  GMG_CUDA(h, dalloc(&flag, 1));
+  GMG_CUDA(h, cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+  sell_add_csr<<<cdiv(std::max(I.n_rows, 1), 256), 256, 0, h->stream>>>(out.v, out.val, I.n_rows, dI.rowptr, dI.col, dI.val, flag);
+  GMG_LAUNCH_CHECK(h);
+  int hf = 0;
+  GMG_CUDA(h, copy_sync(h, &hf, flag, sizeof(int), cudaMemcpyDeviceToHost));
+  dfree(flag);
+  free_csr(dI);
+  ok = hf == 0;
+  return GMG_OK;
+}
+
 static int build_sell_host(gmg_context *h, const HostCsr &m, double drop_tol, Sell &out) {
   DevCsr tmp;
   int rc = upload_host_csr(h, m, tmp);
@@ -267,22 +347,6 @@ static HostCsr add(const HostCsr &a, const HostCsr &b) {
   return c;
 }
 
-static HostCsr select_rows(const HostCsr &a, const std::vector<int> &rows) {
-  HostCsr s;
-  s.n_rows = (int)rows.size();
-  s.n_cols = a.n_cols;
-  s.rowptr.assign(rows.size() + 1, 0);
-  for (size_t i = 0; i < rows.size(); ++i) {
-    const int r = rows[i];
-    for (int64_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k) {
-      s.col.push_back(a.col[k]);
-      s.val.push_back(a.val[k]);
-    }
-    s.rowptr[i + 1] = (int64_t)s.col.size();
-  }
-  return s;
-}
-
 // greedy distance-1 colouring in row order over the significant (non-zero) couplings
 static std::vector<int> greedy_coloring(const HostCsr &a, int &n_colors) {
   std::vector<int> color(a.n_rows, -1);
@@ -340,14 +404,12 @@ static std::vector<std::vector<int>> wavefronts(const HostCsr &a, bool forward) 
   return out;
 }
 
-static int build_colorset(gmg_context *h, const HostCsr &a, const std::vector<int> &rows, ColorSet &cs) {
+// rows of one colour / wavefront as their own SELL matrix, cut out of the level's CSR on the device
+static int build_colorset(gmg_context *h, const DevCsr &a, const std::vector<int> &rows, ColorSet &cs) {
   cs.n = (int)rows.size();
-  HostCsr sub = select_rows(a, rows);
-  int rc = build_sell_host(h, sub, -1.0, cs.A);
-  if (rc) return rc;
   GMG_CUDA(h, dalloc(&cs.rows, cs.n));
-  GMG_CUDA(h, gmg::copy_sync(h, cs.rows, rows.data(), sizeof(int) * cs.n, cudaMemcpyHostToDevice));
-  return GMG_OK;
+  GMG_CUDA(h, copy(h, cs.rows, rows.data(), sizeof(int) * cs.n, cudaMemcpyHostToDevice));
+  return build_sell(h, a, -1.0, cs.A, cs.rows, cs.n);
 }
 
 static void free_level(Level &L) {
@@ -810,6 +872,10 @@ int gmg_destroy(gmg_handle h) {
   cudaStreamSynchronize(h->stream);
   for (auto e : h->ev_begin) cudaEventDestroy(e);
   for (auto e : h->ev_end) cudaEventDestroy(e);
+  for (int i = 0; i < 4; ++i) {
+    if (h->pin[i]) cudaFreeHost(h->pin[i]);
+    if (h->pin_free[i]) cudaEventDestroy(h->pin_free[i]);
+  }
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return GMG_OK;
@@ -837,6 +903,7 @@ int64_t gmg_launch_count(gmg_handle h) { return h ? h->launches : 0; }
 int gmg_set_num_levels(gmg_handle h, int n_levels) {
   if (!h || n_levels < 1) return GMG_EINVAL;
   gmg::enter(h);
+  TraceScope tr("gmg_set_num_levels");
   drop_vc_graphs(h);
   for (auto &L : h->levels) free_level(L);
   h->levels.assign(n_levels, Level{});
@@ -885,6 +952,7 @@ int gmg_set_matrix(gmg_handle h, int which, int level, int32_t n_rows, int32_t n
 int gmg_set_copy_indices(gmg_handle h, int level, int32_t n, const int32_t *gi, const int32_t *li) {
   if (!h || level < 0 || level >= h->n_levels || n < 0) return GMG_EINVAL;
   gmg::enter(h);
+  TraceScope tr("gmg_set_copy_indices");
   Level &L = h->levels[level];
   if (h->dist.on) {
     h->dist.h_copy_g.resize(h->n_levels);
@@ -977,7 +1045,7 @@ int gmg_setup(gmg_handle h) {
     if (L.rawA.rowptr) {
       TraceScope tr("    A -> sell");
       if ((rc = build_sell(h, L.rawA, h->drop_tol, L.A))) return rc;
-      free_csr(L.rawA);
+      if (l == 0) free_csr(L.rawA);  // levels >= 1 cut their colour / wavefront sub-matrices out of it below
       dfree(L.dinv);
       GMG_CUDA(h, dalloc(&L.dinv, L.n));
       if (L.n) {
@@ -999,8 +1067,13 @@ int gmg_setup(gmg_handle h) {
       if (L.hA.empty()) return fail(h, GMG_EINVAL, "host copy of level matrix missing");
       {
         TraceScope tr("    A+I");
-        HostCsr ai = add(L.hA, L.hI);
-        if ((rc = build_sell_host(h, ai, h->drop_tol, L.AI))) return rc;
+        bool on_device = false;
+        if (h->drop_tol < 0.0)
+          if ((rc = build_sum_on_device(h, L.A, L.hI, L.AI, on_device))) return rc;
+        if (!on_device) {  // an interface entry outside A's stored pattern (or entries were dropped): host merge
+          HostCsr ai = add(L.hA, L.hI);
+          if ((rc = build_sell_host(h, ai, h->drop_tol, L.AI))) return rc;
+        }
       }
       TraceScope tr_s("    I^T, colours / wavefronts");
       free_sell(L.IT);
@@ -1025,16 +1098,20 @@ int gmg_setup(gmg_handle h) {
         std::vector<std::vector<int>> rows(nc);
         for (int r = 0; r < L.n; ++r) rows[color[r]].push_back(r);
         L.colors.resize(nc);
+        if (!L.rawA.rowptr)
+          if ((rc = upload_host_csr(h, L.hA, L.rawA))) return rc;
         for (int c = 0; c < nc; ++c)
-          if ((rc = build_colorset(h, L.hA, rows[c], L.colors[c]))) return rc;
+          if ((rc = build_colorset(h, L.rawA, rows[c], L.colors[c]))) return rc;
       } else if (h->smoother == GMG_SMOOTHER_LEX_SSOR) {
         auto f = wavefronts(L.hA, true), b = wavefronts(L.hA, false);
         L.wave_fwd.resize(f.size());
         L.wave_bwd.resize(b.size());
+        if (!L.rawA.rowptr)
+          if ((rc = upload_host_csr(h, L.hA, L.rawA))) return rc;
         for (size_t c = 0; c < f.size(); ++c)
-          if ((rc = build_colorset(h, L.hA, f[c], L.wave_fwd[c]))) return rc;
+          if ((rc = build_colorset(h, L.rawA, f[c], L.wave_fwd[c]))) return rc;
         for (size_t c = 0; c < b.size(); ++c)
-          if ((rc = build_colorset(h, L.hA, b[c], L.wave_bwd[c]))) return rc;
+          if ((rc = build_colorset(h, L.rawA, b[c], L.wave_bwd[c]))) return rc;
       } else if (h->smoother == GMG_SMOOTHER_CHEBYSHEV) {
         // power iteration for lambda_max(D^-1 A) on the host copy (small levels), 20 steps
         const HostCsr &a = L.hA;
@@ -1061,6 +1138,7 @@ int gmg_setup(gmg_handle h) {
         L.lambda_max = lam;
       }
     }
+    free_csr(L.rawA);
     if (!L.hP.empty()) {
       TraceScope trp("    P, R");
       {

@@ -39,6 +39,7 @@ struct Sell {
   int64_t stored_nnz = 0;  // entries kept from the CSR (explicit zeros included unless dropped)
   int64_t padded = 0;      // elements in the sliced-ELL arrays
   bool valid = false;
+  bool shares_structure = false;  // slice_ptr / col belong to another Sell (A + I shares A's)
   std::vector<int64_t> h_slice_ptr;
   // optional lossless compressed copy (CsellView): 4 bytes per entry
   bool compressed = false;
@@ -182,6 +183,10 @@ struct gmg_context {
   int n_lists = 0;
   struct RhsState *rhs = nullptr;
   gmg::DistData dist;
+  // pinned staging ring for host->device uploads of large arrays (csrc/context.cu: staged_h2d)
+  char *pin[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t pin_free[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t pin_bytes = 0;
   // CUDA graphs of the fine-level parts of the V-cycle (down sweep / up sweep), keyed by (src, dst)
   struct VcGraph {
     const double *src = nullptr;

@@ -169,37 +169,45 @@ __global__ void sell_to_csell(SellView A, const int64_t *__restrict__ cslice_ptr
 // ------------------------------------------------------------------------------------------------
 // CSR -> SELL conversion (device side; the host hands over plain CSR)
 // ------------------------------------------------------------------------------------------------
-__global__ void csr_slice_widths(int n_rows, int n_slices, const int64_t *__restrict__ rowptr,
+// `rows` (optional): local row r is CSR row rows[r] (sub-matrices of one colour / wavefront)
+__global__ void csr_slice_widths(int n_rows, int n_slices, const int *__restrict__ rows, const int64_t *__restrict__ rowptr,
                                  const double *__restrict__ val, double drop_tol, int *__restrict__ width,
-                                 int *__restrict__ row_nnz) {
+                                 unsigned long long *__restrict__ total_nnz) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   int cnt = 0;
   if (r < n_rows) {
+    const int src = rows ? rows[r] : r;
     if (drop_tol < 0.0) {
-      cnt = (int)(rowptr[r + 1] - rowptr[r]);
+      cnt = (int)(rowptr[src + 1] - rowptr[src]);
     } else {
-      for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) cnt += (fabs(val[k]) > drop_tol) ? 1 : 0;
+      for (int64_t k = rowptr[src]; k < rowptr[src + 1]; ++k) cnt += (fabs(val[k]) > drop_tol) ? 1 : 0;
     }
-    row_nnz[r] = cnt;
   }
-  int m = cnt;
+  int m = cnt, sum = cnt;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && (r >> 5) < n_slices) width[r >> 5] = (m + 1) & ~1;
+  for (int o = 16; o > 0; o >>= 1) {
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (r >> 5) < n_slices) {
+    width[r >> 5] = (m + 1) & ~1;
+    if (sum) atomicAdd(total_nnz, (unsigned long long)sum);
+  }
 }
 
-__global__ void csr_to_sell(int n_rows, int n_cols, const int64_t *__restrict__ rowptr, const int *__restrict__ col,
-                            const double *__restrict__ val, double drop_tol, const int64_t *__restrict__ slice_ptr,
-                            double *__restrict__ sval, int *__restrict__ scol) {
+__global__ void csr_to_sell(int n_rows, int n_cols, const int *__restrict__ rows, const int64_t *__restrict__ rowptr,
+                            const int *__restrict__ col, const double *__restrict__ val, double drop_tol,
+                            const int64_t *__restrict__ slice_ptr, double *__restrict__ sval, int *__restrict__ scol) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int slice = r >> 5, lane = r & 31;
   if (slice >= (n_rows + 31) / 32) return;
   const int64_t b = slice_ptr[slice];
   const int w = (int)((slice_ptr[slice + 1] - b) >> 5);
   int j = 0;
-  const int pad_col = (r < n_cols) ? r : 0;
+  const int pad_col = rows ? 0 : ((r < n_cols) ? r : 0);
   if (r < n_rows) {
-    for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+    const int src = rows ? rows[r] : r;
+    for (int64_t k = rowptr[src]; k < rowptr[src + 1]; ++k) {
       const double v = val[k];
       if (drop_tol >= 0.0 && !(fabs(v) > drop_tol)) continue;
       const int64_t at = b + (int64_t)(j >> 1) * 64 + lane * 2 + (j & 1);
@@ -212,6 +220,31 @@ __global__ void csr_to_sell(int n_rows, int n_cols, const int64_t *__restrict__ 
     const int64_t at = b + (int64_t)(j >> 1) * 64 + lane * 2 + (j & 1);
     sval[at] = 0.0;
     scol[at] = pad_col;
+  }
+}
+
+// val(i, j) += v for the entries of a (small) CSR matrix whose pattern is contained in the SELL matrix's:
+// A + I of a level without a host round trip.  *flag != 0 if an entry has no slot.
+__global__ void sell_add_csr(SellView A, double *__restrict__ aval, int n_rows, const int64_t *__restrict__ rowptr,
+                             const int *__restrict__ col, const double *__restrict__ val, int *flag) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int64_t k0 = rowptr[r], k1 = rowptr[r + 1];
+  if (k0 == k1) return;
+  const int slice = r >> 5, lane = r & 31;
+  const int64_t b = A.slice_ptr[slice];
+  const int w = (int)((A.slice_ptr[slice + 1] - b) >> 5);
+  for (int64_t k = k0; k < k1; ++k) {
+    const int c = col[k];
+    bool found = false;
+    for (int j = 0; j < w && !found; ++j) {
+      const int64_t at = b + (int64_t)(j >> 1) * 64 + lane * 2 + (j & 1);
+      if (A.col[at] == c) {
+        aval[at] += val[k];
+        found = true;
+      }
+    }
+    if (!found) atomicOr(flag, 1);
   }
 }
 

@@ -221,10 +221,23 @@ void LaplaceProblem<dim>::make_mesh() {
 
 // =============================================================================== RHS path (device)
 namespace {
+struct HostTrace {
+  const char *name;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  bool on = std::getenv("GMG_TRACE") != nullptr;
+  explicit HostTrace(const char *n) : name(n) {}
+  ~HostTrace() {
+    if (on)
+      std::fprintf(stderr, "[step50 trace] %-34s %9.3f ms\n", name,
+                   1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
+}  // namespace
 struct ActiveCells {
   std::vector<double> lo, h;
   std::vector<int32_t> dofs, list;
 };
+namespace {
 ActiveCells flatten(const Forest &f, const DoFs &d, bool with_lists) {
   ActiveCells a;
   for (int l = 0; l < f.n_levels(); ++l)
@@ -267,6 +280,7 @@ void LaplaceProblem<dim>::rhs_assembly_optimization() {
 template <int dim>
 void LaplaceProblem<dim>::compute_charge_densities() {
   TimerOutput::Scope t(computing_timer, "Compute charge densities");
+  HostTrace tr("compute_charge_densities");
   const auto t0 = std::chrono::steady_clock::now();
   const int nq = (int)(degree + quadrature_degree_rhs);
   std::vector<double> gp, gw;
@@ -279,7 +293,10 @@ void LaplaceProblem<dim>::compute_charge_densities() {
         qpts.push_back(gp[y]);
         qpts.push_back(gp[z]);
       }
-  ActiveCells a = flatten(*triangulation, *mg_dof_handler, flag_rhs_assembly);
+  const ActiveCells &a = *active_cells_cache;
+  if (tr.on)
+    std::fprintf(stderr, "[step50 trace]   flatten %.3f ms\n",
+                 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   const int nc = (int)a.h.size();
   density_values.assign((size_t)nc * nq * nq * nq, 0.0);
   gmg_check(gmg_charge_density(gmg, nc, a.lo.data(), a.h.data(), a.list.data(), nq * nq * nq, qpts.data(), r_c,
@@ -329,6 +346,7 @@ template <int dim>
 void LaplaceProblem<dim>::setup_system(const unsigned int &cycle) {
   TimerOutput::Scope t(computing_timer, "Setup system");
   mg_dof_handler.reset(new DoFs(*triangulation));
+  active_cells_cache.reset(new ActiveCells(flatten(*triangulation, *mg_dof_handler, flag_rhs_assembly)));
   solution.assign(mg_dof_handler->n, 0.0);
   system_rhs.assign(mg_dof_handler->n, 0.0);
   if ((cycle == 0) && flag_rhs_assembly && lammpsinput) rhs_assembly_optimization();
@@ -355,7 +373,7 @@ void LaplaceProblem<dim>::assemble_system() {
 // load vector + constraints on the device (the RHS part of assemble_system, src/step-50.cc:798-828)
 template <int dim>
 void LaplaceProblem<dim>::assemble_rhs_on_device() {
-  const Forest &f = *triangulation;
+  HostTrace tr("assemble_rhs_on_device");
   const DoFs &d = *mg_dof_handler;
   const auto t0 = std::chrono::steady_clock::now();
   const int nq = (int)(degree + quadrature_degree_rhs), nq3 = nq * nq * nq;
@@ -373,7 +391,7 @@ void LaplaceProblem<dim>::assemble_rhs_on_device() {
           shape[(size_t)q * NV + v] = s;
         }
       }
-  ActiveCells a = flatten(f, d, false);
+  const ActiveCells &a = *active_cells_cache;
   const int nc = (int)a.h.size();
   const double *rho = nullptr;  // densities already on the device from compute_charge_densities
   std::vector<double> rho_host;
@@ -419,8 +437,10 @@ void LaplaceProblem<dim>::assemble_multigrid() {
   mg_ops = assemble_level_operators(*triangulation, *mg_dof_handler, coef);
 }
 
+
 template <int dim>
 void LaplaceProblem<dim>::hand_over_hierarchy() {
+  HostTrace tr_all("hand_over_hierarchy total");
   const DoFs &d = *mg_dof_handler;
   const bool mg = PreconditionerType == "GMG";
   const int nl = mg ? triangulation->n_levels() : 1;
@@ -472,6 +492,7 @@ void LaplaceProblem<dim>::hand_over_hierarchy() {
   }
   gmg_check(gmg_set_smoother(gmg, smoother_kind, smoother_omega, smoothing_steps), "gmg_set_smoother");
   gmg_check(gmg_set_coarse(gmg, 1000, 1e-10), "gmg_set_coarse");
+  HostTrace tr_setup("  gmg_setup (host view)");
   gmg_check(gmg_setup(gmg), "gmg_setup");
 }
 

@@ -60,6 +60,8 @@ class TimerOutput {
   std::chrono::steady_clock::time_point start = std::chrono::steady_clock::now();
 };
 
+struct ActiveCells;  // flattened active cells (lower corner, edge, dofs, atom-list id), cached per mesh
+
 // what one refinement cycle printed / computed (kept for the test shim)
 struct CycleRecord {
   long n_active_cells = 0, n_dofs = 0;
@@ -148,6 +150,7 @@ class LaplaceProblem {
 
   std::unique_ptr<ministep::Forest> triangulation;
   std::unique_ptr<ministep::DoFs> mg_dof_handler;
+  std::shared_ptr<ActiveCells> active_cells_cache;
   ministep::Csr system_matrix;
   ministep::LevelOperators mg_ops;  // mg_matrices, mg_interface_matrices, transfer matrices
   std::vector<double> solution, system_rhs, boundary_g, distributed_solution;
