@@ -38,6 +38,7 @@ SIGNATURES = {
     "gmg_set_coarse": (_i, [_h, _i, _d]),
     "gmg_set_level_coloring": (_i, [_h, _i, C.c_int32, _pi32]),
     "gmg_set_graphs": (_i, [_h, _i]),
+    "gmg_set_persistent_smoother": (_i, [_h, _i]),
     "gmg_set_drop_tolerance": (_i, [_h, _d]),
     "gmg_set_compression": (_i, [_h, _i]),
     "gmg_setup": (_i, [_h]),
@@ -172,6 +173,9 @@ class Gmg:
     def set_level_coloring(self, level, color):
         color = _i32(color)
         self._ck(self.lib.gmg_set_level_coloring(self.h, level, len(color), color.ctypes.data_as(_pi32)))
+
+    def set_persistent_smoother(self, on):
+        self._ck(self.lib.gmg_set_persistent_smoother(self.h, int(on)))
 
     def set_graphs(self, on):
         self._ck(self.lib.gmg_set_graphs(self.h, int(on)))

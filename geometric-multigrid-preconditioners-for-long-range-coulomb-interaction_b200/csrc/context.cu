@@ -426,6 +426,8 @@ static void free_level(Level &L) {
   dfree(L.tmp);
   dfree(L.copy_g);
   dfree(L.copy_l);
+  dfree(L.d_fwd);
+  dfree(L.d_bwd);
   for (auto *set : {&L.colors, &L.wave_fwd, &L.wave_bwd}) {
     for (auto &c : *set) {
       free_sell(c.A);
@@ -513,8 +515,18 @@ static int smooth(gmg_context *h, Level &L, double *&u, const double *rhs, bool 
   }
   if (h->smoother == GMG_SMOOTHER_MC_SSOR || h->smoother == GMG_SMOOTHER_LEX_SSOR) {
     // a relaxation sweep applied to (u, rhs) equals u + sweep(0, rhs - A u): no residual needed
-    if (zero_start) GMG_CUDA(h, cudaMemsetAsync(u, 0, sizeof(double) * n, h->stream));
     const bool lex = h->smoother == GMG_SMOOTHER_LEX_SSOR;
+    if (h->persistent_ssor && L.d_fwd && L.ssor_grid > 0) {
+      const ColorView *fw = (const ColorView *)L.d_fwd, *bw = (const ColorView *)L.d_bwd;
+      int n_fwd = L.n_fwd, n_bwd = L.n_bwd, rev = lex ? 0 : 1, nn = n, steps = h->steps, zs = zero_start ? 1 : 0;
+      double omega = h->omega;
+      const double *rp = rhs, *dp = L.dinv;
+      void *args[] = {&fw, &n_fwd, &bw, &n_bwd, &rev, &nn, &u, (void *)&rp, (void *)&dp, &omega, &steps, &zs};
+      GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)ssor_persistent<256>, dim3(L.ssor_grid), dim3(256), args, 0, h->stream));
+      h->launches++;
+      return GMG_OK;
+    }
+    if (zero_start) GMG_CUDA(h, cudaMemsetAsync(u, 0, sizeof(double) * n, h->stream));
     auto &fwd = lex ? L.wave_fwd : L.colors;
     auto &bwd = lex ? L.wave_bwd : L.colors;
     auto relax = [&](ColorSet &c) -> int {
@@ -1006,6 +1018,13 @@ int gmg_set_level_coloring(gmg_handle h, int level, int32_t n, const int32_t *co
   return GMG_OK;
 }
 
+int gmg_set_persistent_smoother(gmg_handle h, int on) {
+  if (!h) return GMG_EINVAL;
+  h->persistent_ssor = on != 0;
+  drop_vc_graphs(h);
+  return GMG_OK;
+}
+
 int gmg_set_graphs(gmg_handle h, int on) {
   if (!h) return GMG_EINVAL;
   h->use_graphs = on != 0;
@@ -1139,6 +1158,40 @@ int gmg_setup(gmg_handle h) {
       }
     }
     free_csr(L.rawA);
+    dfree(L.d_fwd);
+    dfree(L.d_bwd);
+    L.n_fwd = L.n_bwd = L.ssor_grid = 0;
+    if (l >= 1 && (h->smoother == GMG_SMOOTHER_MC_SSOR || h->smoother == GMG_SMOOTHER_LEX_SSOR)) {
+      const bool lex = h->smoother == GMG_SMOOTHER_LEX_SSOR;
+      auto &fw = lex ? L.wave_fwd : L.colors;
+      auto &bw = lex ? L.wave_bwd : L.colors;
+      std::vector<ColorView> vf, vb;
+      int max_slices = 1;
+      for (auto &cs : fw) {
+        vf.push_back(ColorView{cs.A.v, cs.rows});
+        max_slices = std::max(max_slices, cs.A.v.n_slices);
+      }
+      for (auto &cs : bw) {
+        vb.push_back(ColorView{cs.A.v, cs.rows});
+        max_slices = std::max(max_slices, cs.A.v.n_slices);
+      }
+      ColorView *df = nullptr, *db = nullptr;
+      GMG_CUDA(h, dalloc(&df, (int64_t)vf.size()));
+      GMG_CUDA(h, dalloc(&db, (int64_t)vb.size()));
+      if (!vf.empty()) GMG_CUDA(h, copy(h, df, vf.data(), sizeof(ColorView) * vf.size(), cudaMemcpyHostToDevice));
+      if (!vb.empty()) GMG_CUDA(h, copy(h, db, vb.data(), sizeof(ColorView) * vb.size(), cudaMemcpyHostToDevice));
+      L.d_fwd = df;
+      L.d_bwd = db;
+      L.n_fwd = (int)vf.size();
+      L.n_bwd = (int)vb.size();
+      // as many blocks as the widest colour can use (8 warps per block), at most what is co-resident
+      if (h->ssor_blocks_per_sm == 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ssor_persistent<256>, 256, 0) != cudaSuccess) per_sm = 0;
+        h->ssor_blocks_per_sm = std::max(per_sm, 0);
+      }
+      L.ssor_grid = std::min(h->sm_count * std::min(h->ssor_blocks_per_sm, 2), std::max(1, cdiv(max_slices, 8)));
+    }
     if (!L.hP.empty()) {
       TraceScope trp("    P, R");
       {

@@ -67,6 +67,8 @@ struct Level {
   int *copy_g = nullptr, *copy_l = nullptr;
   std::vector<ColorSet> colors;      // multicolour SSOR
   std::vector<ColorSet> wave_fwd, wave_bwd;  // level-scheduled lexicographic SSOR
+  void *d_fwd = nullptr, *d_bwd = nullptr;   // device arrays of ColorView for the persistent SSOR kernel
+  int n_fwd = 0, n_bwd = 0, ssor_grid = 0;
   double lambda_max = 0.0;           // Chebyshev
   std::vector<int32_t> user_color;   // optional colouring handed over by the host (gmg_set_level_coloring)
 };
@@ -196,6 +198,8 @@ struct gmg_context {
   };
   std::vector<VcGraph> vc_graphs;
   bool use_graphs = true;
+  bool persistent_ssor = false;  // measured slower than graph-replayed per-colour launches (60.4 vs 54.0 ms/step)
+  int ssor_blocks_per_sm = 0;
 };
 
 namespace gmg {

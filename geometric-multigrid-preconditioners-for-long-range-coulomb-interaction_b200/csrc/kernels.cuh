@@ -350,6 +350,47 @@ __global__ void __launch_bounds__(256) sell_color_relax(SellView Ac, const int *
   }
 }
 
+// One smooth() call of the multicolour / level-scheduled SSOR as ONE cooperative launch: colours (or wavefronts)
+// are separated by grid.sync() instead of kernel boundaries -- on the patch levels a colour is a few microseconds
+// of work, so launch gaps dominated (ncu: 896 launches = 19 % of a step before this kernel).
+struct ColorView {
+  SellView A;
+  const int *rows;
+};
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) ssor_persistent(const ColorView *__restrict__ fwd, int n_fwd,
+                                                         const ColorView *__restrict__ bwd, int n_bwd, int bwd_reversed,
+                                                         int n, double *u, const double *__restrict__ rhs,
+                                                         const double *__restrict__ dinv, double omega, int steps,
+                                                         int zero_start) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * BLOCK + threadIdx.x) >> 5, nwarps = (gridDim.x * BLOCK) >> 5;
+  if (zero_start) {
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) u[i] = 0.0;
+    grid.sync();
+  }
+  for (int s = 0; s < steps; ++s)
+    for (int pass = 0; pass < 2; ++pass) {
+      const ColorView *set = pass == 0 ? fwd : bwd;
+      const int nc = pass == 0 ? n_fwd : n_bwd;
+      for (int k = 0; k < nc; ++k) {
+        const ColorView &C = set[(pass == 1 && bwd_reversed) ? nc - 1 - k : k];
+        for (int sl = gwarp; sl < C.A.n_slices; sl += nwarps) {
+          const double ax = sell_row_dot<false>(C.A, sl, lane, u);
+          const int r = sl * 32 + lane;
+          if (r < C.A.n_rows) {
+            const int i = C.rows[r];
+            u[i] += omega * (rhs[i] - ax) * dinv[i];
+          }
+        }
+        grid.sync();
+      }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // vector kernels
 // ------------------------------------------------------------------------------------------------
