@@ -222,6 +222,7 @@ inline void dfree(T *&p) {
 int fail(gmg_context *h, int code, const std::string &msg);
 int ensure_stage(gmg_context *h, int64_t n);
 void rhs_free(gmg_context *h);
+void rhs_invalidate_partition(gmg_context *h);
 inline cudaError_t copy(gmg_context *h, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
   if (kind == cudaMemcpyHostToDevice) h->h2d_bytes += (int64_t)bytes;
   if (kind == cudaMemcpyDeviceToHost) h->d2h_bytes += (int64_t)bytes;

@@ -372,26 +372,31 @@ static int dist_coarse_cg(gmg_context *h, const double *b, double *x) {
   return GMG_OK;
 }
 
-// PreconditionMG::vmult, distributed: src / dst are owned-only system vectors
-static int dist_vcycle(gmg_context *h, const double *src, double *dst) {
+// PreconditionMG::vmult, distributed: src / dst are owned-only system vectors.  Split into the parts that talk to
+// peers (sequence-numbered, launched directly) and the purely local sweeps (replayed as CUDA graphs).
+static int dist_vc_pre(gmg_context *h, const double *src) {  // copy_to_mg
   DistData &d = h->dist;
   const int nl = h->n_levels;
-  // copy_to_mg
   GMG_CUDA(h, cudaMemsetAsync(d.l0_defect, 0, sizeof(double) * std::max(d.n_l0_owned, 1), h->stream));
   if (d.n_copy0) {
     vec_gather<<<cdiv(d.n_copy0, 256), 256, 0, h->stream>>>(d.n_copy0, d.copy0_l0, d.copy0_sys, src, d.l0_defect);
     GMG_LAUNCH_CHECK(h);
   }
-  if (nl > 1) {
+  if (nl > 1)
     if (int rc = dist_gather(h, d.gather_g, src, CH_GATHER_G)) return rc;
-    const double *gg = reinterpret_cast<const double *>(d.buf + d.gather_g.region);
-    for (int l = 1; l < nl; ++l) {
-      Level &L = h->levels[l];
-      GMG_CUDA(h, cudaMemsetAsync(L.defect, 0, sizeof(double) * std::max(L.n, 1), h->stream));
-      if (L.n_copy) {
-        vec_gather_from<<<cdiv(L.n_copy, 256), 256, 0, h->stream>>>(L.n_copy, L.copy_l, gg + d.gather_g_offset[l], L.defect);
-        GMG_LAUNCH_CHECK(h);
-      }
+  return GMG_OK;
+}
+
+static int dist_vc_down(gmg_context *h) {
+  DistData &d = h->dist;
+  const int nl = h->n_levels;
+  const double *gg = reinterpret_cast<const double *>(d.buf + d.gather_g.region);
+  for (int l = 1; l < nl; ++l) {
+    Level &L = h->levels[l];
+    GMG_CUDA(h, cudaMemsetAsync(L.defect, 0, sizeof(double) * std::max(L.n, 1), h->stream));
+    if (L.n_copy) {
+      vec_gather_from<<<cdiv(L.n_copy, 256), 256, 0, h->stream>>>(L.n_copy, L.copy_l, gg + d.gather_g_offset[l], L.defect);
+      GMG_LAUNCH_CHECK(h);
     }
   }
   for (int l = nl - 1; l >= 1; --l) {
@@ -404,13 +409,17 @@ static int dist_vcycle(gmg_context *h, const double *src, double *dst) {
       if (int rc = spmv<EPI_ADD, DOT_NONE>(h, d.R0, L.t, d.l0_defect)) return rc;
     }
   }
-  if (int rc = dist_coarse_cg(h, d.l0_defect, d.l0_sol)) return rc;
+  return GMG_OK;
+}
+
+static int dist_vc_up(gmg_context *h, double *dst) {
+  DistData &d = h->dist;
+  const int nl = h->n_levels;
   for (int l = 1; l < nl; ++l) {
     Level &L = h->levels[l];
     if (l > 1) {
       if (int rc = spmv<EPI_ADD, DOT_NONE>(h, h->levels[l - 1].P, h->levels[l - 1].sol, L.sol)) return rc;
     } else {
-      if (int rc = dist_gather(h, d.gather_c, d.l0_sol, CH_GATHER_C)) return rc;
       const double *c = reinterpret_cast<const double *>(d.buf + d.gather_c.region);
       if (int rc = spmv<EPI_ADD, DOT_NONE>(h, d.P0F, c, L.sol)) return rc;
     }
@@ -430,6 +439,47 @@ static int dist_vcycle(gmg_context *h, const double *src, double *dst) {
       GMG_LAUNCH_CHECK(h);
     }
   return GMG_OK;
+}
+
+static int dist_vcycle(gmg_context *h, const double *src, double *dst) {
+  DistData &d = h->dist;
+  const int nl = h->n_levels;
+  const bool graphs = h->use_graphs && nl > 1 && h->smoother != GMG_SMOOTHER_JACOBI;
+  gmg_context::VcGraph *g = nullptr;
+  if (graphs) {
+    for (auto &c : h->vc_graphs)
+      if (c.src == src && c.dst == dst) g = &c;
+    if (!g && h->vc_graphs.size() < 8) {
+      gmg_context::VcGraph ng;
+      ng.src = src;
+      ng.dst = dst;
+      if (capture_graph(h, [&]() { return dist_vc_down(h); }, ng.down, ng.n_down) == GMG_OK &&
+          capture_graph(h, [&]() { return dist_vc_up(h, dst); }, ng.up, ng.n_up) == GMG_OK) {
+        h->vc_graphs.push_back(ng);
+        g = &h->vc_graphs.back();
+      } else {
+        if (ng.down) cudaGraphExecDestroy(ng.down);
+        if (ng.up) cudaGraphExecDestroy(ng.up);
+        h->use_graphs = false;
+      }
+    }
+  }
+  if (int rc = dist_vc_pre(h, src)) return rc;
+  if (g) {
+    GMG_CUDA(h, cudaGraphLaunch(g->down, h->stream));
+    h->launches += g->n_down;
+  } else if (int rc = dist_vc_down(h)) {
+    return rc;
+  }
+  if (int rc = dist_coarse_cg(h, d.l0_defect, d.l0_sol)) return rc;
+  if (nl > 1)
+    if (int rc = dist_gather(h, d.gather_c, d.l0_sol, CH_GATHER_C)) return rc;
+  if (g) {
+    GMG_CUDA(h, cudaGraphLaunch(g->up, h->stream));
+    h->launches += g->n_up;
+    return GMG_OK;
+  }
+  return dist_vc_up(h, dst);
 }
 
 // distributed SolverCG with the GMG preconditioner; b, x are GLOBAL-length device vectors (every rank holds
@@ -589,6 +639,7 @@ int gmg_set_ownership(gmg_handle h, int which, int level, int32_t n, const int32
   else if (which == GMG_LEVEL && level == 0) h->dist.l0_owner.assign(owner, owner + n);
   else return fail(h, GMG_EINVAL, "ownership is defined for the system matrix and level 0 (patch levels are replicated)");
   h->is_setup = false;
+  rhs_invalidate_partition(h);
   return GMG_OK;
 }
 

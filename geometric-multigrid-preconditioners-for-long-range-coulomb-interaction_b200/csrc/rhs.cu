@@ -24,6 +24,9 @@ struct RhsState {
   uint8_t *constrained = nullptr;
   bool have_kref = false, have_ghat = false;
   bool bin_pending = false;  // first call of the two-call gmg_bin_atoms protocol done
+  // multi-GPU: the cells that touch a dof this rank owns (the only ones its part of b depends on)
+  int *dist_cells = nullptr;
+  int n_dist_cells = -1;
 };
 
 namespace {
@@ -130,9 +133,9 @@ __global__ void __launch_bounds__(128) density_kernel(int n_cells, const double 
                                                       const int *__restrict__ list_atoms, int n_atoms,
                                                       const double *__restrict__ pos, const double *__restrict__ charge,
                                                       int n_q, const double *__restrict__ qpts, double C, double inv_rc2,
-                                                      double *__restrict__ rho) {
+                                                      double *__restrict__ rho, const int *__restrict__ cell_list) {
   extern __shared__ double sacc[];  // blockDim.x
-  const int c = blockIdx.x;
+  const int c = cell_list ? cell_list[blockIdx.x] : blockIdx.x;
   const int t = threadIdx.x;
   const int groups = max((int)blockDim.x / n_q, 1);  // threads per q-point
   const int lo_t = t % n_q, grp = t / n_q;
@@ -178,9 +181,11 @@ __global__ void __launch_bounds__(128) load_vector_kernel(int n_cells, const dou
                                                           const int64_t *__restrict__ hang_ptr,
                                                           const int *__restrict__ hang_col,
                                                           const double *__restrict__ hang_val,
-                                                          const uint8_t *__restrict__ constrained, double *b) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_cells) return;
+                                                          const uint8_t *__restrict__ constrained, double *b,
+                                                          const int *__restrict__ cell_list) {
+  const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ci >= n_cells) return;
+  const int c = cell_list ? cell_list[ci] : ci;
   const double hh = cell_h[c];
   const double jac = hh * hh * hh;
   double f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -243,23 +248,43 @@ __global__ void point_values_kernel(int n, const int *__restrict__ cell_dofs, co
   out[p] = s;
 }
 
-int run_density(gmg_context *h, RhsState *s) {
+// a cell contributes to this rank's rows of b if one of its dofs is owned here, or is a hanging node with a
+// parent owned here (its share is redistributed to the parents)
+__global__ void select_owned_cells(int n_cells, const int *__restrict__ cell_dofs, const int *__restrict__ owner, int rank,
+                                   const int64_t *__restrict__ hang_ptr, const int *__restrict__ hang_col,
+                                   int *__restrict__ list, int *__restrict__ count) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  bool mine = false;
+  for (int v = 0; v < 8; ++v) {
+    const int dof = cell_dofs[(int64_t)c * 8 + v];
+    mine |= owner[dof] == rank;
+    for (int64_t p = hang_ptr[dof]; p < hang_ptr[dof + 1]; ++p) mine |= owner[hang_col[p]] == rank;
+  }
+  if (mine) list[atomicAdd(count, 1)] = c;
+}
+
+int run_density(gmg_context *h, RhsState *s, const int *cell_list = nullptr, int n_list = 0) {
   if (s->n_cells == 0) return GMG_OK;
   const double C = 4.0 * M_PI / (s->r_c * s->r_c * s->r_c * std::pow(M_PI, 1.5));  // src/step-50.cc:522
   const int block = (s->n_q <= 64) ? 64 : 128;  // threads per cell: blockDim / n_q threads share a q-point
-  density_kernel<<<s->n_cells, block, sizeof(double) * block, h->stream>>>(
+  const int grid = cell_list ? n_list : s->n_cells;
+  if (grid == 0) return GMG_OK;
+  density_kernel<<<grid, block, sizeof(double) * block, h->stream>>>(
       s->n_cells, s->cell_lo, s->cell_h, s->list_of_cell, h->list_ptr, h->list_atoms, h->n_atoms, h->atom_pos, h->atom_q,
-      s->n_q, s->qpts, C, 1.0 / (s->r_c * s->r_c), s->rho);
+      s->n_q, s->qpts, C, 1.0 / (s->r_c * s->r_c), s->rho, cell_list);
   GMG_LAUNCH_CHECK(h);
   return GMG_OK;
 }
 
-int run_load_vector(gmg_context *h, RhsState *s, const double *rho_dev, double *b_dev) {
+int run_load_vector(gmg_context *h, RhsState *s, const double *rho_dev, double *b_dev, const int *cell_list = nullptr,
+                    int n_list = 0) {
   GMG_CUDA(h, cudaMemsetAsync(b_dev, 0, sizeof(double) * s->n_dofs, h->stream));
-  if (s->a_cells == 0) return GMG_OK;
-  load_vector_kernel<<<cdiv(s->a_cells, 128), 128, 0, h->stream>>>(
-      s->a_cells, rho_dev, s->a_h, s->cell_dofs, s->a_nq, s->shape, s->weights, s->have_kref ? s->kref : nullptr,
-      s->have_ghat ? s->ghat : nullptr, s->hang_ptr, s->hang_col, s->hang_val, s->constrained, b_dev);
+  const int n = cell_list ? n_list : s->a_cells;
+  if (n == 0) return GMG_OK;
+  load_vector_kernel<<<cdiv(n, 128), 128, 0, h->stream>>>(
+      n, rho_dev, s->a_h, s->cell_dofs, s->a_nq, s->shape, s->weights, s->have_kref ? s->kref : nullptr,
+      s->have_ghat ? s->ghat : nullptr, s->hang_ptr, s->hang_col, s->hang_val, s->constrained, b_dev, cell_list);
   GMG_LAUNCH_CHECK(h);
   return GMG_OK;
 }
@@ -267,6 +292,9 @@ int run_load_vector(gmg_context *h, RhsState *s, const double *rho_dev, double *
 }  // namespace
 
 namespace gmg {
+void rhs_invalidate_partition(gmg_context *h) {
+  if (h->rhs) h->rhs->n_dist_cells = -1;
+}
 void rhs_free(gmg_context *h) {
   RhsState *s = h->rhs;
   if (!s) return;
@@ -285,6 +313,7 @@ void rhs_free(gmg_context *h) {
   dfree(s->hang_col);
   dfree(s->hang_ptr);
   dfree(s->constrained);
+  dfree(s->dist_cells);
   delete s;
   h->rhs = nullptr;
 }
@@ -451,6 +480,7 @@ int gmg_charge_density(gmg_handle h, int32_t n_cells, const double *cell_lo, con
   s->n_cells = n_cells;
   s->n_q = n_q;
   s->r_c = r_c;
+  s->n_dist_cells = -1;
   if (int rc = upload(h, s->cell_lo, cell_lo, 3 * (int64_t)n_cells)) return rc;
   if (int rc = upload(h, s->cell_h, cell_h, n_cells)) return rc;
   if (int rc = upload(h, s->list_of_cell, list_of_cell, n_cells)) return rc;
@@ -477,6 +507,7 @@ int gmg_assemble_rhs(gmg_handle h, int32_t n_cells, const double *rho, const dou
   s->a_cells = n_cells;
   s->a_nq = n_q;
   s->n_dofs = n_dofs;
+  s->n_dist_cells = -1;
   if (int rc = upload(h, s->a_h, cell_h, n_cells)) return rc;
   if (int rc = upload(h, s->cell_dofs, cell_dofs, 8 * (int64_t)n_cells)) return rc;
   if (int rc = upload(h, s->shape, shape, 8 * (int64_t)n_q)) return rc;
@@ -510,6 +541,26 @@ int gmg_rhs_step_dev(gmg_handle h, double *b_dev) {
   gmg::enter(h);
   RhsState *s = h->rhs;
   if (s->n_cells != s->a_cells || s->n_q != s->a_nq) return fail(h, GMG_EINVAL, "density / load-vector inputs differ");
+  if (h->dist.on && (int)h->dist.sys_owner.size() == s->n_dofs) {
+    // multi-GPU: a rank's rows of b depend only on the cells touching its dofs; the solve reads only those rows
+    if (s->n_dist_cells < 0) {
+      int *owner = nullptr, *count = nullptr;
+      dfree(s->dist_cells);
+      GMG_CUDA(h, dalloc(&owner, s->n_dofs));
+      GMG_CUDA(h, dalloc(&count, 1));
+      GMG_CUDA(h, dalloc(&s->dist_cells, s->a_cells));
+      GMG_CUDA(h, gmg::copy(h, owner, h->dist.sys_owner.data(), sizeof(int) * s->n_dofs, cudaMemcpyHostToDevice));
+      GMG_CUDA(h, cudaMemsetAsync(count, 0, sizeof(int), h->stream));
+      select_owned_cells<<<cdiv(std::max(s->a_cells, 1), 256), 256, 0, h->stream>>>(
+          s->a_cells, s->cell_dofs, owner, h->dist.rank, s->hang_ptr, s->hang_col, s->dist_cells, count);
+      h->launches++;
+      GMG_CUDA(h, gmg::copy_sync(h, &s->n_dist_cells, count, sizeof(int), cudaMemcpyDeviceToHost));
+      dfree(owner);
+      dfree(count);
+    }
+    if (int rc = run_density(h, s, s->dist_cells, s->n_dist_cells)) return rc;
+    return run_load_vector(h, s, s->rho, b_dev, s->dist_cells, s->n_dist_cells);
+  }
   if (int rc = run_density(h, s)) return rc;
   return run_load_vector(h, s, s->rho, b_dev);
 }
