@@ -69,6 +69,30 @@ def test_main_executable_lattice_8_atoms_reproduces_cluster_log(tmp_path, golden
     assert its[0] == 1
 
 
+def test_64k_atoms_five_cycles_reproduce_cluster_log(tmp_path, goldens):
+    """BASELINE config 4 at full size (atom_n20_64000, the SSOR_64k_atoms.o876224 run): cell / DoF counts per level,
+    ||b||_2 of cycle 0, starting residuals and solution norms of all 5 cycles to the printed digits; CG iteration
+    counts within +-2 (the log ran 20-rank block SSOR; here: multicolour SSOR)."""
+    P = pkg()
+    pos, q = P.lattice.nacl_lattice(20)
+    atom = tmp_path / "atom_n20_64000.data"
+    P.lattice.write_lammps(str(atom), pos, q)
+    text, recs = hostlib.run_problem(P.lattice.cluster_prm(str(atom), 20, cycles=5, smoother="MulticolourSSOR"))
+    g = goldens["cluster_ssor_64k"][0]["cycles"]
+    assert goldens["cluster_ssor_64k"][0]["n_atoms"] == 64000 and len(recs) == 5
+    for c, (rec, gold) in enumerate(zip(recs, g)):
+        assert rec["n_active_cells"] == gold["n_active_cells"]
+        assert rec["n_dofs_level"] == gold["n_dofs_level"]
+        digits = gold["start_digits"]
+        tol = 0.5000001 * 10.0 ** (-len(digits.split(".")[1])) + 2e-9
+        assert abs(rec["start"] - gold["start"]) <= tol, (c, rec["start"], digits)
+        assert abs(rec["its"] - gold["its"]) <= 2
+        for k in ("sol_l1", "sol_l2", "sol_linf"):
+            assert abs(rec[k] - gold[k]) <= 2e-7 * gold[k], (c, k, rec[k], gold[k])
+    assert recs[0]["its"] == 1 and recs[0]["coarse_its"] == [243]
+    assert abs(recs[0]["conv"] - g[0]["conv"]) <= 1e-4 * g[0]["conv"]
+
+
 def test_missing_parameter_file_and_bad_device_fail_loudly(tmp_path):
     exe = os.path.join(os.path.dirname(pkg().capi.LIB_PATH), "main")
     out = subprocess.run([exe], capture_output=True, text=True)
