@@ -292,7 +292,7 @@ class Gmg:
         out = np.zeros(6)
         self._ck(self.lib.gmg_matrix_traffic(self.h, which, level, _pd_of(out)))
         return dict(nnz=out[0], spmv_bytes=out[1], cg_iter_bytes=out[2], csr_spmv_bytes=out[3], csr_cg_iter_bytes=out[4],
-                    compressed=bool(out[5]))
+                    compressed=bool(out[5]), format=int(out[5]))
 
     def coarse_profile(self, reset=True):
         ms, n, it = _d(0), _i64(0), _i64(0)

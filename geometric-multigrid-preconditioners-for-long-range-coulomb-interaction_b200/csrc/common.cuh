@@ -124,6 +124,18 @@ struct CsellView {
   int dict_n;
 };
 
+// Row-pattern dictionary format (pattern.cuh): one pattern id per row + the table of distinct rows.
+struct PatView {
+  int n_rows, n_cols, n_slices;
+  const uint32_t *pat;   // pattern id per row (padded to a multiple of 32 rows with the empty pattern)
+  const int *ptr;        // n_pat + 1 offsets into off / val
+  const int *off;        // column - row
+  const double *val;
+  int n_pat, n_ent;       // n_pat includes the empty pattern (id n_pat - 1): row handled by the remainder / padding
+  SellView rem;           // rows whose pattern is not in the table, as a SELL matrix (zeros dropped) ...
+  const int *rem_rows;    // ... and their row indices, ascending
+};
+
 struct PcgScalars {
   double gh[2];   // g.h, double-buffered (beta = gh[new] / gh[old])
   double dh;      // d.(A d)

@@ -6,6 +6,8 @@
 #include <thread>
 
 #include "context.h"
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include "kernels.cuh"
 // (dist.cuh uses RowDot / CSELL_SMEM_DICT from kernels.cuh)
 #include "dist.cuh"
@@ -34,6 +36,14 @@ static void free_sell(Sell &s) {
   dfree(s.cslice_ptr);
   dfree(s.ent);
   dfree(s.dict);
+  dfree(s.pat);
+  dfree(s.pat_ptr);
+  dfree(s.pat_off);
+  dfree(s.pat_val);
+  dfree(s.rem_rows);
+  dfree(s.rem_slice_ptr);
+  dfree(s.rem_val);
+  dfree(s.rem_col);
   s = Sell{};
 }
 static void free_csr(DevCsr &c) {
@@ -249,6 +259,174 @@ static int build_csell(gmg_context *h, Sell &s) {
   return GMG_OK;
 }
 
+// Row-pattern dictionary copy (pattern.cuh) of a SELL matrix: the frequent rows through the shared-memory pattern
+// table, the rest as a (small) remainder SELL matrix.  Leaves s.patterned == false when fewer than 3/4 of the rows
+// are covered by the table or (never observed) a row fails the entry-by-entry verification.
+static int build_pat(gmg_context *h, Sell &s) {
+  s.patterned = false;
+  if (!s.valid || s.v.n_slices == 0) return GMG_OK;
+  TraceScope tr("    row patterns");
+  constexpr int LOG_TABLE = 18, LIMIT = 120000, MIN_COUNT = 16;
+  const int mask = (1 << LOG_TABLE) - 1;
+  const int n = s.v.n_rows, n_padded = s.v.n_slices * 32;
+  uint64_t *hash = nullptr;
+  unsigned long long *keys = nullptr;
+  int *rep = nullptr, *cnt = nullptr, *d_count = nullptr, *slot_pid = nullptr, *pid_rep = nullptr, *width = nullptr;
+  unsigned char *irregular = nullptr;
+  void *cub_tmp = nullptr;
+  int *sub_width = nullptr;
+  auto cleanup = [&]() {
+    dfree(hash);
+    dfree(keys);
+    dfree(rep);
+    dfree(cnt);
+    dfree(d_count);
+    dfree(slot_pid);
+    dfree(pid_rep);
+    dfree(width);
+    dfree(irregular);
+    dfree(sub_width);
+    if (cub_tmp) cudaFreeAsync(cub_tmp, h->stream);
+    cub_tmp = nullptr;
+  };
+  auto drop = [&]() {
+    cleanup();
+    dfree(s.pat);
+    dfree(s.pat_ptr);
+    dfree(s.pat_off);
+    dfree(s.pat_val);
+    dfree(s.rem_rows);
+    dfree(s.rem_slice_ptr);
+    dfree(s.rem_val);
+    dfree(s.rem_col);
+  };
+  GMG_CUDA(h, dalloc(&hash, n));
+  GMG_CUDA(h, dalloc(&keys, (int64_t)mask + 1));
+  GMG_CUDA(h, dalloc(&rep, (int64_t)mask + 1));
+  GMG_CUDA(h, dalloc(&cnt, (int64_t)mask + 1));
+  GMG_CUDA(h, dalloc(&d_count, 4));
+  GMG_CUDA(h, cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * ((size_t)mask + 1), h->stream));
+  GMG_CUDA(h, cudaMemsetAsync(rep, 0x7f, sizeof(int) * ((size_t)mask + 1), h->stream));
+  GMG_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)mask + 1), h->stream));
+  GMG_CUDA(h, cudaMemsetAsync(d_count, 0, 4 * sizeof(int), h->stream));
+  pat_row_hash<<<cdiv(n, 256), 256, 0, h->stream>>>(s.v, hash);
+  GMG_LAUNCH_CHECK(h);
+  pat_table_insert<<<cdiv(n, 256), 256, 0, h->stream>>>(n, hash, keys, rep, cnt, mask, d_count, LIMIT);
+  GMG_LAUNCH_CHECK(h);
+  int count = 0;
+  GMG_CUDA(h, copy_sync(h, &count, d_count, sizeof(int), cudaMemcpyDeviceToHost));
+  if (count > LIMIT) {
+    cleanup();
+    return GMG_OK;
+  }
+  std::vector<unsigned long long> hk((size_t)mask + 1);
+  std::vector<int> hrep((size_t)mask + 1), hcnt((size_t)mask + 1);
+  GMG_CUDA(h, copy(h, hk.data(), keys, sizeof(unsigned long long) * hk.size(), cudaMemcpyDeviceToHost));
+  GMG_CUDA(h, copy(h, hrep.data(), rep, sizeof(int) * hrep.size(), cudaMemcpyDeviceToHost));
+  GMG_CUDA(h, copy_sync(h, hcnt.data(), cnt, sizeof(int) * hcnt.size(), cudaMemcpyDeviceToHost));
+  struct Entry {
+    int slot, rep, cnt;
+  };
+  std::vector<Entry> ents;
+  for (int i = 0; i <= mask; ++i)
+    if (hk[i] != 0ull && hcnt[i] >= MIN_COUNT) ents.push_back(Entry{i, hrep[i], hcnt[i]});
+  // most frequent first; ties by representative row: deterministic
+  std::sort(ents.begin(), ents.end(), [](const Entry &a, const Entry &b) { return a.cnt != b.cnt ? a.cnt > b.cnt : a.rep < b.rep; });
+  if (ents.size() > 4 * (size_t)PAT_MAX_PAT) ents.resize(4 * (size_t)PAT_MAX_PAT);
+  const int n_cand = (int)ents.size();
+  if (n_cand == 0) {
+    cleanup();
+    return GMG_OK;
+  }
+  std::vector<int> h_cand_rep(n_cand);
+  for (int p = 0; p < n_cand; ++p) h_cand_rep[p] = ents[p].rep;
+  GMG_CUDA(h, dalloc(&pid_rep, n_cand));
+  GMG_CUDA(h, dalloc(&width, n_cand));
+  GMG_CUDA(h, copy(h, pid_rep, h_cand_rep.data(), sizeof(int) * n_cand, cudaMemcpyHostToDevice));
+  pat_widths<<<cdiv(n_cand, 128), 128, 0, h->stream>>>(s.v, n_cand, pid_rep, width);
+  GMG_LAUNCH_CHECK(h);
+  std::vector<int> hw(n_cand);
+  GMG_CUDA(h, copy_sync(h, hw.data(), width, sizeof(int) * n_cand, cudaMemcpyDeviceToHost));
+  // the table holds the most frequent patterns that fit the shared-memory budget; pattern np = the empty pattern
+  std::vector<int> hptr(1, 0), h_pid_rep, h_slot_pid((size_t)mask + 1, -1);
+  int64_t covered = 0;
+  for (int p = 0; p < n_cand && (int)h_pid_rep.size() < PAT_MAX_PAT; ++p) {
+    if (hptr.back() + hw[p] > PAT_MAX_ENT) continue;
+    h_slot_pid[ents[p].slot] = (int)h_pid_rep.size();
+    h_pid_rep.push_back(ents[p].rep);
+    hptr.push_back(hptr.back() + hw[p]);
+    covered += ents[p].cnt;
+  }
+  const int np = (int)h_pid_rep.size();
+  if (covered * 4 < (int64_t)n * 3) {
+    cleanup();
+    return GMG_OK;
+  }
+  for (auto &v : h_slot_pid)
+    if (v < 0) v = np;
+  hptr.push_back(hptr.back());
+  const int n_ent = hptr[np];
+  GMG_CUDA(h, dalloc(&slot_pid, (int64_t)mask + 1));
+  GMG_CUDA(h, copy(h, slot_pid, h_slot_pid.data(), sizeof(int) * h_slot_pid.size(), cudaMemcpyHostToDevice));
+  GMG_CUDA(h, copy(h, pid_rep, h_pid_rep.data(), sizeof(int) * np, cudaMemcpyHostToDevice));
+  GMG_CUDA(h, dalloc(&s.pat_ptr, np + 2));
+  GMG_CUDA(h, dalloc(&s.pat_off, n_ent));
+  GMG_CUDA(h, dalloc(&s.pat_val, n_ent));
+  GMG_CUDA(h, dalloc(&s.pat, n_padded));
+  GMG_CUDA(h, dalloc(&irregular, n_padded));
+  GMG_CUDA(h, cudaMemsetAsync(irregular, 0, n_padded, h->stream));
+  GMG_CUDA(h, copy(h, s.pat_ptr, hptr.data(), sizeof(int) * (np + 2), cudaMemcpyHostToDevice));
+  pat_fill<<<cdiv(np, 128), 128, 0, h->stream>>>(s.v, np, pid_rep, s.pat_ptr, s.pat_off, s.pat_val);
+  GMG_LAUNCH_CHECK(h);
+  pat_assign_verify<<<cdiv(n_padded, 256), 256, 0, h->stream>>>(s.v, hash, keys, slot_pid, mask, s.pat_ptr, s.pat_off, s.pat_val,
+                                                                np, s.pat, irregular, d_count + 1);
+  GMG_LAUNCH_CHECK(h);
+  // remainder rows, ascending
+  const int n_rem_max = (int)((int64_t)n - covered);
+  GMG_CUDA(h, dalloc(&s.rem_rows, n_rem_max));
+  size_t tmp_bytes = 0;
+  thrust::counting_iterator<int> iota(0);
+  GMG_CUDA(h, cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, irregular, s.rem_rows, d_count + 2, n, h->stream));
+  GMG_CUDA(h, cudaMallocAsync(&cub_tmp, std::max<size_t>(tmp_bytes, 1), h->stream));
+  GMG_CUDA(h, cub::DeviceSelect::Flagged(cub_tmp, tmp_bytes, iota, irregular, s.rem_rows, d_count + 2, n, h->stream));
+  int flags[4] = {0, 0, 0, 0};
+  GMG_CUDA(h, copy_sync(h, flags, d_count, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+  const int n_rem = flags[2];
+  if (flags[1] != 0 || n_rem != n_rem_max) {
+    drop();
+    return GMG_OK;
+  }
+  const int rs = cdiv(n_rem, SLICE);
+  std::vector<int64_t> rsp(rs + 1, 0);
+  if (rs > 0) {
+    GMG_CUDA(h, dalloc(&sub_width, rs));
+    sell_sub_widths<<<cdiv((int64_t)rs * 32, 256), 256, 0, h->stream>>>(s.v, n_rem, s.rem_rows, sub_width);
+    GMG_LAUNCH_CHECK(h);
+    std::vector<int> rw(rs);
+    GMG_CUDA(h, copy_sync(h, rw.data(), sub_width, sizeof(int) * rs, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < rs; ++i) rsp[i + 1] = rsp[i] + (int64_t)rw[i] * SLICE;
+  }
+  s.rem_padded = rsp[rs];
+  GMG_CUDA(h, dalloc(&s.rem_slice_ptr, rs + 1));
+  GMG_CUDA(h, dalloc(&s.rem_val, s.rem_padded));
+  GMG_CUDA(h, dalloc(&s.rem_col, s.rem_padded));
+  GMG_CUDA(h, copy(h, s.rem_slice_ptr, rsp.data(), sizeof(int64_t) * (rs + 1), cudaMemcpyHostToDevice));
+  if (rs > 0) {
+    sell_sub_fill<<<cdiv((int64_t)rs * 32, 256), 256, 0, h->stream>>>(s.v, n_rem, s.rem_rows, s.rem_slice_ptr, s.rem_val, s.rem_col);
+    GMG_LAUNCH_CHECK(h);
+  }
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  cleanup();
+  s.pv = PatView{s.v.n_rows, s.v.n_cols,  s.v.n_slices, s.pat,     s.pat_ptr,
+                 s.pat_off,  s.pat_val,   np + 1,       n_ent,     SellView{n_rem, s.v.n_cols, rs, s.rem_slice_ptr, s.rem_val, s.rem_col},
+                 s.rem_rows};
+  s.patterned = true;
+  if (std::getenv("GMG_TRACE"))
+    std::fprintf(stderr, "[gmg trace]     row patterns: %d rows, %d distinct, %d in the table (%d entries), %d remainder rows\n", n,
+                 count, np, n_ent, n_rem);
+  return GMG_OK;
+}
+
 // AI = A + I on the device: same structure as A (shared), values = A's plus I's entries
 static int build_sum_on_device(gmg_context *h, const Sell &A, const HostCsr &I, Sell &out, bool &ok) {
   ok = false;
@@ -444,7 +622,11 @@ static int spmv(gmg_context *h, const Sell &A, const double *x, double *y, const
   if (A.v.n_slices == 0) return GMG_OK;
   const int grid = cdiv((int64_t)A.v.n_slices * 32, 256);
   if (DOT != DOT_NONE && grid > h->partials_cap) return fail(h, GMG_EINVAL, "partials buffer too small");
-  sell_spmv<EPI, DOT><<<grid, 256, 0, h->stream>>>(A.v, x, y, b, dinv, omega, h->partials, h->counter, out);
+  if (A.patterned && h->compress >= 2) {
+    const int pgrid = std::min(cdiv(A.v.n_slices, 16), 2 * h->sm_count);
+    pat_spmv<EPI, DOT><<<pgrid, 512, 0, h->stream>>>(A.pv, x, y, b, dinv, omega, h->partials, h->counter, out);
+  } else
+    sell_spmv<EPI, DOT><<<grid, 256, 0, h->stream>>>(A.v, x, y, b, dinv, omega, h->partials, h->counter, out);
   GMG_LAUNCH_CHECK(h);
   return GMG_OK;
 }
@@ -458,15 +640,19 @@ static int coarse_cg(gmg_context *h, const Sell &A, const double *b, double *x, 
   CgResult *res = h->cg_results + slot;
   SellView v = A.v;
   CsellView cv = A.cv;
-  const bool comp = A.compressed && h->compress;
-  void *args[] = {comp ? (void *)&cv : (void *)&v, (void *)&b, &x, &h->cg_g, &h->cg_d, &h->cg_h, &h->cg_partials, &max_it,
-                  &tol, &res};
+  PatView pv = A.pv;
+  const bool pat = A.patterned && h->compress >= 2;
+  const bool comp = !pat && A.compressed && h->compress >= 1;
+  void *args[] = {pat ? (void *)&pv : comp ? (void *)&cv : (void *)&v, (void *)&b, &x, &h->cg_g, &h->cg_d, &h->cg_h,
+                  &h->cg_partials, &max_it, &tol, &res};
   int ev = -1;
   if (h->ev_used < (int)h->ev_begin.size()) {
     ev = h->ev_used++;
     cudaEventRecord(h->ev_begin[ev], h->stream);
   }
-  if (comp)
+  if (pat)
+    GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_pat<512>, dim3(h->cg_grid_p), dim3(512), args, 0, h->stream));
+  else if (comp)
     GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent<512, CsellView>, dim3(h->cg_grid_c), dim3(512), args, 0,
                                             h->stream));
   else
@@ -837,7 +1023,11 @@ int gmg_create(int device, gmg_handle *out) {
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, cg_persistent<512, CsellView>, 512, 0) == cudaSuccess &&
          per_sm_c > 0;
     h->cg_grid_c = h->sm_count * std::max(per_sm_c, 1);
-    ok = ok && dalloc(&h->cg_partials, 3 * std::max(h->cg_grid, h->cg_grid_c)) == cudaSuccess;
+    int per_sm_p = 0;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, cg_persistent_pat<512>, 512, 0) == cudaSuccess &&
+         per_sm_p > 0;
+    h->cg_grid_p = h->sm_count * std::max(per_sm_p, 1);
+    ok = ok && dalloc(&h->cg_partials, 3 * std::max(std::max(h->cg_grid, h->cg_grid_c), h->cg_grid_p)) == cudaSuccess;
     h->ev_begin.resize(512);
     h->ev_end.resize(512);
     h->ev_result_slot.resize(512);
@@ -998,9 +1188,9 @@ int gmg_set_coarse(gmg_handle h, int max_it, double abs_tol) {
   return GMG_OK;
 }
 
-int gmg_set_compression(gmg_handle h, int on) {
-  if (!h) return GMG_EINVAL;
-  h->compress = on != 0;
+int gmg_set_compression(gmg_handle h, int mode) {
+  if (!h || mode < 0 || mode > 2) return GMG_EINVAL;
+  h->compress = mode;
   return GMG_OK;
 }
 
@@ -1042,6 +1232,8 @@ int gmg_setup(gmg_handle h) {
     TraceScope tr("  system -> sell");
     if ((rc = build_sell(h, h->rawS, h->drop_tol, h->S))) return rc;
     free_csr(h->rawS);
+    if (h->compress >= 2)
+      if ((rc = build_pat(h, h->S))) return rc;
     dfree(h->s_dinv);
     dfree(h->g);
     dfree(h->d);
@@ -1073,7 +1265,9 @@ int gmg_setup(gmg_handle h) {
       }
     }
     if (!L.A.valid) return fail(h, GMG_EINVAL, "level matrix missing on level " + std::to_string(l));
-    if (l == 0 && h->compress && !L.A.compressed)
+    if (l == 0 && h->compress >= 2 && !L.A.patterned)
+      if ((rc = build_pat(h, L.A))) return rc;
+    if (l == 0 && h->compress >= 1 && !L.A.patterned && !L.A.compressed)
       if ((rc = build_csell(h, L.A))) return rc;
     TraceScope trv("    vectors");
     for (double **p : {&L.defect, &L.sol, &L.t, &L.tmp}) {
@@ -1490,8 +1684,12 @@ int gmg_matrix_traffic(gmg_handle h, int which, int level, double out[3]) {
   out[0] = nnz;
   out[3] = 12.0 * nnz + 4.0 * (n + 1.0) + 16.0 * n;  // CSR-equivalent algorithmic bytes of one SpMV
   out[4] = out[3] + 72.0 * n;                         // + x,d,g,h reads and x,g,d writes of one CG iteration
-  out[5] = (A->compressed && h->compress) ? 1.0 : 0.0;
-  if (out[5] != 0.0) {  // bytes of the format actually streamed: 4-byte entries (padded to 4 per row) + slice pointers
+  out[5] = (A->patterned && h->compress >= 2) ? 2.0 : (A->compressed && h->compress >= 1) ? 1.0 : 0.0;
+  if (out[5] == 2.0) {  // 4 bytes per row + the pattern table
+    out[1] = 4.0 * 32.0 * A->v.n_slices + 12.0 * A->pv.n_ent + 4.0 * (A->pv.n_pat + 1.0) + 12.0 * (double)A->rem_padded +
+             4.0 * A->pv.rem.n_rows + 8.0 * (A->pv.rem.n_slices + 1.0) + 16.0 * n;
+    out[2] = out[1] + 72.0 * n;
+  } else if (out[5] == 1.0) {  // bytes of the format actually streamed: 4-byte entries (padded to 4 per row) + slice pointers
     out[1] = 4.0 * (double)A->cpadded + 8.0 * (A->v.n_slices + 1.0) + 8.0 * A->cv.dict_n + 16.0 * n;
     out[2] = out[1] + 72.0 * n;
   } else {

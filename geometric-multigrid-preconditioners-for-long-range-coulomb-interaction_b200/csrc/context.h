@@ -48,6 +48,17 @@ struct Sell {
   uint32_t *ent = nullptr;
   double *dict = nullptr;
   int64_t cpadded = 0;
+  // optional row-pattern dictionary copy (PatView, pattern.cuh): 4 bytes per row
+  bool patterned = false;
+  PatView pv{};
+  uint32_t *pat = nullptr;
+  int *pat_ptr = nullptr, *pat_off = nullptr;
+  double *pat_val = nullptr;
+  int *rem_rows = nullptr;
+  int64_t *rem_slice_ptr = nullptr;
+  double *rem_val = nullptr;
+  int *rem_col = nullptr;
+  int64_t rem_padded = 0;
 };
 
 struct ColorSet {
@@ -154,8 +165,9 @@ struct gmg_context {
   int coarse_max_it = 1000;
   double coarse_tol = 1e-10;
   double drop_tol = -1.0;
-  bool compress = true;  // build the compressed copy of the coarse-level matrix when it qualifies
+  int compress = 2;      // 0: plain SELL; 1: CSELL entries; 2: row-pattern dictionary (falls back to 1, then 0)
   int cg_grid_c = 0;     // cooperative grid of the compressed-format CG kernel
+  int cg_grid_p = 0;     // cooperative grid of the row-pattern CG kernel
   bool is_setup = false;
 
   // reductions

@@ -635,3 +635,5 @@ __global__ void __launch_bounds__(BLOCK, 2) cg_persistent(MAT A, const double *_
 }
 
 }  // namespace gmg
+
+#include "pattern.cuh"

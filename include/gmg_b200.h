@@ -85,10 +85,14 @@ int gmg_set_graphs(gmg_handle h, int on);
 int gmg_set_coarse(gmg_handle h, int max_it, double abs_tol);
 /* Drop stored entries with |a_ij| <= drop_tol when building the device format (default: keep all). */
 int gmg_set_drop_tolerance(gmg_handle h, double drop_tol);
-/* Lossless compression of the coarse-level matrix on the device (16-bit value dictionary codes + 16-bit column
- * offsets, 4 bytes per entry instead of 12; results are bit-identical).  Default on; falls back to the plain
- * sliced-ELL format when a matrix has more than 60000 distinct values or a half bandwidth >= 32768. */
-int gmg_set_compression(gmg_handle h, int on);
+/* Lossless device formats of the coarse-level matrix (results are bit-identical in all three):
+ *   mode 0  plain sliced ELL, 12 bytes per entry;
+ *   mode 1  CSELL: 16-bit value-dictionary code + 16-bit column offset, 4 bytes per entry (falls back to 0 when a
+ *           matrix has more than 60000 distinct values or a half bandwidth >= 32768);
+ *   mode 2  (default) row-pattern dictionary: one 32-bit pattern id per ROW + the table of distinct
+ *           (column offset, value) rows -- an FE matrix on a uniform level has a few dozen; falls back to mode 1
+ *           when the rows are not repetitive enough (more than n/8 or 20000 distinct rows). */
+int gmg_set_compression(gmg_handle h, int mode);
 /* Build device formats (sliced ELL), transposes, colourings, eigenvalue bounds. */
 int gmg_setup(gmg_handle h);
 
@@ -134,7 +138,7 @@ int gmg_cg_solve_dev(gmg_handle h, int which, int level, const double *b_dev, do
                      int max_it, double abs_tol, int *iters, double *res_final);
 /* bytes one SpMV / one coarse-CG iteration with this matrix moves algorithmically:
  * out[0] = stored nnz, out[1] = SpMV bytes and out[2] = CG-iteration bytes of the format actually stored,
- * out[3], out[4] = the same for plain CSR (12 B per entry), out[5] = 1 if the compressed format is in use */
+ * out[3], out[4] = the same for plain CSR (12 B per entry), out[5] = format in use (0, 1, 2 as in gmg_set_compression) */
 int gmg_matrix_traffic(gmg_handle h, int which, int level, double out[6]);
 /* accumulated device time (ms, CUDA events on the handle's stream) and launch count of the
  * persistent coarse-CG kernel since the last reset; inner iterations summed in *iters. */

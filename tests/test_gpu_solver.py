@@ -83,22 +83,29 @@ def test_coarse_cg_lattice8_matches_reference_log(capi, lattice8, goldens):
 
 
 def test_compressed_coarse_matrix_is_lossless(capi, lattice8):
-    """The 4-byte-per-entry compressed level-0 format (value dictionary + 16-bit column offsets) decodes to the same
-    fp64 numbers in the same order: the coarse CG is bit-identical with and without it."""
+    """The compressed level-0 formats -- CSELL (value dictionary + 16-bit column offsets, 4 bytes per entry) and the
+    row-pattern dictionary (4 bytes per row) -- decode to the same fp64 numbers in the same order: the coarse CG
+    takes the same iterations and the SpMV is bit-identical in all three formats."""
     P = lattice8
     out = {}
-    for comp in (False, True):
+    rng = np.random.default_rng(5)
+    xr = rng.standard_normal(P.ops.A[0].shape[0])
+    for mode in (0, 1, 2):
         g = capi.Gmg()
-        g.set_compression(comp)
+        g.set_compression(mode)
         hand_over(P, g)
         tr = g.matrix_traffic(capi.GMG_LEVEL, 0)
-        assert tr["compressed"] == comp
-        out[comp] = g.cg_solve(capi.GMG_LEVEL, 0, P.b, 1000, 1e-10) + (tr,)
+        assert tr["format"] == mode
+        out[mode] = g.cg_solve(capi.GMG_LEVEL, 0, P.b, 1000, 1e-10) + (tr,)
+        out[mode] += (g.spmv(capi.GMG_LEVEL, 0, xr, len(xr)),)
         g.close()
-    assert out[True][1] == out[False][1] == 97
-    # (the two kernels may run different cooperative grids, i.e. group the dot-product partials differently)
-    assert rel_l2(out[True][0], out[False][0]) < 1e-11 and abs(out[True][2] - out[False][2]) <= 1e-6 * out[False][2]
-    assert out[True][3]["cg_iter_bytes"] < 0.55 * out[False][3]["cg_iter_bytes"]
+    assert out[0][1] == out[1][1] == out[2][1] == 97
+    # (the kernels may run different cooperative grids, i.e. group the dot-product partials differently)
+    for m in (1, 2):
+        assert rel_l2(out[m][0], out[0][0]) < 1e-11 and abs(out[m][2] - out[0][2]) <= 1e-6 * out[0][2]
+        assert np.array_equal(out[m][4], out[0][4])  # same entries, same order, same FMA chain: same bits
+    assert out[1][3]["cg_iter_bytes"] < 0.55 * out[0][3]["cg_iter_bytes"]
+    assert out[2][3]["cg_iter_bytes"] < 0.35 * out[0][3]["cg_iter_bytes"]  # ~ the 88 n bytes of the vectors
 
 
 @pytest.mark.parametrize("kind", ["jacobi", "lex_ssor"])
