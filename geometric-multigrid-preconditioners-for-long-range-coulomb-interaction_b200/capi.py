@@ -62,6 +62,8 @@ SIGNATURES = {
     "gmg_spmv_dev": (_i, [_h, _i, _i, C.c_void_p, C.c_void_p]),
     "gmg_cg_solve_dev": (_i, [_h, _i, _i, C.c_void_p, C.c_void_p, _i, _d, C.POINTER(_i), _pd]),
     "gmg_matrix_traffic": (_i, [_h, _i, _i, _pd]),
+    "gmg_debug_cg_phases": (_i, [_h, _i, _pd]),
+    "gmg_debug_cg_blocks": (_i, [_h, _pd]),
     "gmg_coarse_profile": (_i, [_h, _i, _pd, _pi64, _pi64]),
     "gmg_launch_count": (_i64, [_h]),
     "gmg_dist_init": (_i, [_h, _i, _i, _i64, C.c_void_p]),
@@ -293,6 +295,16 @@ class Gmg:
         self._ck(self.lib.gmg_matrix_traffic(self.h, which, level, _pd_of(out)))
         return dict(nnz=out[0], spmv_bytes=out[1], cg_iter_bytes=out[2], csr_spmv_bytes=out[3], csr_cg_iter_bytes=out[4],
                     compressed=bool(out[5]), format=int(out[5]))
+
+    def debug_cg_phases(self, block_plus_1=1):
+        out = np.zeros(16)
+        self._ck(self.lib.gmg_debug_cg_phases(self.h, int(block_plus_1), _pd_of(out)))
+        return out
+
+    def debug_cg_blocks(self):
+        out = np.zeros(768)
+        self._ck(self.lib.gmg_debug_cg_blocks(self.h, _pd_of(out)))
+        return out.reshape(3, 256)
 
     def coarse_profile(self, reset=True):
         ms, n, it = _d(0), _i64(0), _i64(0)

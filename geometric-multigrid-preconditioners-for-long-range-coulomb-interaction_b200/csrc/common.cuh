@@ -125,6 +125,9 @@ struct CsellView {
 };
 
 // Row-pattern dictionary format (pattern.cuh): one pattern id per row + the table of distinct rows.
+constexpr uint32_t PAT_ID_MASK = 0x3fffffffu;   // pattern id bits of PatView::pat[r]
+constexpr uint32_t PAT_GENERAL = 0x40000000u;   // window kernel: row must take the general path (a dominant column is out of range)
+constexpr uint32_t PAT_ZEROED = 0x80000000u;    // window kernel: entry r of the zeroed operand copy is 0 (see pattern_win.cuh)
 struct PatView {
   int n_rows, n_cols, n_slices;
   const uint32_t *pat;   // pattern id per row (padded to a multiple of 32 rows with the empty pattern)
@@ -134,6 +137,29 @@ struct PatView {
   int n_pat, n_ent;       // n_pat includes the empty pattern (id n_pat - 1): row handled by the remainder / padding
   SellView rem;           // rows whose pattern is not in the table, as a SELL matrix (zeros dropped) ...
   const int *rem_rows;    // ... and their row indices, ascending
+  const int *rem_ptr;     // the same rows as CSR (rem.n_rows + 1 offsets; window kernel: 4 lanes per row)
+  const int *rem_ccol;
+  const double *rem_cval;
+};
+
+// Dominant pattern + window plan of the TMA-staged persistent CG (pattern_win.cuh)
+constexpr int WIN_BLOCK = 1024;      // threads of the window kernel: 31 consumer warps + 1 producer warp
+constexpr int WIN_SPW = 2;           // slices per consumer warp and tile
+constexpr int WIN_TILE_SLICES = (WIN_BLOCK / 32 - 1) * WIN_SPW;
+constexpr int WIN_TILE_ROWS = WIN_TILE_SLICES * 32;
+constexpr int DOM_MAX = 32;
+constexpr int WIN_MAX_SEG = 4;
+
+struct DomPat {
+  int len;                    // entries of the dominant pattern (0: none)
+  int nseg;                   // window segments per tile
+  int win_elems;              // doubles per window stage (even)
+  int diag_wbyte;             // window byte offset of column == row
+  int wbyte[DOM_MAX];         // window byte offset of entry k for the first row of a tile (+ 8 * local row); 0 past len
+  double val[DOM_MAX];
+  int seg_lo[WIN_MAX_SEG];    // first column of the segment relative to the tile's first row (even)
+  int seg_len[WIN_MAX_SEG];   // doubles (even)
+  int seg_base[WIN_MAX_SEG];  // position in the window (even)
 };
 
 struct PcgScalars {

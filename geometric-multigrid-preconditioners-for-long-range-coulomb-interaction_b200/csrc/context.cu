@@ -7,6 +7,7 @@
 
 #include "context.h"
 #include <cub/device/device_select.cuh>
+#include <cub/device/device_scan.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include "kernels.cuh"
 // (dist.cuh uses RowDot / CSELL_SMEM_DICT from kernels.cuh)
@@ -44,6 +45,10 @@ static void free_sell(Sell &s) {
   dfree(s.rem_slice_ptr);
   dfree(s.rem_val);
   dfree(s.rem_col);
+  dfree(s.rem_ptr);
+  dfree(s.rem_ccol);
+  dfree(s.rem_cval);
+  dfree(s.dom_mask);
   s = Sell{};
 }
 static void free_csr(DevCsr &c) {
@@ -259,6 +264,73 @@ static int build_csell(gmg_context *h, Sell &s) {
   return GMG_OK;
 }
 
+// Dominant pattern + TMA window plan (pattern_win.cuh) from the host copy of the pattern table.  mask[p] != 0: the
+// entries of pattern p are a sub-sequence (same offsets, same value bits) of the dominant pattern's.
+static void plan_windows(const std::vector<int> &ptr, const std::vector<int> &off, const std::vector<double> &val, int np,
+                         DomPat &D, std::vector<uint32_t> &mask) {
+  D = DomPat{};
+  mask.assign(np + 1, 0u);
+  if (np == 0) return;
+  const int len = ptr[1] - ptr[0];
+  if (len <= 0 || len > DOM_MAX) return;
+  std::vector<int> o(off.begin(), off.begin() + len);
+  std::vector<int> sorted = o;
+  sorted.push_back(0);  // the row's own entry (d . A d is read from the window)
+  std::sort(sorted.begin(), sorted.end());
+  // ranges [o, o + TILE_ROWS) of neighbouring offsets that overlap (or nearly do) share a segment
+  struct Seg {
+    int lo, hi;
+  };
+  std::vector<Seg> segs;
+  for (int v : sorted) {
+    if (!segs.empty() && v <= segs.back().hi + WIN_TILE_ROWS + 64) segs.back().hi = std::max(segs.back().hi, v);
+    else segs.push_back(Seg{v, v});
+  }
+  if ((int)segs.size() > WIN_MAX_SEG) return;
+  int base = 0;
+  for (size_t i = 0; i < segs.size(); ++i) {
+    const int lo = segs[i].lo - (segs[i].lo & 1);  // even (also for negative offsets: two's complement)
+    const int n = (segs[i].hi - lo + WIN_TILE_ROWS + 1) & ~1;
+    D.seg_lo[i] = lo;
+    D.seg_len[i] = n;
+    D.seg_base[i] = base;
+    base += n;
+  }
+  if ((int64_t)base * 16 > 112 * 1024) return;  // two stages must leave room for the table (and h) in 227 KB
+  D.nseg = (int)segs.size();
+  D.win_elems = base;
+  auto widx = [&](int v) {
+    for (int i = 0; i < D.nseg; ++i)
+      if (v >= D.seg_lo[i] && v - D.seg_lo[i] + WIN_TILE_ROWS <= D.seg_len[i]) return D.seg_base[i] + (v - D.seg_lo[i]);
+    return -1;
+  };
+  for (int k = 0; k < len; ++k) {
+    const int wi = widx(o[k]);
+    if (wi < 0) return;  // (cannot happen)
+    D.wbyte[k] = 8 * wi;
+    D.val[k] = val[k];
+  }
+  int kdiag = -1;
+  for (int k = 0; k < len; ++k)
+    if (o[k] == 0) kdiag = k;
+  if (kdiag < 0 || widx(0) < 0) return;  // (the row's own entry is read from the window)
+  D.diag_wbyte = 8 * widx(0);
+  D.len = len;
+  for (int p = 0; p < np; ++p) {
+    const int n = ptr[p + 1] - ptr[p];
+    if (n == 0) continue;
+    uint32_t m = 0;
+    int j = 0;
+    bool ok = true;
+    for (int e = ptr[p]; e < ptr[p + 1] && ok; ++e) {
+      while (j < len && !(o[j] == off[e] && std::memcmp(&val[j], &val[e], sizeof(double)) == 0)) ++j;
+      if (j == len) ok = false;
+      else m |= 1u << j++;
+    }
+    mask[p] = (ok && ((m >> kdiag) & 1u)) ? m : 0u;
+  }
+}
+
 // Row-pattern dictionary copy (pattern.cuh) of a SELL matrix: the frequent rows through the shared-memory pattern
 // table, the rest as a (small) remainder SELL matrix.  Leaves s.patterned == false when fewer than 3/4 of the rows
 // are covered by the table or (never observed) a row fails the entry-by-entry verification.
@@ -299,6 +371,10 @@ static int build_pat(gmg_context *h, Sell &s) {
     dfree(s.rem_slice_ptr);
     dfree(s.rem_val);
     dfree(s.rem_col);
+    dfree(s.rem_ptr);
+    dfree(s.rem_ccol);
+    dfree(s.rem_cval);
+    dfree(s.dom_mask);
   };
   GMG_CUDA(h, dalloc(&hash, n));
   GMG_CUDA(h, dalloc(&keys, (int64_t)mask + 1));
@@ -415,12 +491,89 @@ static int build_pat(gmg_context *h, Sell &s) {
     sell_sub_fill<<<cdiv((int64_t)rs * 32, 256), 256, 0, h->stream>>>(s.v, n_rem, s.rem_rows, s.rem_slice_ptr, s.rem_val, s.rem_col);
     GMG_LAUNCH_CHECK(h);
   }
+  // ... and as CSR (4 lanes per row in the window kernel)
+  {
+    int *rcnt = nullptr;
+    GMG_CUDA(h, dalloc(&rcnt, n_rem + 1));
+    GMG_CUDA(h, dalloc(&s.rem_ptr, n_rem + 1));
+    GMG_CUDA(h, cudaMemsetAsync(rcnt, 0, sizeof(int) * (n_rem + 1), h->stream));
+    if (n_rem > 0) {
+      sell_sub_count<<<cdiv(n_rem, 256), 256, 0, h->stream>>>(s.v, n_rem, s.rem_rows, rcnt);
+      GMG_LAUNCH_CHECK(h);
+    }
+    size_t scan_bytes = 0;
+    void *scan_tmp = nullptr;
+    GMG_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, rcnt, s.rem_ptr, n_rem + 1, h->stream));
+    GMG_CUDA(h, cudaMallocAsync(&scan_tmp, std::max<size_t>(scan_bytes, 1), h->stream));
+    GMG_CUDA(h, cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, rcnt, s.rem_ptr, n_rem + 1, h->stream));
+    int rem_nnz = 0;
+    GMG_CUDA(h, copy_sync(h, &rem_nnz, s.rem_ptr + n_rem, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFreeAsync(scan_tmp, h->stream);
+    dfree(rcnt);
+    GMG_CUDA(h, dalloc(&s.rem_ccol, rem_nnz));
+    GMG_CUDA(h, dalloc(&s.rem_cval, rem_nnz));
+    if (n_rem > 0) {
+      sell_sub_fill_csr<<<cdiv(n_rem, 256), 256, 0, h->stream>>>(s.v, n_rem, s.rem_rows, s.rem_ptr, s.rem_ccol, s.rem_cval);
+      GMG_LAUNCH_CHECK(h);
+    }
+  }
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   cleanup();
-  s.pv = PatView{s.v.n_rows, s.v.n_cols,  s.v.n_slices, s.pat,     s.pat_ptr,
-                 s.pat_off,  s.pat_val,   np + 1,       n_ent,     SellView{n_rem, s.v.n_cols, rs, s.rem_slice_ptr, s.rem_val, s.rem_col},
-                 s.rem_rows};
+  s.pv = PatView{s.v.n_rows, s.v.n_cols, s.v.n_slices, s.pat,      s.pat_ptr,  s.pat_off, s.pat_val, np + 1, n_ent,
+                 SellView{n_rem, s.v.n_cols, rs, s.rem_slice_ptr, s.rem_val, s.rem_col},
+                 s.rem_rows, s.rem_ptr,  s.rem_ccol,   s.rem_cval};
   s.patterned = true;
+  {
+    std::vector<int> hoff(n_ent);
+    std::vector<double> hval(n_ent);
+    if (n_ent > 0) {
+      GMG_CUDA(h, copy(h, hoff.data(), s.pat_off, sizeof(int) * n_ent, cudaMemcpyDeviceToHost));
+      GMG_CUDA(h, copy_sync(h, hval.data(), s.pat_val, sizeof(double) * n_ent, cudaMemcpyDeviceToHost));
+    }
+    std::vector<uint32_t> hmask;
+    plan_windows(hptr, hoff, hval, np, s.dom, hmask);
+    GMG_CUDA(h, dalloc(&s.dom_mask, np + 1));
+    GMG_CUDA(h, copy_sync(h, s.dom_mask, hmask.data(), sizeof(uint32_t) * (np + 1), cudaMemcpyHostToDevice));
+    if (s.dom.len > 0 && s.v.n_rows == s.v.n_cols) {
+      // the set Z of columns the sub-sequence rows need zeroed in the operand copy (pattern_win.cuh)
+      int *colflag = nullptr, *conflict = nullptr;
+      GMG_CUDA(h, dalloc(&colflag, n));
+      GMG_CUDA(h, dalloc(&conflict, 1));
+      GMG_CUDA(h, cudaMemsetAsync(colflag, 0, sizeof(int) * n, h->stream));
+      GMG_CUDA(h, cudaMemsetAsync(conflict, 0, sizeof(int), h->stream));
+      pat_mark_columns<<<cdiv(n, 256), 256, 0, h->stream>>>(s.pv, s.pat, s.dom_mask, s.dom.len, colflag);
+      GMG_LAUNCH_CHECK(h);
+      if (n_rem > 0) {
+        pat_mark_remainder<<<cdiv(n_rem, 256), 256, 0, h->stream>>>(s.pv.rem, colflag);
+        GMG_LAUNCH_CHECK(h);
+      }
+      pat_apply_zero_set<<<cdiv(n, 256), 256, 0, h->stream>>>(n, colflag, s.pat, conflict, 0);
+      GMG_LAUNCH_CHECK(h);
+      int hc = 0;
+      GMG_CUDA(h, copy_sync(h, &hc, conflict, sizeof(int), cudaMemcpyDeviceToHost));
+      if (hc == 0) {
+        pat_apply_zero_set<<<cdiv(n, 256), 256, 0, h->stream>>>(n, colflag, s.pat, conflict, 1);
+        GMG_LAUNCH_CHECK(h);
+      } else {  // some row needs a column another row wants zeroed: only the exact dominant rows stay on the window path
+        const uint32_t full = s.dom.len >= 32 ? 0xffffffffu : ((1u << s.dom.len) - 1u);
+        for (auto &m : hmask)
+          if (m != full) m = 0u;
+        GMG_CUDA(h, copy_sync(h, s.dom_mask, hmask.data(), sizeof(uint32_t) * (np + 1), cudaMemcpyHostToDevice));
+      }
+      GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+      dfree(colflag);
+      dfree(conflict);
+      if (std::getenv("GMG_TRACE")) std::fprintf(stderr, "[gmg trace]     zeroed-operand set: %s\n", hc ? "conflict (exact rows only)" : "ok");
+    } else {
+      s.dom.len = 0;
+    }
+    if (std::getenv("GMG_TRACE")) {
+      int64_t n_compat = 0;
+      for (int p = 0; p < np; ++p) n_compat += hmask[p] != 0u;
+      std::fprintf(stderr, "[gmg trace]     dominant pattern: %d entries, %d window segments, %d doubles per stage, %lld compatible patterns\n",
+                   s.dom.len, s.dom.nseg, s.dom.win_elems, (long long)n_compat);
+    }
+  }
   if (std::getenv("GMG_TRACE"))
     std::fprintf(stderr, "[gmg trace]     row patterns: %d rows, %d distinct, %d in the table (%d entries), %d remainder rows\n", n,
                  count, np, n_ent, n_rem);
@@ -650,7 +803,29 @@ static int coarse_cg(gmg_context *h, const Sell &A, const double *b, double *x, 
     ev = h->ev_used++;
     cudaEventRecord(h->ev_begin[ev], h->stream);
   }
-  if (pat)
+  bool win = pat && A.dom.len > 0 && h->cg_win && A.pv.n_pat <= (int)RC_ID;
+  if (win) {
+    const int grid = h->sm_count;
+    const int smem_cap = 232448 - 1024;
+    int rows_per_block = (A.v.n_slices / grid + 1) * 32;
+    const WinLayout lay = win_layout(A.dom.win_elems, rows_per_block);
+    if (lay.total > smem_cap) win = false;  // (too many rows per block for the 16-bit row codes in shared memory)
+    if (win) {
+      if (lay.total > h->cg_win_smem) {
+        GMG_CUDA(h, cudaFuncSetAttribute((const void *)cg_persistent_win<WIN_SPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         lay.total));
+        h->cg_win_smem = lay.total;
+      }
+      DomPat dom = A.dom;
+      const uint32_t *mask = A.dom_mask;
+      void *wargs[] = {&pv, &dom, (void *)&mask, (void *)&b, &x, &h->cg_g, &h->cg_d, &h->cg_dz, &h->cg_h, &h->cg_partials,
+                       &max_it, &tol, &res, &rows_per_block, &h->cg_prof};
+      GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_win<WIN_SPW>, dim3(grid), dim3(WIN_BLOCK), wargs,
+                                              (size_t)lay.total, h->stream));
+    }
+  }
+  if (win) {
+  } else if (pat)
     GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_pat<512>, dim3(h->cg_grid_p), dim3(512), args, 0, h->stream));
   else if (comp)
     GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent<512, CsellView>, dim3(h->cg_grid_c), dim3(512), args, 0,
@@ -1008,6 +1183,7 @@ int gmg_create(int device, gmg_handle *out) {
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
   }
+  h->cg_win = !(std::getenv("GMG_CG_WIN") && std::atoi(std::getenv("GMG_CG_WIN")) == 0);
   h->partials_cap = 1 << 16;
   bool ok = dalloc(&h->partials, 3 * h->partials_cap) == cudaSuccess && dalloc(&h->counter, 4) == cudaSuccess &&
             dalloc(&h->scalars, 1) == cudaSuccess && dalloc(&h->cg_results, h->cg_ring) == cudaSuccess;
@@ -1058,6 +1234,7 @@ int gmg_destroy(gmg_handle h) {
   dfree(h->hh);
   dfree(h->cg_g);
   dfree(h->cg_d);
+  dfree(h->cg_dz);
   dfree(h->cg_h);
   dfree(h->stage_a);
   dfree(h->stage_b);
@@ -1415,7 +1592,11 @@ int gmg_setup(gmg_handle h) {
     dfree(h->cg_d);
     dfree(h->cg_h);
     GMG_CUDA(h, dalloc(&h->cg_g, cg_n));
-    GMG_CUDA(h, dalloc(&h->cg_d, cg_n));
+    GMG_CUDA(h, dalloc(&h->cg_d, cg_n + 2));  // (+2: the window copies of pattern_win.cuh read whole 16-byte units)
+    GMG_CUDA(h, cudaMemsetAsync(h->cg_d, 0, sizeof(double) * (cg_n + 2), h->stream));
+    dfree(h->cg_dz);
+    GMG_CUDA(h, dalloc(&h->cg_dz, cg_n));
+    GMG_CUDA(h, cudaMemsetAsync(h->cg_dz, 0, sizeof(double) * cg_n, h->stream));
     GMG_CUDA(h, dalloc(&h->cg_h, cg_n));
     h->cg_n = cg_n;
   }
@@ -1696,6 +1877,32 @@ int gmg_matrix_traffic(gmg_handle h, int which, int level, double out[3]) {
     out[1] = out[3];
     out[2] = out[4];
   }
+  return GMG_OK;
+}
+
+int gmg_debug_cg_phases(gmg_handle h, int block_plus_1, double out_ns[16]) {
+  if (!h) return GMG_EINVAL;
+  gmg::enter(h);
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  unsigned long long v[16] = {0};
+  GMG_CUDA(h, cudaMemcpyFromSymbol(v, g_cg_phase_ns, sizeof(v)));
+  if (out_ns)
+    for (int i = 0; i < 16; ++i) out_ns[i] = (double)v[i];
+  unsigned long long z[16] = {0};
+  GMG_CUDA(h, cudaMemcpyToSymbol(g_cg_phase_ns, z, sizeof(z)));
+  h->cg_prof = block_plus_1 > 0 ? block_plus_1 : 0;
+  return GMG_OK;
+}
+
+int gmg_debug_cg_blocks(gmg_handle h, double out_ns[768]) {
+  if (!h || !out_ns) return GMG_EINVAL;
+  gmg::enter(h);
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  static unsigned long long v[768];
+  GMG_CUDA(h, cudaMemcpyFromSymbol(v, g_cg_block_ns, sizeof(v)));
+  for (int i = 0; i < 768; ++i) out_ns[i] = (double)v[i];
+  std::memset(v, 0, sizeof(v));
+  GMG_CUDA(h, cudaMemcpyToSymbol(g_cg_block_ns, v, sizeof(v)));
   return GMG_OK;
 }
 

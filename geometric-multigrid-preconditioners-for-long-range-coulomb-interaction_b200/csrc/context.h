@@ -59,6 +59,11 @@ struct Sell {
   double *rem_val = nullptr;
   int *rem_col = nullptr;
   int64_t rem_padded = 0;
+  int *rem_ptr = nullptr, *rem_ccol = nullptr;  // the remainder rows as CSR
+  double *rem_cval = nullptr;
+  // dominant pattern + TMA window plan for the persistent CG (pattern_win.cuh); dom.len == 0: not available
+  DomPat dom{};
+  uint32_t *dom_mask = nullptr;
 };
 
 struct ColorSet {
@@ -154,7 +159,7 @@ struct gmg_context {
   int n_sys = 0;
   double *s_dinv = nullptr;
   double *g = nullptr, *d = nullptr, *hh = nullptr;      // outer PCG work vectors
-  double *cg_g = nullptr, *cg_d = nullptr, *cg_h = nullptr;  // coarse CG work vectors
+  double *cg_g = nullptr, *cg_d = nullptr, *cg_h = nullptr, *cg_dz = nullptr;  // coarse CG work vectors
   int cg_n = 0;
   double *stage_a = nullptr, *stage_b = nullptr;  // device staging for host-pointer entry points
   int64_t stage_n = 0;
@@ -168,6 +173,9 @@ struct gmg_context {
   int compress = 2;      // 0: plain SELL; 1: CSELL entries; 2: row-pattern dictionary (falls back to 1, then 0)
   int cg_grid_c = 0;     // cooperative grid of the compressed-format CG kernel
   int cg_grid_p = 0;     // cooperative grid of the row-pattern CG kernel
+  bool cg_win = true;    // TMA-window variant of the row-pattern CG (pattern_win.cuh); GMG_CG_WIN=0 disables
+  int cg_prof = 0;       // gmg_debug_cg_phases: per-phase timing inside the window kernel
+  int cg_win_smem = 0;   // dynamic shared memory the window kernel is currently configured for
   bool is_setup = false;
 
   // reductions

@@ -637,3 +637,4 @@ __global__ void __launch_bounds__(BLOCK, 2) cg_persistent(MAT A, const double *_
 }  // namespace gmg
 
 #include "pattern.cuh"
+#include "pattern_win.cuh"

@@ -182,6 +182,27 @@ __global__ void sell_sub_fill(SellView A, int n_sub, const int *__restrict__ row
   }
 }
 
+// the same remainder rows as CSR (zeros dropped): nonzeros per row, then (after an exclusive scan) the entries
+__global__ void sell_sub_count(SellView A, int n_sub, const int *__restrict__ rows, int *__restrict__ cnt) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_sub) return;
+  int w = 0;
+  sell_row_foreach_nonzero(A, rows[k], [&](int, double) { ++w; });
+  cnt[k] = w;
+}
+__global__ void sell_sub_fill_csr(SellView A, int n_sub, const int *__restrict__ rows, const int *__restrict__ ptr,
+                                  int *__restrict__ col, double *__restrict__ val) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_sub) return;
+  const int r = rows[k];
+  int e = ptr[k];
+  sell_row_foreach_nonzero(A, r, [&](int o, double v) {
+    col[e] = r + o;
+    val[e] = v;
+    ++e;
+  });
+}
+
 // The pattern table in shared memory.
 struct PatTable {
   const int *ptr;
@@ -276,7 +297,7 @@ __global__ void __launch_bounds__(512) pat_spmv(PatView A, const double *__restr
     const int s_end = (int)(((int64_t)A.n_slices * (blockIdx.x + 1)) / nb);
     for (int s = s_begin + warp; s < s_end; s += WPB) {
       const int r = s * 32 + lane;
-      const uint32_t pid = __ldg(A.pat + r);
+      const uint32_t pid = __ldg(A.pat + r) & PAT_ID_MASK;
       const double ax = pat_row_dot<true>(T, pid, x + r);
       if (pid != empty) {
         const double yv = pat_epilogue<EPI>(r, ax, x, y, b, dinv, omega);
@@ -356,9 +377,9 @@ __global__ void __launch_bounds__(BLOCK, 2) cg_persistent_pat(PatView A, const d
       acc = 0.0;
       {
         int s = s_begin + warp;
-        uint32_t pid = (s < s_end) ? __ldg(A.pat + s * 32 + lane) : empty;
+        uint32_t pid = (s < s_end) ? (__ldg(A.pat + s * 32 + lane) & PAT_ID_MASK) : empty;
         for (; s < s_end; s += WPB) {
-          const uint32_t pid_next = (s + WPB < s_end) ? __ldg(A.pat + (s + WPB) * 32 + lane) : empty;
+          const uint32_t pid_next = (s + WPB < s_end) ? (__ldg(A.pat + (s + WPB) * 32 + lane) & PAT_ID_MASK) : empty;
           const int r = s * 32 + lane;
           const double ad = pat_row_dot<false>(T, pid, d + r);
           if (pid != empty) {

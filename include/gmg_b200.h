@@ -140,6 +140,15 @@ int gmg_cg_solve_dev(gmg_handle h, int which, int level, const double *b_dev, do
  * out[0] = stored nnz, out[1] = SpMV bytes and out[2] = CG-iteration bytes of the format actually stored,
  * out[3], out[4] = the same for plain CSR (12 B per entry), out[5] = format in use (0, 1, 2 as in gmg_set_compression) */
 int gmg_matrix_traffic(gmg_handle h, int which, int level, double out[6]);
+/* Developer probe: per-phase time of the windowed coarse-CG kernel as seen by thread 0 of block (block_plus_1 - 1)
+ * (globaltimer ns, summed over iterations): out[0] SpMV tail + block reduction, [1] barrier + grid reduction,
+ * [2] x/g update, [3] barrier + reduction, [4] new direction, [5] barrier, [6] iterations; inside the SpMV, per tile:
+ * [8] issue of the next window + pattern ids, [9] wait for the window, [10] dominant loop, [11] other rows + stores,
+ * [12] block barrier, [13] remainder rows.  Returns the counters since the last call, resets them and selects the
+ * block (0 switches timing off). */
+int gmg_debug_cg_phases(gmg_handle h, int block_plus_1, double out_ns[16]);
+/* ... and per block (256 slots each): time in the SpMV, update and direction phases while timing was on. */
+int gmg_debug_cg_blocks(gmg_handle h, double out_ns[768]);
 /* accumulated device time (ms, CUDA events on the handle's stream) and launch count of the
  * persistent coarse-CG kernel since the last reset; inner iterations summed in *iters. */
 int gmg_coarse_profile(gmg_handle h, int reset, double *ms, int64_t *launches, int64_t *iters);

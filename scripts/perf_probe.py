@@ -27,7 +27,8 @@ N = A.shape[0]
 rng = np.random.default_rng(0)
 b = rng.standard_normal(N); b[d.level_boundary[0]] = 0
 xs = {}
-for comp in (0, 1, 2):
+MODES = [int(c) for c in os.environ.get('PROBE_MODES', '012')]
+for comp in MODES:
     g.set_compression(comp)
     t = time.time(); g.setup(); print("setup %.2fs" % (time.time() - t))
     tr = g.matrix_traffic(capi.GMG_LEVEL, 0)
@@ -42,6 +43,7 @@ for comp in (0, 1, 2):
     print("spmv %.3f ms  %.0f GB/s CSR-equivalent" % (dt * 1e3, tr["csr_spmv_bytes"] / dt / 1e9))
     g.vec_upload(x, b)
     g.coarse_profile(True)
+    g.debug_cg_phases(1)
     for rep in range(2):
         try:
             g.cg_solve_dev(capi.GMG_LEVEL, 0, x, y, 200, 1e-300)
@@ -51,6 +53,10 @@ for comp in (0, 1, 2):
     per = p["ms"] / p["iterations"]
     print("cg: %d its in %.2f ms -> %.4f ms/it, %.0f GB/s of the stored format, %.0f GB/s CSR-equivalent" % (
         p["iterations"], p["ms"], per, tr["cg_iter_bytes"] / per / 1e6, tr["csr_cg_iter_bytes"] / per / 1e6))
+    ph = g.debug_cg_phases(0)
+    if ph[6] > 0:
+        print("phases (us/it, block 0): spmv %.1f  bar1 %.1f  update %.1f  bar2 %.1f  direction %.1f  bar3 %.1f" % tuple(ph[:6] / ph[6] / 1e3))
     xs[comp] = g.vec_download(y, N)
     g.vec_free(x); g.vec_free(y)
-print("bit-identical:", np.array_equal(xs[0], xs[1]), np.array_equal(xs[0], xs[2]), "rel", np.linalg.norm(xs[2]-xs[0])/np.linalg.norm(xs[0]))
+for m in MODES[1:]:
+    print("mode", m, "vs", MODES[0], "bit-identical:", np.array_equal(xs[MODES[0]], xs[m]), "rel", np.linalg.norm(xs[m] - xs[MODES[0]]) / np.linalg.norm(xs[MODES[0]]))
