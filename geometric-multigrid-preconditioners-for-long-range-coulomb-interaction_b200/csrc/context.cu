@@ -52,10 +52,53 @@ static void free_sell(Sell &s) {
   s = Sell{};
 }
 static void free_csr(DevCsr &c) {
-  dfree(c.rowptr);
-  dfree(c.col);
-  dfree(c.val);
+  if (!c.in_arena) {
+    dfree(c.rowptr);
+    dfree(c.col);
+    dfree(c.val);
+  }
   c = DevCsr{};
+}
+
+// ---- arenas (context.h) ----------------------------------------------------------------------------
+static void arena_reset(Arena &a) {
+  if (!a.overflow.empty() || a.wanted > a.cap) {
+    cudaDeviceSynchronize();
+    for (char *p : a.overflow) cudaFree(p);
+    a.overflow.clear();
+    if (a.wanted > a.cap) {
+      if (a.base) cudaFree(a.base);
+      a.base = nullptr;
+      a.cap = 0;
+      const size_t want = a.wanted + a.wanted / 8;
+      if (cudaMalloc((void **)&a.base, want) == cudaSuccess) a.cap = want;
+      else cudaGetLastError();
+    }
+  }
+  a.used = 0;
+  a.wanted = 0;
+}
+static void arena_destroy(Arena &a) {
+  for (char *p : a.overflow) cudaFree(p);
+  a.overflow.clear();
+  if (a.base) cudaFree(a.base);
+  a = Arena{};
+}
+template <class T>
+static cudaError_t arena_alloc(Arena &a, T **p, int64_t n) {
+  const size_t bytes = ((size_t)(n > 0 ? n : 1) * sizeof(T) + 255) & ~(size_t)255;
+  a.wanted += bytes;
+  if (a.used + bytes <= a.cap) {
+    *p = reinterpret_cast<T *>(a.base + a.used);
+    a.used += bytes;
+    return cudaSuccess;
+  }
+  char *q = nullptr;
+  const cudaError_t e = cudaMalloc((void **)&q, bytes);
+  if (e != cudaSuccess) return e;
+  a.overflow.push_back(q);
+  *p = reinterpret_cast<T *>(q);
+  return cudaSuccess;
 }
 
 int ensure_stage(gmg_context *h, int64_t n) {
@@ -112,14 +155,22 @@ static int staged_h2d(gmg_context *h, void *dst, const void *src, size_t bytes) 
 }
 
 static int upload_csr(gmg_context *h, int n_rows, int n_cols, const int64_t *rowptr, const int32_t *col,
-                      const double *val, DevCsr &out) {
+                      const double *val, DevCsr &out, Arena *arena = nullptr) {
   free_csr(out);
   out.n_rows = n_rows;
   out.n_cols = n_cols;
   out.nnz = rowptr[n_rows];
-  GMG_CUDA(h, dalloc(&out.rowptr, n_rows + 1));
-  GMG_CUDA(h, dalloc(&out.col, out.nnz));
-  GMG_CUDA(h, dalloc(&out.val, out.nnz));
+  if (arena) {
+    arena_reset(*arena);
+    out.in_arena = true;
+    GMG_CUDA(h, arena_alloc(*arena, &out.rowptr, n_rows + 1));
+    GMG_CUDA(h, arena_alloc(*arena, &out.col, out.nnz));
+    GMG_CUDA(h, arena_alloc(*arena, &out.val, out.nnz));
+  } else {
+    GMG_CUDA(h, dalloc(&out.rowptr, n_rows + 1));
+    GMG_CUDA(h, dalloc(&out.col, out.nnz));
+    GMG_CUDA(h, dalloc(&out.val, out.nnz));
+  }
   if (int rc = staged_h2d(h, out.rowptr, rowptr, sizeof(int64_t) * (n_rows + 1))) return rc;
   if (int rc = staged_h2d(h, out.col, col, sizeof(int) * out.nnz)) return rc;
   if (int rc = staged_h2d(h, out.val, val, sizeof(double) * out.nnz)) return rc;
@@ -338,6 +389,7 @@ static int build_pat(gmg_context *h, Sell &s) {
   s.patterned = false;
   if (!s.valid || s.v.n_slices == 0) return GMG_OK;
   TraceScope tr("    row patterns");
+  arena_reset(h->scratch);  // (every temporary below is a bump allocation from it)
   constexpr int LOG_TABLE = 18, LIMIT = 120000, MIN_COUNT = 16;
   const int mask = (1 << LOG_TABLE) - 1;
   const int n = s.v.n_rows, n_padded = s.v.n_slices * 32;
@@ -348,18 +400,6 @@ static int build_pat(gmg_context *h, Sell &s) {
   void *cub_tmp = nullptr;
   int *sub_width = nullptr;
   auto cleanup = [&]() {
-    dfree(hash);
-    dfree(keys);
-    dfree(rep);
-    dfree(cnt);
-    dfree(d_count);
-    dfree(slot_pid);
-    dfree(pid_rep);
-    dfree(width);
-    dfree(irregular);
-    dfree(sub_width);
-    if (cub_tmp) cudaFreeAsync(cub_tmp, h->stream);
-    cub_tmp = nullptr;
   };
   auto drop = [&]() {
     cleanup();
@@ -376,11 +416,11 @@ static int build_pat(gmg_context *h, Sell &s) {
     dfree(s.rem_cval);
     dfree(s.dom_mask);
   };
-  GMG_CUDA(h, dalloc(&hash, n));
-  GMG_CUDA(h, dalloc(&keys, (int64_t)mask + 1));
-  GMG_CUDA(h, dalloc(&rep, (int64_t)mask + 1));
-  GMG_CUDA(h, dalloc(&cnt, (int64_t)mask + 1));
-  GMG_CUDA(h, dalloc(&d_count, 4));
+  GMG_CUDA(h, arena_alloc(h->scratch, &hash, n));
+  GMG_CUDA(h, arena_alloc(h->scratch, &keys, (int64_t)mask + 1));
+  GMG_CUDA(h, arena_alloc(h->scratch, &rep, (int64_t)mask + 1));
+  GMG_CUDA(h, arena_alloc(h->scratch, &cnt, (int64_t)mask + 1));
+  GMG_CUDA(h, arena_alloc(h->scratch, &d_count, 4));
   GMG_CUDA(h, cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * ((size_t)mask + 1), h->stream));
   GMG_CUDA(h, cudaMemsetAsync(rep, 0x7f, sizeof(int) * ((size_t)mask + 1), h->stream));
   GMG_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)mask + 1), h->stream));
@@ -416,8 +456,8 @@ static int build_pat(gmg_context *h, Sell &s) {
   }
   std::vector<int> h_cand_rep(n_cand);
   for (int p = 0; p < n_cand; ++p) h_cand_rep[p] = ents[p].rep;
-  GMG_CUDA(h, dalloc(&pid_rep, n_cand));
-  GMG_CUDA(h, dalloc(&width, n_cand));
+  GMG_CUDA(h, arena_alloc(h->scratch, &pid_rep, n_cand));
+  GMG_CUDA(h, arena_alloc(h->scratch, &width, n_cand));
   GMG_CUDA(h, copy(h, pid_rep, h_cand_rep.data(), sizeof(int) * n_cand, cudaMemcpyHostToDevice));
   pat_widths<<<cdiv(n_cand, 128), 128, 0, h->stream>>>(s.v, n_cand, pid_rep, width);
   GMG_LAUNCH_CHECK(h);
@@ -442,14 +482,14 @@ static int build_pat(gmg_context *h, Sell &s) {
     if (v < 0) v = np;
   hptr.push_back(hptr.back());
   const int n_ent = hptr[np];
-  GMG_CUDA(h, dalloc(&slot_pid, (int64_t)mask + 1));
+  GMG_CUDA(h, arena_alloc(h->scratch, &slot_pid, (int64_t)mask + 1));
   GMG_CUDA(h, copy(h, slot_pid, h_slot_pid.data(), sizeof(int) * h_slot_pid.size(), cudaMemcpyHostToDevice));
   GMG_CUDA(h, copy(h, pid_rep, h_pid_rep.data(), sizeof(int) * np, cudaMemcpyHostToDevice));
   GMG_CUDA(h, dalloc(&s.pat_ptr, np + 2));
   GMG_CUDA(h, dalloc(&s.pat_off, n_ent));
   GMG_CUDA(h, dalloc(&s.pat_val, n_ent));
   GMG_CUDA(h, dalloc(&s.pat, n_padded));
-  GMG_CUDA(h, dalloc(&irregular, n_padded));
+  GMG_CUDA(h, arena_alloc(h->scratch, &irregular, n_padded));
   GMG_CUDA(h, cudaMemsetAsync(irregular, 0, n_padded, h->stream));
   GMG_CUDA(h, copy(h, s.pat_ptr, hptr.data(), sizeof(int) * (np + 2), cudaMemcpyHostToDevice));
   pat_fill<<<cdiv(np, 128), 128, 0, h->stream>>>(s.v, np, pid_rep, s.pat_ptr, s.pat_off, s.pat_val);
@@ -463,7 +503,7 @@ static int build_pat(gmg_context *h, Sell &s) {
   size_t tmp_bytes = 0;
   thrust::counting_iterator<int> iota(0);
   GMG_CUDA(h, cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, irregular, s.rem_rows, d_count + 2, n, h->stream));
-  GMG_CUDA(h, cudaMallocAsync(&cub_tmp, std::max<size_t>(tmp_bytes, 1), h->stream));
+  GMG_CUDA(h, arena_alloc(h->scratch, (char **)&cub_tmp, (int64_t)tmp_bytes));
   GMG_CUDA(h, cub::DeviceSelect::Flagged(cub_tmp, tmp_bytes, iota, irregular, s.rem_rows, d_count + 2, n, h->stream));
   int flags[4] = {0, 0, 0, 0};
   GMG_CUDA(h, copy_sync(h, flags, d_count, 4 * sizeof(int), cudaMemcpyDeviceToHost));
@@ -475,7 +515,7 @@ static int build_pat(gmg_context *h, Sell &s) {
   const int rs = cdiv(n_rem, SLICE);
   std::vector<int64_t> rsp(rs + 1, 0);
   if (rs > 0) {
-    GMG_CUDA(h, dalloc(&sub_width, rs));
+    GMG_CUDA(h, arena_alloc(h->scratch, &sub_width, rs));
     sell_sub_widths<<<cdiv((int64_t)rs * 32, 256), 256, 0, h->stream>>>(s.v, n_rem, s.rem_rows, sub_width);
     GMG_LAUNCH_CHECK(h);
     std::vector<int> rw(rs);
@@ -494,7 +534,7 @@ static int build_pat(gmg_context *h, Sell &s) {
   // ... and as CSR (4 lanes per row in the window kernel)
   {
     int *rcnt = nullptr;
-    GMG_CUDA(h, dalloc(&rcnt, n_rem + 1));
+    GMG_CUDA(h, arena_alloc(h->scratch, &rcnt, n_rem + 1));
     GMG_CUDA(h, dalloc(&s.rem_ptr, n_rem + 1));
     GMG_CUDA(h, cudaMemsetAsync(rcnt, 0, sizeof(int) * (n_rem + 1), h->stream));
     if (n_rem > 0) {
@@ -504,12 +544,10 @@ static int build_pat(gmg_context *h, Sell &s) {
     size_t scan_bytes = 0;
     void *scan_tmp = nullptr;
     GMG_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, rcnt, s.rem_ptr, n_rem + 1, h->stream));
-    GMG_CUDA(h, cudaMallocAsync(&scan_tmp, std::max<size_t>(scan_bytes, 1), h->stream));
+    GMG_CUDA(h, arena_alloc(h->scratch, (char **)&scan_tmp, (int64_t)scan_bytes));
     GMG_CUDA(h, cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, rcnt, s.rem_ptr, n_rem + 1, h->stream));
     int rem_nnz = 0;
     GMG_CUDA(h, copy_sync(h, &rem_nnz, s.rem_ptr + n_rem, sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFreeAsync(scan_tmp, h->stream);
-    dfree(rcnt);
     GMG_CUDA(h, dalloc(&s.rem_ccol, rem_nnz));
     GMG_CUDA(h, dalloc(&s.rem_cval, rem_nnz));
     if (n_rem > 0) {
@@ -537,8 +575,8 @@ static int build_pat(gmg_context *h, Sell &s) {
     if (s.dom.len > 0 && s.v.n_rows == s.v.n_cols) {
       // the set Z of columns the sub-sequence rows need zeroed in the operand copy (pattern_win.cuh)
       int *colflag = nullptr, *conflict = nullptr;
-      GMG_CUDA(h, dalloc(&colflag, n));
-      GMG_CUDA(h, dalloc(&conflict, 1));
+      GMG_CUDA(h, arena_alloc(h->scratch, &colflag, n));
+      GMG_CUDA(h, arena_alloc(h->scratch, &conflict, 1));
       GMG_CUDA(h, cudaMemsetAsync(colflag, 0, sizeof(int) * n, h->stream));
       GMG_CUDA(h, cudaMemsetAsync(conflict, 0, sizeof(int), h->stream));
       pat_mark_columns<<<cdiv(n, 256), 256, 0, h->stream>>>(s.pv, s.pat, s.dom_mask, s.dom.len, colflag);
@@ -561,9 +599,7 @@ static int build_pat(gmg_context *h, Sell &s) {
         GMG_CUDA(h, copy_sync(h, s.dom_mask, hmask.data(), sizeof(uint32_t) * (np + 1), cudaMemcpyHostToDevice));
       }
       GMG_CUDA(h, cudaStreamSynchronize(h->stream));
-      dfree(colflag);
-      dfree(conflict);
-      if (std::getenv("GMG_TRACE")) std::fprintf(stderr, "[gmg trace]     zeroed-operand set: %s\n", hc ? "conflict (exact rows only)" : "ok");
+          if (std::getenv("GMG_TRACE")) std::fprintf(stderr, "[gmg trace]     zeroed-operand set: %s\n", hc ? "conflict (exact rows only)" : "ok");
     } else {
       s.dom.len = 0;
     }
@@ -1227,6 +1263,9 @@ int gmg_destroy(gmg_handle h) {
   drop_vc_graphs(h);
   for (auto &L : h->levels) free_level(L);
   free_csr(h->rawS);
+  arena_destroy(h->scratch);
+  arena_destroy(h->upload[0]);
+  arena_destroy(h->upload[1]);
   free_sell(h->S);
   dfree(h->s_dinv);
   dfree(h->g);
@@ -1304,7 +1343,7 @@ int gmg_set_matrix(gmg_handle h, int which, int level, int32_t n_rows, int32_t n
       h->dist.hS = make_host(n_rows, n_cols, rowptr, col, val);
       return GMG_OK;
     }
-    return upload_csr(h, n_rows, n_cols, rowptr, col, val, h->rawS);
+    return upload_csr(h, n_rows, n_cols, rowptr, col, val, h->rawS, &h->upload[0]);
   }
   if (level < 0 || level >= h->n_levels) return fail(h, GMG_EINVAL, "level out of range (call gmg_set_num_levels)");
   Level &L = h->levels[level];
@@ -1315,7 +1354,7 @@ int gmg_set_matrix(gmg_handle h, int which, int level, int32_t n_rows, int32_t n
       return GMG_OK;
     }
     if (level >= 1) L.hA = make_host(n_rows, n_cols, rowptr, col, val);
-    return upload_csr(h, n_rows, n_cols, rowptr, col, val, L.rawA);
+    return upload_csr(h, n_rows, n_cols, rowptr, col, val, L.rawA, level == 0 ? &h->upload[1] : nullptr);
   }
   if (which == GMG_EDGE) {
     L.hI = make_host(n_rows, n_cols, rowptr, col, val);

@@ -24,6 +24,7 @@ struct HostCsr {
 };
 
 struct DevCsr {
+  bool in_arena = false;  // arrays live in an Arena of the context (not freed individually)
   int n_rows = 0, n_cols = 0;
   int64_t nnz = 0;
   int64_t *rowptr = nullptr;
@@ -143,6 +144,17 @@ struct DistData {
 
 }  // namespace gmg
 
+namespace gmg {
+// Grow-only device arena with bump allocation: transient set-up buffers (raw CSR uploads, the temporaries of the
+// row-pattern build) stay out of the stream-ordered pool, whose free blocks they would otherwise fragment: a
+// hierarchy that is handed over again then finds its (large) blocks free instead of growing the pool.
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0, used = 0, wanted = 0;
+  std::vector<char *> overflow;  // blocks taken while the arena was too small (released at the next reset)
+};
+}  // namespace gmg
+
 struct gmg_context {
   int device = 0;
   int sm_count = 0;
@@ -154,6 +166,8 @@ struct gmg_context {
 
   int n_levels = 0;
   std::vector<gmg::Level> levels;
+  gmg::Arena scratch;          // temporaries of build_pat
+  gmg::Arena upload[2];        // raw CSR of the system matrix / the level-0 matrix
   gmg::DevCsr rawS;
   gmg::Sell S;  // system matrix
   int n_sys = 0;
