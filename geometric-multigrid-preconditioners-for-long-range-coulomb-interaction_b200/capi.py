@@ -62,6 +62,7 @@ SIGNATURES = {
     "gmg_spmv_dev": (_i, [_h, _i, _i, C.c_void_p, C.c_void_p]),
     "gmg_cg_solve_dev": (_i, [_h, _i, _i, C.c_void_p, C.c_void_p, _i, _d, C.POINTER(_i), _pd]),
     "gmg_matrix_traffic": (_i, [_h, _i, _i, _pd]),
+    "gmg_pair_energies": (_i, [_h, _d, _pd]),
     "gmg_debug_cg_phases": (_i, [_h, _i, _pd]),
     "gmg_debug_cg_blocks": (_i, [_h, _pd]),
     "gmg_coarse_profile": (_i, [_h, _i, _pd, _pi64, _pi64]),
@@ -295,6 +296,11 @@ class Gmg:
         self._ck(self.lib.gmg_matrix_traffic(self.h, which, level, _pd_of(out)))
         return dict(nnz=out[0], spmv_bytes=out[1], cg_iter_bytes=out[2], csr_spmv_bytes=out[3], csr_cg_iter_bytes=out[4],
                     compressed=bool(out[5]), format=int(out[5]))
+
+    def pair_energies(self, r_c):
+        out = np.zeros(2)
+        self._ck(self.lib.gmg_pair_energies(self.h, float(r_c), _pd_of(out)))
+        return dict(analytic=out[0], short=out[1])
 
     def debug_cg_phases(self, block_plus_1=1):
         out = np.zeros(16)

@@ -113,7 +113,7 @@ int ensure_stage(gmg_context *h, int64_t n) {
 
 // Large host->device copies from pageable memory: chunks are copied into a ring of pinned buffers by a few host
 // threads (one memcpy thread tops out near 10 GB/s) while the previous chunk is in flight on the copy engine.
-static int staged_h2d(gmg_context *h, void *dst, const void *src, size_t bytes) {
+int staged_h2d(gmg_context *h, void *dst, const void *src, size_t bytes) {
   constexpr size_t CHUNK = 32u << 20;
   constexpr int NBUF = 4, NTHREADS = 6;
   if (bytes < (8u << 20)) {
@@ -151,6 +151,44 @@ static int staged_h2d(gmg_context *h, void *dst, const void *src, size_t bytes) 
     off += n;
     buf = (buf + 1) % NBUF;
   }
+  return GMG_OK;
+}
+
+// Large device->host copies into pageable memory: DMA into the pinned ring, host threads copy out while the next
+// chunk is in flight.  Synchronous (the destination is complete on return).
+int staged_d2h(gmg_context *h, void *dst, const void *src, size_t bytes) {
+  constexpr size_t CHUNK = 32u << 20;
+  constexpr int NBUF = 4, NTHREADS = 6;
+  if (bytes < (8u << 20) || !h->pin[0]) {
+    GMG_CUDA(h, copy_sync(h, dst, src, bytes, cudaMemcpyDeviceToHost));
+    return GMG_OK;
+  }
+  h->d2h_bytes += (int64_t)bytes;
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));  // (the ring may still be draining uploads)
+  const int n_chunks = (int)((bytes + CHUNK - 1) / CHUNK);
+  auto issue = [&](int c) {
+    const size_t off = (size_t)c * CHUNK, n = std::min(CHUNK, bytes - off);
+    cudaMemcpyAsync(h->pin[c % NBUF], (const char *)src + off, n, cudaMemcpyDeviceToHost, h->stream);
+    cudaEventRecord(h->pin_free[c % NBUF], h->stream);
+  };
+  for (int c = 0; c < std::min(n_chunks, NBUF - 1); ++c) issue(c);
+  for (int c = 0; c < n_chunks; ++c) {
+    if (c + NBUF - 1 < n_chunks) issue(c + NBUF - 1);  // its buffer was emptied in the previous iteration
+    GMG_CUDA(h, cudaEventSynchronize(h->pin_free[c % NBUF]));
+    const size_t off = (size_t)c * CHUNK, n = std::min(CHUNK, bytes - off);
+    const char *s = h->pin[c % NBUF];
+    char *d = (char *)dst + off;
+    std::thread th[NTHREADS];
+    const size_t part = (n + NTHREADS - 1) / NTHREADS;
+    for (int t = 0; t < NTHREADS; ++t) {
+      const size_t a = std::min(n, part * t), b = std::min(n, part * (t + 1));
+      th[t] = std::thread([=]() {
+        if (b > a) std::memcpy(d + a, s + a, b - a);
+      });
+    }
+    for (auto &t : th) t.join();
+  }
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return GMG_OK;
 }
 
@@ -928,8 +966,7 @@ static int smooth(gmg_context *h, Level &L, double *&u, const double *rhs, bool 
     auto &bwd = lex ? L.wave_bwd : L.colors;
     auto relax = [&](ColorSet &c) -> int {
       if (c.n == 0) return GMG_OK;
-      sell_color_relax<<<cdiv((int64_t)c.A.v.n_slices * 32, 256), 256, 0, h->stream>>>(c.A.v, c.rows, u, rhs, L.dinv,
-                                                                                        h->omega);
+      sell_color_relax<<<cdiv((int64_t)c.A.v.n_rows * 8, 256), 256, 0, h->stream>>>(c.A.v, c.rows, u, rhs, L.dinv, h->omega);
       GMG_LAUNCH_CHECK(h);
       return GMG_OK;
     };

@@ -255,6 +255,8 @@ inline void dfree(T *&p) {
 }
 int fail(gmg_context *h, int code, const std::string &msg);
 int ensure_stage(gmg_context *h, int64_t n);
+int staged_h2d(gmg_context *h, void *dst, const void *src, size_t bytes);  // large copies through the pinned ring
+int staged_d2h(gmg_context *h, void *dst, const void *src, size_t bytes);
 void rhs_free(gmg_context *h);
 void rhs_invalidate_partition(gmg_context *h);
 inline cudaError_t copy(gmg_context *h, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {

@@ -337,17 +337,68 @@ __global__ void __launch_bounds__(256) sell_spmv(SellView A, const double *__res
 
 // rows of one colour, in place Gauss-Seidel update: u_i += omega (rhs_i - sum_j a_ij u_j) / a_ii
 // (A_c holds the rows of this colour; rows[k] is the global row of local row k; dinv global).
+// A colour of a patch level is a few thousand rows: the launch is latency-bound, not bandwidth-bound.  Eight lanes
+// share a row: every lane loads its part of the row's entries and operands at once (two memory round trips per row
+// instead of two per four entry pairs), then the FMA chain runs through the eight lanes in entry order, the
+// partial sum handed on by shuffle: same order, same bits as one lane per row.
 __global__ void __launch_bounds__(256) sell_color_relax(SellView Ac, const int *__restrict__ rows, double *u,
                                                         const double *__restrict__ rhs, const double *__restrict__ dinv,
                                                         double omega) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int slice = k >> 5, lane = k & 31;
-  if (slice >= Ac.n_slices) return;
-  const double ax = sell_row_dot<false>(Ac, slice, lane, u);
-  if (k < Ac.n_rows) {
-    const int i = rows[k];
-    u[i] += omega * (rhs[i] - ax) * dinv[i];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = t >> 3, sub = t & 7;
+  const bool on = k < Ac.n_rows;
+  const int slice = k >> 5, rlane = k & 31;
+  int64_t b = 0;
+  int npairs = 0;
+  int i = 0;
+  double rv = 0.0, dv = 0.0;
+  if (on) {
+    b = Ac.slice_ptr[slice];
+    npairs = (int)((Ac.slice_ptr[slice + 1] - b) >> 6);
+    if (sub == 0) {
+      i = rows[k];
+      rv = rhs[i];
+      dv = dinv[i];
+    }
   }
+  const double2 *v2 = reinterpret_cast<const double2 *>(Ac.val) + (b >> 1) + rlane;
+  const int2 *c2 = reinterpret_cast<const int2 *>(Ac.col) + (b >> 1) + rlane;
+  const int pmax = __reduce_max_sync(0xffffffffu, npairs);
+  double acc = 0.0;
+  for (int base = 0; base < pmax; base += 32) {  // 32 pairs per round, 4 per lane
+    const int n_here = min(max(npairs - base, 0), 32);
+    const int chunk = (n_here + 7) >> 3;
+    const int p0 = base + sub * chunk;
+    const int cnt = max(min(chunk, n_here - sub * chunk), 0);
+    double2 v[4];
+    int2 c[4];
+    double x0[4], x1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < cnt) {
+        v[q] = ld_stream_d2(v2 + (p0 + q) * 32);
+        c[q] = ld_stream_i2(c2 + (p0 + q) * 32);
+      }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < cnt) {
+        x0[q] = u[c[q].x];
+        x1[q] = u[c[q].y];
+      }
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      if (sub == cc) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < cnt) {
+            acc = fma(v[q].x, x0[q], acc);
+            acc = fma(v[q].y, x1[q], acc);
+          }
+      }
+      acc = __shfl_sync(0xffffffffu, acc, (threadIdx.x & 24) | cc);
+    }
+  }
+  if (on && sub == 0) u[i] += omega * (rv - acc) * dv;
 }
 
 // One smooth() call of the multicolour / level-scheduled SSOR as ONE cooperative launch: colours (or wavefronts)

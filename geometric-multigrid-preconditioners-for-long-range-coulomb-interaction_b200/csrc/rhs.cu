@@ -37,8 +37,60 @@ template <class T>
 int upload(gmg_context *h, T *&dst, const T *src, int64_t n) {
   dfree(dst);
   GMG_CUDA(h, dalloc(&dst, n));
-  if (n > 0) GMG_CUDA(h, gmg::copy(h, dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+  if (n > 0)
+    if (int rc = gmg::staged_h2d(h, dst, src, sizeof(T) * n)) return rc;
   return GMG_OK;
+}
+
+// Pair sums of the energy post-processing (src/step-50.cc:1316-1332): sum_{i<j} q_i q_j / r_ij and
+// sum_{i<j} q_i q_j erfc(r_ij / r_c) / r_ij.  One thread per atom i, atoms j > i streamed through shared memory in
+// tiles; fp64 throughout; per-block partial sums are added on the host in block order (deterministic).
+constexpr int PAIR_BLOCK = 128;
+__global__ void __launch_bounds__(PAIR_BLOCK) pair_energy_kernel(int n, const double *__restrict__ pos, const double *__restrict__ q,
+                                                                   double inv_rc, double *__restrict__ partial /* [2][gridDim.x] */) {
+  __shared__ double sx[PAIR_BLOCK], sy[PAIR_BLOCK], sz[PAIR_BLOCK], sq[PAIR_BLOCK];
+  __shared__ double red[2][PAIR_BLOCK / 32];
+  const int i = blockIdx.x * PAIR_BLOCK + threadIdx.x;
+  const bool on = i < n;
+  const double xi = on ? pos[3 * i] : 0.0, yi = on ? pos[3 * i + 1] : 0.0, zi = on ? pos[3 * i + 2] : 0.0, qi = on ? q[i] : 0.0;
+  double e_coul = 0.0, e_short = 0.0;
+  for (int j0 = blockIdx.x * PAIR_BLOCK; j0 < n; j0 += PAIR_BLOCK) {  // tiles at or after this block's own
+    const int j = j0 + threadIdx.x;
+    __syncthreads();
+    sx[threadIdx.x] = j < n ? pos[3 * j] : 0.0;
+    sy[threadIdx.x] = j < n ? pos[3 * j + 1] : 0.0;
+    sz[threadIdx.x] = j < n ? pos[3 * j + 2] : 0.0;
+    sq[threadIdx.x] = j < n ? q[j] : 0.0;
+    __syncthreads();
+    const int m = min(PAIR_BLOCK, n - j0);
+    for (int t = 0; t < m; ++t) {
+      if (j0 + t > i && on) {
+        const double dx = xi - sx[t], dy = yi - sy[t], dz = zi - sz[t];
+        const double r = sqrt(dx * dx + dy * dy + dz * dz);
+        const double qq = qi * sq[t];
+        e_coul += qq / r;
+        e_short += qi * (sq[t] * (erfc(r * inv_rc) / r));
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    e_coul += __shfl_xor_sync(0xffffffffu, e_coul, o);
+    e_short += __shfl_xor_sync(0xffffffffu, e_short, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = e_coul;
+    red[1][threadIdx.x >> 5] = e_short;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < PAIR_BLOCK / 32; ++w) {
+      a += red[0][w];
+      b += red[1][w];
+    }
+    partial[blockIdx.x] = a;
+    partial[gridDim.x + blockIdx.x] = b;
+  }
 }
 
 RhsState *state(gmg_context *h) {
@@ -489,7 +541,7 @@ int gmg_charge_density(gmg_handle h, int32_t n_cells, const double *cell_lo, con
   GMG_CUDA(h, dalloc(&s->rho, (int64_t)n_cells * n_q));
   if (int rc = run_density(h, s)) return rc;
   if (rho_out)
-    GMG_CUDA(h, gmg::copy(h, rho_out, s->rho, sizeof(double) * (int64_t)n_cells * n_q, cudaMemcpyDeviceToHost));
+    if (int rc = gmg::staged_d2h(h, rho_out, s->rho, sizeof(double) * (int64_t)n_cells * n_q)) return rc;
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return GMG_OK;
 }
@@ -589,6 +641,29 @@ int gmg_point_values(gmg_handle h, int32_t n_points, const int32_t *cell_dofs, c
   dfree(d_u);
   dfree(d_out);
   return rc;
+}
+
+int gmg_pair_energies(gmg_handle h, double r_c, double out[2]) {
+  if (!h || !out || !(r_c > 0.0)) return GMG_EINVAL;
+  if (!h->atom_pos) return fail(h, GMG_EINVAL, "gmg_set_atoms first");
+  gmg::enter(h);
+  const int n = h->n_atoms;
+  out[0] = out[1] = 0.0;
+  if (n < 2) return GMG_OK;
+  const int grid = cdiv(n, PAIR_BLOCK);
+  double *partial = nullptr;
+  GMG_CUDA(h, dalloc(&partial, 2 * (int64_t)grid));
+  pair_energy_kernel<<<grid, PAIR_BLOCK, 0, h->stream>>>(n, h->atom_pos, h->atom_q, 1.0 / r_c, partial);
+  h->launches++;
+  std::vector<double> hp(2 * (size_t)grid);
+  const cudaError_t e = gmg::copy_sync(h, hp.data(), partial, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost);
+  dfree(partial);
+  if (e != cudaSuccess) return fail(h, GMG_ECUDA, std::string("pair energies: ") + cudaGetErrorString(e));
+  for (int b = 0; b < grid; ++b) {
+    out[0] += hp[b];
+    out[1] += hp[grid + b];
+  }
+  return GMG_OK;
 }
 
 }  // extern "C"

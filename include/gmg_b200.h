@@ -208,6 +208,9 @@ int gmg_assemble_rhs(gmg_handle h, int32_t n_cells, const double *rho, const dou
 int gmg_point_values(gmg_handle h, int32_t n_points, const int32_t *cell_dofs /*[n][8]*/,
                      const double *ref_coords /*[n][3]*/, const double *u, int32_t n_dofs,
                      double *phi_out);
+/* The O(N^2) pair sums of postprocess_electrostatic_energy (src/step-50.cc:1316-1332) over the atoms of gmg_set_atoms:
+ * out[0] = sum_{i<j} q_i q_j / r_ij, out[1] = sum_{i<j} q_i q_j erfc(r_ij / r_c) / r_ij. */
+int gmg_pair_energies(gmg_handle h, double r_c, double out[2]);
 /* fused device-resident RHS step used by the bench `value` leg: densities + load vector with the
  * inputs of the last gmg_charge_density / gmg_assemble_rhs calls kept on the device. */
 int gmg_rhs_step_dev(gmg_handle h, double *b_dev);
