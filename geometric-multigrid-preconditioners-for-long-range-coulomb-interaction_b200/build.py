@@ -24,7 +24,7 @@ def _stale(target, sources):
 def build_cuda(verbose=False, force=False):
     os.makedirs(LIB, exist_ok=True)
     src_dir = os.path.join(HERE, "csrc")
-    srcs = [os.path.join(src_dir, f) for f in ("context.cu", "rhs.cu", "partition.cc")]
+    srcs = [os.path.join(src_dir, f) for f in ("context.cu", "rhs.cu", "indicator.cu", "partition.cc")]
     deps = [os.path.join(src_dir, f) for f in os.listdir(src_dir)] + [os.path.join(ROOT, "include", "gmg_b200.h")]
     out = os.path.join(LIB, "libgmg_b200.so")
     if force or _stale(out, deps):

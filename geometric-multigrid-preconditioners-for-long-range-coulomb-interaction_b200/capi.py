@@ -63,6 +63,8 @@ SIGNATURES = {
     "gmg_cg_solve_dev": (_i, [_h, _i, _i, C.c_void_p, C.c_void_p, _i, _d, C.POINTER(_i), _pd]),
     "gmg_matrix_traffic": (_i, [_h, _i, _i, _pd]),
     "gmg_pair_energies": (_i, [_h, _d, _pd]),
+    "gmg_error_indicator": (_i, [_h, _i, _pi32, _pu8, _i, _pi32, _pd, _i, _pd, _i, _pd, _pd, C.POINTER(C.c_float),
+                                 C.POINTER(C.c_float)]),
     "gmg_debug_cg_phases": (_i, [_h, _i, _pd]),
     "gmg_debug_cg_blocks": (_i, [_h, _pd]),
     "gmg_coarse_profile": (_i, [_h, _i, _pd, _pi64, _pi64]),
@@ -296,6 +298,21 @@ class Gmg:
         self._ck(self.lib.gmg_matrix_traffic(self.h, which, level, _pd_of(out)))
         return dict(nnz=out[0], spmv_bytes=out[1], cg_iter_bytes=out[2], csr_spmv_bytes=out[3], csr_cg_iter_bytes=out[4],
                     compressed=bool(out[5]), format=int(out[5]))
+
+    def error_indicator(self, face_nb, face_kind, hang_children, u, rho, residual_term, gauss2_points, gauss2_weights):
+        """eta (float32 per active cell of the last assemble_rhs call) and max eta; rho None = device-resident densities."""
+        face_nb, hang_children = _i32(face_nb), _i32(hang_children)
+        face_kind = np.ascontiguousarray(face_kind, dtype=np.uint8)
+        u, gp, gw = _f64(u), _f64(gauss2_points), _f64(gauss2_weights)
+        n_cells = len(face_nb) // 6
+        rho_a = _f64(rho).ravel() if rho is not None else None
+        eta = np.zeros(n_cells, dtype=np.float32)
+        mx = C.c_float(0)
+        self._ck(self.lib.gmg_error_indicator(
+            self.h, n_cells, face_nb.ctypes.data_as(_pi32), face_kind.ctypes.data_as(_pu8), len(hang_children) // 4,
+            hang_children.ctypes.data_as(_pi32), _pd_of(u), len(u), _pd_of(rho_a) if rho_a is not None else None,
+            int(residual_term), _pd_of(gp), _pd_of(gw), eta.ctypes.data_as(C.POINTER(C.c_float)), C.byref(mx)))
+        return eta, mx.value
 
     def pair_energies(self, r_c):
         out = np.zeros(2)

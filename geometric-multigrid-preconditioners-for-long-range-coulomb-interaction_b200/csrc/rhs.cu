@@ -371,6 +371,21 @@ void rhs_free(gmg_context *h) {
 }
 }  // namespace gmg
 
+// the cell arrays kept on the device by the last gmg_assemble_rhs / gmg_charge_density call (indicator.cu)
+int gmg_rhs_resident(gmg_context *h, int *n_cells, const double **cell_h, const int **cell_dofs, const double **weights, int *n_q,
+                     const double **rho, int *rho_cells, int *rho_nq) {
+  RhsState *s = state(h);
+  *n_cells = s->a_cells;
+  *cell_h = s->a_h;
+  *cell_dofs = s->cell_dofs;
+  *weights = s->weights;
+  *n_q = s->a_nq;
+  *rho = s->rho;
+  *rho_cells = s->n_cells;
+  *rho_nq = s->n_q;
+  return GMG_OK;
+}
+
 extern "C" {
 
 int gmg_set_atoms(gmg_handle h, int32_t n_atoms, const double *pos, const double *charge) {

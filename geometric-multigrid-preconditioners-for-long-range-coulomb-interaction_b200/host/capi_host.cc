@@ -19,6 +19,7 @@ struct Bundle {
   std::vector<std::vector<float>> eta;
   std::vector<std::vector<char>> flags;
   double threshold = 0.0;
+  IndicatorTopology topo;
   std::vector<int32_t> scratch_i32;
   std::vector<double> scratch_f64;
   std::string err;
@@ -124,6 +125,18 @@ static int get_array(const Forest *fp, const DoFs *dp, const Csr *system, const 
 
 int ms_get(void *p, const char *name, int l, const void **ptr, int64_t *count, int *dtype) {
   Bundle *b = (Bundle *)p;
+  const std::string nm(name);
+  if (nm.rfind("topo_", 0) == 0) {  // face topology for gmg_error_indicator
+    try {
+      if (!b->dofs) { g_err = "DoFs not built"; return -1; }
+      b->topo = indicator_topology(*b->forest, *b->dofs);
+    } catch (std::exception &e) { g_err = e.what(); return -1; }
+    if (nm == "topo_face_nb") { *ptr = b->topo.face_nb.data(); *count = (int64_t)b->topo.face_nb.size(); *dtype = 0; return 0; }
+    if (nm == "topo_face_kind") { *ptr = b->topo.face_kind.data(); *count = (int64_t)b->topo.face_kind.size(); *dtype = 3; return 0; }
+    if (nm == "topo_hang_children") { *ptr = b->topo.hang_children.data(); *count = (int64_t)b->topo.hang_children.size(); *dtype = 0; return 0; }
+    g_err = "unknown array " + nm;
+    return -1;
+  }
   return get_array(b->forest.get(), b->dofs.get(), &b->system, &b->ops, &b->eta, &b->flags, name, l, ptr, count, dtype);
 }
 

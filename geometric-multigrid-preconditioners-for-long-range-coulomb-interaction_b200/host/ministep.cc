@@ -642,6 +642,59 @@ inline double normal_derivative(const double U[NV], double h, int a, double s, d
 }
 }  // namespace
 
+IndicatorTopology indicator_topology(const Forest &f, const DoFs &d) {
+  const int nl = f.n_levels();
+  std::vector<int64_t> off(nl + 1, 0);
+  for (int l = 0; l < nl; ++l) off[l + 1] = off[l] + (int64_t)d.active_cells[l].size();
+  IndicatorTopology T;
+  T.face_nb.assign(6 * (size_t)off[nl], -1);
+  T.face_kind.assign(6 * (size_t)off[nl], 0);
+  for (int l = 0; l < nl; ++l)
+    for (size_t p = 0; p < d.active_cells[l].size(); ++p) {
+      const int c = d.active_cells[l][p];
+      const Int3 &ijk = f.L[l].ijk[c];
+      const size_t me = 6 * (size_t)(off[l] + (int64_t)p);
+      for (int a = 0; a < DIM; ++a) {
+        const int o0 = (a == 0) ? 1 : 0, o1 = (a == 2) ? 1 : 2;
+        for (int side = 0; side < 2; ++side) {
+          Int3 q = ijk;
+          q[a] += side ? 1 : -1;
+          if (!f.inside(l, q[0], q[1], q[2])) continue;  // Dirichlet boundary face
+          const int nb = f.lookup(l, q[0], q[1], q[2]);
+          const size_t at = me + 2 * a + side;
+          if (nb >= 0 && f.active(l, nb)) {
+            T.face_nb[at] = (int32_t)(off[l] + d.active_pos[l][nb]);
+            T.face_kind[at] = 0;
+          } else if (nb >= 0) {  // refined neighbour: its four children on this face, ascending active position
+            int32_t ch[4];
+            int n = 0;
+            for (int b1 = 0; b1 < 2; ++b1)
+              for (int b0 = 0; b0 < 2; ++b0) {
+                Int3 cq;
+                cq[a] = 2 * q[a] + (side ? 0 : 1);
+                cq[o0] = 2 * q[o0] + b0;
+                cq[o1] = 2 * q[o1] + b1;
+                const int cc = (l + 1 < nl) ? f.lookup(l + 1, cq[0], cq[1], cq[2]) : -1;
+                if (cc < 0 || !f.active(l + 1, cc)) throw std::logic_error("unbalanced mesh in indicator_topology");
+                ch[n++] = (int32_t)(off[l + 1] + d.active_pos[l + 1][cc]);
+              }
+            std::sort(ch, ch + 4);
+            T.face_nb[at] = (int32_t)(T.hang_children.size() / 4);
+            T.face_kind[at] = 2;
+            T.hang_children.insert(T.hang_children.end(), ch, ch + 4);
+          } else {  // coarser neighbour
+            const int cc = f.lookup(l - 1, q[0] >> 1, q[1] >> 1, q[2] >> 1);
+            if (cc < 0 || !f.active(l - 1, cc)) throw std::logic_error("unbalanced mesh in indicator_topology");
+            const int sub0 = ijk[o0] - 2 * f.L[l - 1].ijk[cc][o0], sub1 = ijk[o1] - 2 * f.L[l - 1].ijk[cc][o1];
+            T.face_nb[at] = (int32_t)(off[l - 1] + d.active_pos[l - 1][cc]);
+            T.face_kind[at] = (uint8_t)(1 | (sub0 << 2) | (sub1 << 3));
+          }
+        }
+      }
+    }
+  return T;
+}
+
 std::vector<std::vector<float>> error_indicator(const Forest &f, const DoFs &d, const std::vector<double> &u,
                                                 const std::vector<double> &rho, int nq, bool residual_term) {
   const int nl = f.n_levels();

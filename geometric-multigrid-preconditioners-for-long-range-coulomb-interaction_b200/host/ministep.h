@@ -108,6 +108,14 @@ std::vector<double> resolve_inhomogeneity(const DoFs &d, const std::vector<doubl
 // constraints.distribute(solution) (src/step-50.cc:1016)
 void distribute(const DoFs &d, const std::vector<double> &g, std::vector<double> &x);
 
+// face topology of the active cells for the device indicator (gmg_error_indicator, include/gmg_b200.h): active cells
+// numbered level by level in active order (the order of the RHS cell arrays)
+struct IndicatorTopology {
+  std::vector<int32_t> face_nb;        // [n_active][6]
+  std::vector<uint8_t> face_kind;      // [n_active][6]
+  std::vector<int32_t> hang_children;  // [n_hang][4]
+};
+IndicatorTopology indicator_topology(const Forest &f, const DoFs &d);
 // Kelly(cell_diameter) + h_K^2 * int (4 pi rho)^2, Vector<float> storage (src/step-50.cc:1020-1090)
 std::vector<std::vector<float>> error_indicator(const Forest &f, const DoFs &d, const std::vector<double> &u,
                                                 const std::vector<double> &rho /*active cells x nq^3*/, int nq,

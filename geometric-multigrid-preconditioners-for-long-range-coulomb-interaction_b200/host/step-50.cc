@@ -555,8 +555,32 @@ template <int dim>
 void LaplaceProblem<dim>::estimate_error_and_mark_cells() {
   TimerOutput::Scope t(computing_timer, "Estimate error and mark cells");
   const int nq = (int)(degree + quadrature_degree_rhs);
-  error_per_cell = error_indicator(*triangulation, *mg_dof_handler, distributed_solution, density_values, nq,
-                                   indicator_with_residual);
+  // face jumps + residual term on the device (gmg_error_indicator); the host keeps the mesh and provides the face
+  // topology.  The float32 indicators are bit-identical to ministep's error_indicator (tests/test_gpu_indicator.py).
+  {
+    const Forest &f = *triangulation;
+    const DoFs &d = *mg_dof_handler;
+    const IndicatorTopology topo = indicator_topology(f, d);
+    const int nc = (int)(topo.face_nb.size() / 6);
+    std::vector<double> gp2, gw2;
+    gauss_unit(2, gp2, gw2);
+    std::vector<float> eta((size_t)nc);
+    float eta_max = 0.0f;
+    const bool with_rho = indicator_with_residual && !density_values.empty();
+    // GaussianCharges with atoms: the densities of compute_charge_densities are still on the device
+    const double *rho = (with_rho && !lammpsinput) ? density_values.data() : nullptr;
+    (void)nq;
+    gmg_check(gmg_error_indicator(gmg, nc, topo.face_nb.data(), topo.face_kind.data(), (int)(topo.hang_children.size() / 4),
+                                  topo.hang_children.data(), distributed_solution.data(), (int)distributed_solution.size(), rho,
+                                  with_rho ? 1 : 0, gp2.data(), gw2.data(), eta.data(), &eta_max),
+              "gmg_error_indicator");
+    error_per_cell.assign(f.n_levels(), std::vector<float>());
+    size_t off = 0;
+    for (int l = 0; l < f.n_levels(); ++l) {
+      error_per_cell[l].assign(eta.begin() + off, eta.begin() + off + d.active_cells[l].size());
+      off += d.active_cells[l].size();
+    }
+  }
   const double threshold = mark_cells(*triangulation, *mg_dof_handler, error_per_cell, refine_flags);
   *pcout << "Threshold value for refinement:\t" << threshold << std::endl;
   if (rec) {

@@ -208,6 +208,24 @@ int gmg_assemble_rhs(gmg_handle h, int32_t n_cells, const double *rho, const dou
 int gmg_point_values(gmg_handle h, int32_t n_points, const int32_t *cell_dofs /*[n][8]*/,
                      const double *ref_coords /*[n][3]*/, const double *u, int32_t n_dofs,
                      double *phi_out);
+/* Error indicator of estimate_error_and_mark_cells (src/step-50.cc:1020-1090): eta_K = float(sqrt(h_K * sum over the
+ * interior faces of K of int [d_n u_h]^2 + h_K^2 * int_K (4 pi rho)^2)), h_K = cell diameter, face rule QGauss<2>(2),
+ * Vector<float> accumulation as KellyErrorEstimator does.  The active cells are those of the last gmg_assemble_rhs
+ * call (their edges, dofs and quadrature weights are still on the device).  Face topology from the host's mesh
+ * (face = 2 * axis + side):
+ *   face_nb[c][face] < 0     no contribution (Dirichlet boundary face)
+ *   face_kind & 3 == 0       face_nb = active neighbour of the same level
+ *   face_kind & 3 == 1       c is the fine side of a hanging face: face_nb = the coarse neighbour; bits 2 and 3 of
+ *                            face_kind = position of the subface in the coarse face along the two tangential axes
+ *   face_kind & 3 == 2       c is the coarse side: face_nb = row of hang_children, the four fine neighbours in the
+ *                            order the reference visits them (ascending active index)
+ * u = solution after constraints.distribute.  rho: n_cells x n_q densities, or NULL to use those of the last
+ * gmg_charge_density call (device-resident); ignored unless residual_term.  eta_out[n_cells] (float32, bit-identical
+ * to the sequential restatement), *max_out = max eta (the refinement threshold is 0.6 * max, :1084). */
+int gmg_error_indicator(gmg_handle h, int32_t n_cells, const int32_t *face_nb /*[n_cells][6]*/,
+                        const uint8_t *face_kind /*[n_cells][6]*/, int32_t n_hang, const int32_t *hang_children /*[n_hang][4]*/,
+                        const double *u, int32_t n_dofs, const double *rho, int residual_term,
+                        const double gauss2_points[2], const double gauss2_weights[2], float *eta_out, float *max_out);
 /* The O(N^2) pair sums of postprocess_electrostatic_energy (src/step-50.cc:1316-1332) over the atoms of gmg_set_atoms:
  * out[0] = sum_{i<j} q_i q_j / r_ij, out[1] = sum_{i<j} q_i q_j erfc(r_ij / r_c) / r_ij. */
 int gmg_pair_energies(gmg_handle h, double r_c, double out[2]);

@@ -1,0 +1,59 @@
+"""GPU parity test of the refinement indicator (src/step-50.cc:1020-1090): gmg_error_indicator
+against the sequential host restatement (ministep error_indicator, itself pinned against the oracle and the reference's
+golden thresholds in test_host_vs_oracle.py / test_oracle_goldens.py).  The device gathers the face integrals in the
+same order with unfused arithmetic: the float32 indicators must be BIT-identical, so the marked cells are too."""
+import numpy as np
+import pytest
+
+from conftest import make_prm
+from helpers import oracle_cycle, pkg
+import hostlib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def refined():
+    """The 2-atom golden case advanced three adaptive cycles (4 levels, hanging faces in all three directions)."""
+    P = oracle_cycle(make_prm(cycles=4, bc="Exact", atom="atom_n1_2.data", nq=4), 3)
+    f = P.forest
+    M = hostlib.Ministep(f.reps, f.lo, f.hi)
+    for flags in P.flag_history[:3]:
+        M.refine(flags)
+    M.build(matrices=False)
+    return P, M
+
+
+@pytest.mark.parametrize("residual", [True, False])
+def test_indicator_bit_identical_to_sequential_restatement(refined, residual):
+    P, M = refined
+    capi = pkg().capi
+    f = P.forest
+    nq = 2
+    gp, gw = hostlib.gauss(nq)
+    cell_h = np.concatenate([np.full(len(M.get("active_cells", l)), f.h(l)) for l in range(M.n_levels)])
+    cell_dofs = np.concatenate([M.get("cell_dofs", l).reshape(-1, 8) for l in range(M.n_levels)])
+    nc, n_dofs = len(cell_h), len(M.get("boundary"))
+    weights = np.array([gw[x] * gw[y] * gw[z] for z in range(nq) for y in range(nq) for x in range(nq)])
+    shape = np.zeros((nq ** 3, 8))
+    for q, (z, y, x) in enumerate([(z, y, x) for z in range(nq) for y in range(nq) for x in range(nq)]):
+        p = (gp[x], gp[y], gp[z])
+        for v in range(8):
+            shape[q, v] = np.prod([p[k] if (v >> k) & 1 else 1.0 - p[k] for k in range(3)])
+    rng = np.random.default_rng(11)
+    rho = rng.standard_normal((nc, nq ** 3))
+    u = rng.standard_normal(n_dofs)
+    g = capi.Gmg()
+    g.assemble_rhs(rho, cell_h, cell_dofs, shape, weights, n_dofs, M.get("hang_rowptr"), M.get("hang_col"), M.get("hang_val"),
+                   M.get("constrained"))
+    gp2, gw2 = hostlib.gauss(2)
+    eta, mx = g.error_indicator(M.get("topo_face_nb"), M.get("topo_face_kind"), M.get("topo_hang_children"), u, rho, residual,
+                                gp2, gw2)
+    g.close()
+    thr = M.error_indicator(u, rho, nq, residual)
+    ref = np.concatenate([M.get("eta", l) for l in range(M.n_levels)])
+    assert ref.dtype == np.float32 and eta.dtype == np.float32
+    assert (M.get("topo_face_kind") & 3 == 2).any() and (M.get("topo_face_kind") & 3 == 1).any()  # hanging faces are covered
+    assert np.array_equal(eta.view(np.uint32), ref.view(np.uint32))
+    # same indicators, same maximum: the threshold 0.6 * max (src/step-50.cc:1084) marks the same cells
+    assert mx == ref.max() and abs(thr - 0.6 * float(mx)) <= 1e-12 * thr
