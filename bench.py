@@ -294,7 +294,7 @@ def run_b200(args):
     if world > 1:
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        _emit(line)
 
 
 def cpu_baseline_from(B, pos, q, args):
@@ -337,7 +337,7 @@ def run_reference(args):
     value = step.n_dofs * k / sec
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": w + 1,
-        "ms_per_step": 1e3 * sec / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": 1e3 * sec / k, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "impl": "reference",
         "config": workload_config(args, {"n_dofs": step.n_dofs, "outer_iterations": r["its"], "smoother":
                                          f"processor-block SSOR(0.5) x 2, {step.n_blocks} blocks (= threads, as MPI ranks)",
@@ -347,11 +347,20 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
+
+
+def _emit(line):
+    """The ONE JSON line on the real stdout (everything else the process prints goes to stderr, see below)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
     a = parse_args()
+    # libraries print to stdout too (e.g. "NCCL version ..." from the native side): keep stdout for the JSON line alone
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:
