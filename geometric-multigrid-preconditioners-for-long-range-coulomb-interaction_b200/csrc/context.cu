@@ -1111,22 +1111,34 @@ static int vcycle(gmg_context *h, const double *src, double *dst) {
       }
     }
   }
+  // developer probe (gmg_debug_vcycle_profile): events around the three parts
+  cudaEvent_t *ev = nullptr;
+  if (h->vc_prof && h->vc_ev_used + 4 <= (int)h->vc_ev.size()) {
+    ev = &h->vc_ev[h->vc_ev_used];
+    h->vc_ev_used += 4;
+    cudaEventRecord(ev[0], h->stream);
+  }
   if (g) {
     GMG_CUDA(h, cudaGraphLaunch(g->down, h->stream));
     h->launches += g->n_down;
   } else if (int rc = vcycle_down(h, src)) {
     return rc;
   }
+  if (ev) cudaEventRecord(ev[1], h->stream);
   {
     Level &L0 = h->levels[0];
     if (int rc = coarse_cg(h, L0.A, L0.defect, L0.sol, h->coarse_max_it, h->coarse_tol)) return rc;
   }
+  if (ev) cudaEventRecord(ev[2], h->stream);
+  int rc_up = GMG_OK;
   if (g) {
     GMG_CUDA(h, cudaGraphLaunch(g->up, h->stream));
     h->launches += g->n_up;
-    return GMG_OK;
+  } else {
+    rc_up = vcycle_up(h, dst);
   }
-  return vcycle_up(h, dst);
+  if (ev) cudaEventRecord(ev[3], h->stream);
+  return rc_up;
 }
 
 enum { PRECOND_GMG = 0, PRECOND_JACOBI = 1 };
@@ -1257,6 +1269,7 @@ int gmg_create(int device, gmg_handle *out) {
     }
   }
   h->cg_win = !(std::getenv("GMG_CG_WIN") && std::atoi(std::getenv("GMG_CG_WIN")) == 0);
+  if (std::getenv("GMG_PERSISTENT_SSOR")) h->persistent_ssor = std::atoi(std::getenv("GMG_PERSISTENT_SSOR")) != 0;
   h->partials_cap = 1 << 16;
   bool ok = dalloc(&h->partials, 3 * h->partials_cap) == cudaSuccess && dalloc(&h->counter, 4) == cudaSuccess &&
             dalloc(&h->scalars, 1) == cudaSuccess && dalloc(&h->cg_results, h->cg_ring) == cudaSuccess;
@@ -1327,6 +1340,7 @@ int gmg_destroy(gmg_handle h) {
   cudaStreamSynchronize(h->stream);
   for (auto e : h->ev_begin) cudaEventDestroy(e);
   for (auto e : h->ev_end) cudaEventDestroy(e);
+  for (auto e : h->vc_ev) cudaEventDestroy(e);
   for (int i = 0; i < 4; ++i) {
     if (h->pin[i]) cudaFreeHost(h->pin[i]);
     if (h->pin_free[i]) cudaEventDestroy(h->pin_free[i]);
@@ -1637,7 +1651,8 @@ int gmg_setup(gmg_handle h) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ssor_persistent<256>, 256, 0) != cudaSuccess) per_sm = 0;
         h->ssor_blocks_per_sm = std::max(per_sm, 0);
       }
-      L.ssor_grid = std::min(h->sm_count * std::min(h->ssor_blocks_per_sm, 2), std::max(1, cdiv(max_slices, 8)));
+      // eight lanes per row: a block of 256 threads relaxes 32 rows per sweep
+      L.ssor_grid = std::min(h->sm_count * std::min(h->ssor_blocks_per_sm, 4), std::max(1, max_slices));
     }
     if (!L.hP.empty()) {
       TraceScope trp("    P, R");
@@ -1967,6 +1982,30 @@ int gmg_debug_cg_phases(gmg_handle h, int block_plus_1, double out_ns[16]) {
   unsigned long long z[16] = {0};
   GMG_CUDA(h, cudaMemcpyToSymbol(g_cg_phase_ns, z, sizeof(z)));
   h->cg_prof = block_plus_1 > 0 ? block_plus_1 : 0;
+  return GMG_OK;
+}
+
+int gmg_debug_vcycle_profile(gmg_handle h, int enable, double out_ms[4]) {
+  if (!h) return GMG_EINVAL;
+  gmg::enter(h);
+  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  double acc[4] = {0, 0, 0, 0};
+  for (int i = 0; i + 4 <= h->vc_ev_used; i += 4) {
+    for (int k = 0; k < 3; ++k) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, h->vc_ev[i + k], h->vc_ev[i + k + 1]);
+      acc[k] += ms;
+    }
+    acc[3] += 1.0;
+  }
+  if (out_ms)
+    for (int k = 0; k < 4; ++k) out_ms[k] = acc[k];
+  h->vc_ev_used = 0;
+  h->vc_prof = enable != 0;
+  if (h->vc_prof && h->vc_ev.empty()) {
+    h->vc_ev.resize(4 * 256);
+    for (auto &e : h->vc_ev) cudaEventCreate(&e);
+  }
   return GMG_OK;
 }
 

@@ -188,6 +188,9 @@ struct gmg_context {
   int cg_grid_c = 0;     // cooperative grid of the compressed-format CG kernel
   int cg_grid_p = 0;     // cooperative grid of the row-pattern CG kernel
   bool cg_win = true;    // TMA-window variant of the row-pattern CG (pattern_win.cuh); GMG_CG_WIN=0 disables
+  bool vc_prof = false;  // gmg_debug_vcycle_profile: events around down sweep / coarse solve / up sweep
+  std::vector<cudaEvent_t> vc_ev;
+  int vc_ev_used = 0;
   int cg_prof = 0;       // gmg_debug_cg_phases: per-phase timing inside the window kernel
   int cg_win_smem = 0;   // dynamic shared memory the window kernel is currently configured for
   bool is_setup = false;

@@ -341,11 +341,11 @@ __global__ void __launch_bounds__(256) sell_spmv(SellView A, const double *__res
 // share a row: every lane loads its part of the row's entries and operands at once (two memory round trips per row
 // instead of two per four entry pairs), then the FMA chain runs through the eight lanes in entry order, the
 // partial sum handed on by shuffle: same order, same bits as one lane per row.
-__global__ void __launch_bounds__(256) sell_color_relax(SellView Ac, const int *__restrict__ rows, double *u,
-                                                        const double *__restrict__ rhs, const double *__restrict__ dinv,
-                                                        double omega) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int k = t >> 3, sub = t & 7;
+// (k: local row of the colour or out of range; sub: this lane's position among the eight lanes of the row; all
+// 32 lanes of a warp must call it)
+__device__ __forceinline__ void color_relax_row8(const SellView &Ac, const int *__restrict__ rows, double *u,
+                                                 const double *__restrict__ rhs, const double *__restrict__ dinv, double omega,
+                                                 int k, int sub) {
   const bool on = k < Ac.n_rows;
   const int slice = k >> 5, rlane = k & 31;
   int64_t b = 0;
@@ -401,6 +401,13 @@ __global__ void __launch_bounds__(256) sell_color_relax(SellView Ac, const int *
   if (on && sub == 0) u[i] += omega * (rv - acc) * dv;
 }
 
+__global__ void __launch_bounds__(256) sell_color_relax(SellView Ac, const int *__restrict__ rows, double *u,
+                                                        const double *__restrict__ rhs, const double *__restrict__ dinv,
+                                                        double omega) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  color_relax_row8(Ac, rows, u, rhs, dinv, omega, t >> 3, t & 7);
+}
+
 // One smooth() call of the multicolour / level-scheduled SSOR as ONE cooperative launch: colours (or wavefronts)
 // are separated by grid.sync() instead of kernel boundaries -- on the patch levels a colour is a few microseconds
 // of work, so launch gaps dominated (ncu: 896 launches = 19 % of a step before this kernel).
@@ -417,8 +424,6 @@ __global__ void __launch_bounds__(BLOCK) ssor_persistent(const ColorView *__rest
                                                          int zero_start) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
-  const int lane = threadIdx.x & 31;
-  const int gwarp = (blockIdx.x * BLOCK + threadIdx.x) >> 5, nwarps = (gridDim.x * BLOCK) >> 5;
   if (zero_start) {
     for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) u[i] = 0.0;
     grid.sync();
@@ -429,14 +434,10 @@ __global__ void __launch_bounds__(BLOCK) ssor_persistent(const ColorView *__rest
       const int nc = pass == 0 ? n_fwd : n_bwd;
       for (int k = 0; k < nc; ++k) {
         const ColorView &C = set[(pass == 1 && bwd_reversed) ? nc - 1 - k : k];
-        for (int sl = gwarp; sl < C.A.n_slices; sl += nwarps) {
-          const double ax = sell_row_dot<false>(C.A, sl, lane, u);
-          const int r = sl * 32 + lane;
-          if (r < C.A.n_rows) {
-            const int i = C.rows[r];
-            u[i] += omega * (rhs[i] - ax) * dinv[i];
-          }
-        }
+        // eight lanes per row (color_relax_row8); whole warps iterate together
+        const int rows_per_sweep = (gridDim.x * BLOCK) >> 3;
+        for (int r0 = 0; r0 < C.A.n_rows; r0 += rows_per_sweep)
+          color_relax_row8(C.A, C.rows, u, rhs, dinv, omega, r0 + ((blockIdx.x * BLOCK + threadIdx.x) >> 3), threadIdx.x & 7);
         grid.sync();
       }
     }

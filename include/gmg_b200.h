@@ -147,6 +147,10 @@ int gmg_matrix_traffic(gmg_handle h, int which, int level, double out[6]);
  * [12] block barrier, [13] remainder rows.  Returns the counters since the last call, resets them and selects the
  * block (0 switches timing off). */
 int gmg_debug_cg_phases(gmg_handle h, int block_plus_1, double out_ns[16]);
+/* Developer probe: device time (ms, CUDA events) of the three parts of the V-cycles since the last call: out[0] down
+ * sweep (copy_to_mg, pre-smoothing, residuals, restrictions), out[1] coarse solve, out[2] up sweep (prolongations,
+ * post-smoothing, copy_from_mg), out[3] number of V-cycles; resets the counters and switches the timing on/off. */
+int gmg_debug_vcycle_profile(gmg_handle h, int enable, double out_ms[4]);
 /* ... and per block (256 slots each): time in the SpMV, update and direction phases while timing was on. */
 int gmg_debug_cg_blocks(gmg_handle h, double out_ns[768]);
 /* accumulated device time (ms, CUDA events on the handle's stream) and launch count of the
