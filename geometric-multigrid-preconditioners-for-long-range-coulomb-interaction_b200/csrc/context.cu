@@ -900,7 +900,7 @@ static int coarse_cg(gmg_context *h, const Sell &A, const double *b, double *x, 
   }
   if (win) {
   } else if (pat)
-    GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_pat<512>, dim3(h->cg_grid_p), dim3(512), args, 0, h->stream));
+    GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent<512, PatView>, dim3(h->cg_grid_p), dim3(512), args, 0, h->stream));
   else if (comp)
     GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent<512, CsellView>, dim3(h->cg_grid_c), dim3(512), args, 0,
                                             h->stream));
@@ -1286,7 +1286,7 @@ int gmg_create(int device, gmg_handle *out) {
          per_sm_c > 0;
     h->cg_grid_c = h->sm_count * std::max(per_sm_c, 1);
     int per_sm_p = 0;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, cg_persistent_pat<512>, 512, 0) == cudaSuccess &&
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, cg_persistent<512, PatView>, 512, 0) == cudaSuccess &&
          per_sm_p > 0;
     h->cg_grid_p = h->sm_count * std::max(per_sm_p, 1);
     ok = ok && dalloc(&h->cg_partials, 3 * std::max(std::max(h->cg_grid, h->cg_grid_c), h->cg_grid_p)) == cudaSuccess;

@@ -195,9 +195,9 @@ __global__ void __launch_bounds__(BLOCK, 2) cg_persistent_dist(MAT A, const doub
   cg::grid_group grid = cg::this_grid();
   __shared__ double red[32];
   __shared__ double s_bc;
-  __shared__ double sdict[std::is_same<MAT, CsellView>::value ? CSELL_SMEM_DICT : 1];
+  __shared__ RowSmem<MAT> row_smem;
   RowDot<MAT> row_dot;
-  row_dot.init(A, sdict);
+  row_dot.init(A, row_smem);
   const int nb = gridDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int WPB = BLOCK / 32;
@@ -287,11 +287,15 @@ __global__ void __launch_bounds__(BLOCK, 2) cg_persistent_dist(MAT A, const doub
         if (s + WPB < s_end) row_dot.prefetch(A, s + WPB, lane);
         const double ad = row_dot(A, s, lane, d);
         const int r = s * 32 + lane;
-        if (r < A.n_rows) {
+        if (r < A.n_rows && row_dot.valid()) {
           h[r] = ad;
           acc += d[r] * ad;
         }
       }
+      row_dot.remainder(A, blockIdx.x, nb, warp, WPB, d, [&](int r, double ad) {
+        h[r] = ad;
+        acc += d[r] * ad;
+      });
       acc = block_sum(acc, red);
       const double alpha = gh / all_sum(acc);
       if (aborted) { status = 2; break; }

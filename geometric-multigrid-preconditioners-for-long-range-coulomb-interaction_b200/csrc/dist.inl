@@ -184,13 +184,18 @@ static int dist_setup(gmg_context *h) {
   }
   d.n_sys_owned = lmS.n_owned;
   d.n_l0_owned = lmA.n_owned;
-  if (h->compress)
+  // row-pattern format of the rank-local block (columns in [-n_halo_lo, n_owned + halo)), else CSELL, else SELL
+  if (h->compress >= 2)
+    if ((rc = build_pat(h, d.A0.A))) return rc;
+  if (h->compress >= 1 && !d.A0.A.patterned)
     if ((rc = build_csell(h, d.A0.A))) return rc;  // note: offsets into [owned | halo] must fit 16 bits, else plain SELL
   {
     int per_sm = 0;
-    const bool comp = d.A0.A.compressed && h->compress;
-    cudaError_t e = comp ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_dist<512, CsellView>, 512, 0)
-                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_dist<512, SellView>, 512, 0);
+    const bool pat = d.A0.A.patterned && h->compress >= 2;
+    const bool comp = !pat && d.A0.A.compressed && h->compress;
+    cudaError_t e = pat    ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_dist<512, PatView>, 512, 0)
+                    : comp ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_dist<512, CsellView>, 512, 0)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_dist<512, SellView>, 512, 0);
     if (e != cudaSuccess || per_sm < 1) return fail(h, GMG_ECUDA, "occupancy query of the distributed CG kernel failed");
     d.cg_grid = h->sm_count * per_sm;
   }
@@ -333,7 +338,9 @@ static int dist_coarse_cg(gmg_context *h, const double *b, double *x) {
   CgResult *res = h->cg_results + slot;
   SellView v = d.A0.A.v;
   CsellView cv = d.A0.A.cv;
-  const bool comp = d.A0.A.compressed && h->compress;
+  PatView pv = d.A0.A.pv;
+  const bool pat = d.A0.A.patterned && h->compress >= 2;
+  const bool comp = !pat && d.A0.A.compressed && h->compress;
   DistCgArgs D;
   D.P = peers_of(h);
   D.n_owned = d.A0.n_owned;
@@ -351,14 +358,17 @@ static int dist_coarse_cg(gmg_context *h, const double *b, double *x) {
   int max_it = h->coarse_max_it;
   double tol = h->coarse_tol;
   int grid = d.cg_grid;
-  void *args[] = {comp ? (void *)&cv : (void *)&v, (void *)&b, &x, &d.cg_g, &d.cg_h, &d.cg_partials, &max_it, &tol, &res, &D,
-                  &d.d_error};
+  void *args[] = {pat ? (void *)&pv : comp ? (void *)&cv : (void *)&v, (void *)&b, &x, &d.cg_g, &d.cg_h, &d.cg_partials, &max_it,
+                  &tol, &res, &D, &d.d_error};
   int ev = -1;
   if (h->ev_used < (int)h->ev_begin.size()) {
     ev = h->ev_used++;
     cudaEventRecord(h->ev_begin[ev], h->stream);
   }
-  if (comp)
+  if (pat)
+    GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_dist<512, PatView>, dim3(grid), dim3(512), args, 0,
+                                            h->stream));
+  else if (comp)
     GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_dist<512, CsellView>, dim3(grid), dim3(512), args, 0,
                                             h->stream));
   else

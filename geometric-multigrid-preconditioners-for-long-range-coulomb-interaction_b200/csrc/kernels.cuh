@@ -565,32 +565,49 @@ __device__ __forceinline__ double grid_total(const double *partials, int nblocks
 
 constexpr int CSELL_SMEM_DICT = 2048;  // dictionary entries staged in shared memory (16 KB)
 
+// Row kernels of the persistent CG kernels, per matrix format.  init() stages what the format keeps in shared memory;
+// operator() is sum_j a_rj x_j of row (slice, lane); valid() tells whether that row belongs to the slice pass at all
+// (the row-pattern format handles its rare rows in remainder()).
+template <class MAT>
+struct RowSmem {
+  double unused[1];
+};
+template <>
+struct RowSmem<CsellView> {
+  double dict[CSELL_SMEM_DICT];
+};
 template <class MAT>
 struct RowDot;
 template <>
 struct RowDot<SellView> {
-  __device__ __forceinline__ void init(const SellView &, double *) {}
+  __device__ __forceinline__ void init(const SellView &, RowSmem<SellView> &) {}
   __device__ __forceinline__ void prefetch(const SellView &, int, int) const {}
-  __device__ __forceinline__ double operator()(const SellView &A, int s, int lane, const double *x) const {
+  __device__ __forceinline__ double operator()(const SellView &A, int s, int lane, const double *x) {
     return sell_row_dot<false>(A, s, lane, x);
   }
+  __device__ __forceinline__ bool valid() const { return true; }
+  template <class F>
+  __device__ __forceinline__ void remainder(const SellView &, int, int, int, int, const double *, F &&) const {}
 };
 template <>
 struct RowDot<CsellView> {
   const double *dict;
-  __device__ __forceinline__ void init(const CsellView &A, double *sdict) {
+  __device__ __forceinline__ void init(const CsellView &A, RowSmem<CsellView> &sm) {
     if (A.dict_n <= CSELL_SMEM_DICT) {
-      for (int i = threadIdx.x; i < A.dict_n; i += blockDim.x) sdict[i] = A.dict[i];
+      for (int i = threadIdx.x; i < A.dict_n; i += blockDim.x) sm.dict[i] = A.dict[i];
       __syncthreads();
-      dict = sdict;
+      dict = sm.dict;
     } else {
       dict = A.dict;
     }
   }
   __device__ __forceinline__ void prefetch(const CsellView &A, int s, int lane) const { csell_prefetch_slice(A, s, lane); }
-  __device__ __forceinline__ double operator()(const CsellView &A, int s, int lane, const double *x) const {
+  __device__ __forceinline__ double operator()(const CsellView &A, int s, int lane, const double *x) {
     return csell_row_dot<false>(A, s, lane, x, dict);
   }
+  __device__ __forceinline__ bool valid() const { return true; }
+  template <class F>
+  __device__ __forceinline__ void remainder(const CsellView &, int, int, int, int, const double *, F &&) const {}
 };
 
 template <int BLOCK, class MAT>
@@ -601,9 +618,9 @@ __global__ void __launch_bounds__(BLOCK, 2) cg_persistent(MAT A, const double *_
   cg::grid_group grid = cg::this_grid();
   __shared__ double red[32];
   __shared__ double bc;
-  __shared__ double sdict[std::is_same<MAT, CsellView>::value ? CSELL_SMEM_DICT : 1];
+  __shared__ RowSmem<MAT> row_smem;
   RowDot<MAT> row_dot;
-  row_dot.init(A, sdict);
+  row_dot.init(A, row_smem);
   const int nb = gridDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int WPB = BLOCK / 32;
@@ -641,11 +658,15 @@ __global__ void __launch_bounds__(BLOCK, 2) cg_persistent(MAT A, const double *_
         if (s + WPB < s_end) row_dot.prefetch(A, s + WPB, lane);
         const double ad = row_dot(A, s, lane, d);
         const int r = s * 32 + lane;
-        if (r < A.n_rows) {
+        if (r < A.n_rows && row_dot.valid()) {
           h[r] = ad;
           acc += d[r] * ad;
         }
       }
+      row_dot.remainder(A, blockIdx.x, nb, warp, WPB, d, [&](int r, double ad) {
+        h[r] = ad;
+        acc += d[r] * ad;
+      });
       acc = block_sum(acc, red);
       if (threadIdx.x == 0) pa[blockIdx.x] = acc;
       grid.sync();

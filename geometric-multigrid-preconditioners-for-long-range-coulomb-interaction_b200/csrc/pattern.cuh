@@ -326,117 +326,42 @@ __global__ void __launch_bounds__(512) pat_spmv(PatView A, const double *__restr
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Persistent cooperative CG on a row-pattern matrix: same recurrences, same reduction order and the same three
-// grid barriers per iteration as cg_persistent (kernels.cuh); the matrix stream is 4 bytes per row, so the vectors
-// stay L2-resident.  Pattern ids of the next slice are loaded while the current one is processed.
-// ------------------------------------------------------------------------------------------------
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 2) cg_persistent_pat(PatView A, const double *__restrict__ b, double *x, double *g,
-                                                              double *d, double *h, double *partials /* 3 * gridDim.x */,
-                                                              int max_it, double tol, CgResult *result) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
-  __shared__ double red[32];
-  __shared__ double bc;
-  __shared__ PatSmem sm;
-  const PatTable T = pat_stage(A, sm);
-  const uint32_t empty = (uint32_t)(A.n_pat - 1);
-  const int nb = gridDim.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int WPB = BLOCK / 32;
-  const int s_begin = (int)(((int64_t)A.n_slices * blockIdx.x) / nb);
-  const int s_end = (int)(((int64_t)A.n_slices * (blockIdx.x + 1)) / nb);
-  const int q_begin = (int)(((int64_t)A.rem.n_slices * blockIdx.x) / nb);
-  const int q_end = (int)(((int64_t)A.rem.n_slices * (blockIdx.x + 1)) / nb);
-  double *pa = partials, *pb = partials + nb, *pc = partials + 2 * nb;
-
-  double acc = 0.0;
-  for (int s = s_begin + warp; s < s_end; s += WPB) {
+// Row kernel of the persistent CG kernels (kernels.cuh: cg_persistent, dist.cuh: cg_persistent_dist) for the
+// row-pattern format with L1 gathers: the pattern table in shared memory, the rare rows through the remainder SELL
+// matrix (each block takes a contiguous share of its slices).
+template <>
+struct RowSmem<PatView> {
+  PatSmem p;
+};
+template <>
+struct RowDot<PatView> {
+  PatTable T;
+  uint32_t empty;
+  bool ok;
+  __device__ __forceinline__ void init(const PatView &A, RowSmem<PatView> &sm) {
+    T = pat_stage(A, sm.p);
+    empty = (uint32_t)(A.n_pat - 1);
+    ok = false;
+  }
+  __device__ __forceinline__ void prefetch(const PatView &, int, int) const {}
+  __device__ __forceinline__ double operator()(const PatView &A, int s, int lane, const double *x) {
     const int r = s * 32 + lane;
-    if (r < A.n_rows) {
-      const double bv = b[r];
-      x[r] = 0.0;
-      g[r] = -bv;
-      d[r] = bv;
-      acc += bv * bv;
+    const uint32_t pid = __ldg(A.pat + r) & PAT_ID_MASK;
+    ok = pid != empty;
+    return pat_row_dot<false>(T, pid, x + r);
+  }
+  __device__ __forceinline__ bool valid() const { return ok; }
+  template <class F>
+  __device__ __forceinline__ void remainder(const PatView &A, int block, int nb, int warp, int wpb, const double *x, F &&f) const {
+    const int lane = threadIdx.x & 31;
+    const int q_begin = (int)(((int64_t)A.rem.n_slices * block) / nb);
+    const int q_end = (int)(((int64_t)A.rem.n_slices * (block + 1)) / nb);
+    for (int q = q_begin + warp; q < q_end; q += wpb) {
+      const double ad = sell_row_dot<false>(A.rem, q, lane, x);
+      const int k = q * 32 + lane;
+      if (k < A.rem.n_rows) f(A.rem_rows[k], ad);
     }
   }
-  acc = block_sum(acc, red);
-  if (threadIdx.x == 0) pc[blockIdx.x] = acc;
-  grid.sync();
-  double res2 = grid_total(pc, nb, &bc);
-  double res = sqrt(res2);
-  const double res0 = res;
-  int it = 0, status = 0;
-  if (res > tol) {
-    double gh = res * res;
-    while (true) {
-      ++it;
-      // h = A d ; dh = d.h
-      acc = 0.0;
-      {
-        int s = s_begin + warp;
-        uint32_t pid = (s < s_end) ? (__ldg(A.pat + s * 32 + lane) & PAT_ID_MASK) : empty;
-        for (; s < s_end; s += WPB) {
-          const uint32_t pid_next = (s + WPB < s_end) ? (__ldg(A.pat + (s + WPB) * 32 + lane) & PAT_ID_MASK) : empty;
-          const int r = s * 32 + lane;
-          const double ad = pat_row_dot<false>(T, pid, d + r);
-          if (pid != empty) {
-            h[r] = ad;
-            acc += d[r] * ad;
-          }
-          pid = pid_next;
-        }
-        // rows whose pattern is not in the table
-        for (int q = q_begin + warp; q < q_end; q += WPB) {
-          const double ad = sell_row_dot<false>(A.rem, q, lane, d);
-          const int k = q * 32 + lane;
-          if (k < A.rem.n_rows) {
-            const int r = A.rem_rows[k];
-            h[r] = ad;
-            acc += d[r] * ad;
-          }
-        }
-      }
-      acc = block_sum(acc, red);
-      if (threadIdx.x == 0) pa[blockIdx.x] = acc;
-      grid.sync();
-      const double alpha = gh / grid_total(pa, nb, &bc);
-      // x += alpha d ; g += alpha h ; res2 = g.g
-      acc = 0.0;
-      for (int s = s_begin + warp; s < s_end; s += WPB) {
-        const int r = s * 32 + lane;
-        if (r < A.n_rows) {
-          x[r] += alpha * d[r];
-          const double gv = g[r] + alpha * h[r];
-          g[r] = gv;
-          acc += gv * gv;
-        }
-      }
-      acc = block_sum(acc, red);
-      if (threadIdx.x == 0) pb[blockIdx.x] = acc;
-      grid.sync();
-      res2 = grid_total(pb, nb, &bc);
-      res = sqrt(res2);
-      if (res <= tol) break;
-      if (it >= max_it) { status = 1; break; }
-      const double beta = res2 / gh;
-      gh = res2;
-      // d = beta d - g
-      for (int s = s_begin + warp; s < s_end; s += WPB) {
-        const int r = s * 32 + lane;
-        if (r < A.n_rows) d[r] = beta * d[r] - g[r];
-      }
-      grid.sync();
-    }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    result->iterations = it;
-    result->status = status;
-    result->res0 = res0;
-    result->res = res;
-  }
-}
+};
 
 }  // namespace gmg
