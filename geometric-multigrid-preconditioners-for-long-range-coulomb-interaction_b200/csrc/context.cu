@@ -115,7 +115,8 @@ int ensure_stage(gmg_context *h, int64_t n) {
 // threads (one memcpy thread tops out near 10 GB/s) while the previous chunk is in flight on the copy engine.
 int staged_h2d(gmg_context *h, void *dst, const void *src, size_t bytes) {
   constexpr size_t CHUNK = 32u << 20;
-  constexpr int NBUF = 4, NTHREADS = 6;
+  constexpr int NBUF = 4, MAXT = 32;
+  const int NTHREADS = std::min(std::max(h->stage_threads, 1), MAXT);
   if (bytes < (8u << 20)) {
     GMG_CUDA(h, copy(h, dst, src, bytes, cudaMemcpyHostToDevice));
     return GMG_OK;
@@ -136,7 +137,7 @@ int staged_h2d(gmg_context *h, void *dst, const void *src, size_t bytes) {
     {
       const char *s = (const char *)src + off;
       char *d = h->pin[buf];
-      std::thread th[NTHREADS];
+      std::thread th[MAXT];
       const size_t part = (n + NTHREADS - 1) / NTHREADS;
       for (int t = 0; t < NTHREADS; ++t) {
         const size_t a = std::min(n, part * t), b = std::min(n, part * (t + 1));
@@ -144,7 +145,7 @@ int staged_h2d(gmg_context *h, void *dst, const void *src, size_t bytes) {
           if (b > a) std::memcpy(d + a, s + a, b - a);
         });
       }
-      for (auto &t : th) t.join();
+      for (int t = 0; t < NTHREADS; ++t) th[t].join();
     }
     GMG_CUDA(h, cudaMemcpyAsync((char *)dst + off, h->pin[buf], n, cudaMemcpyHostToDevice, h->stream));
     GMG_CUDA(h, cudaEventRecord(h->pin_free[buf], h->stream));
@@ -158,7 +159,8 @@ int staged_h2d(gmg_context *h, void *dst, const void *src, size_t bytes) {
 // chunk is in flight.  Synchronous (the destination is complete on return).
 int staged_d2h(gmg_context *h, void *dst, const void *src, size_t bytes) {
   constexpr size_t CHUNK = 32u << 20;
-  constexpr int NBUF = 4, NTHREADS = 6;
+  constexpr int NBUF = 4, MAXT = 32;
+  const int NTHREADS = std::min(std::max(h->stage_threads, 1), MAXT);
   if (bytes < (8u << 20) || !h->pin[0]) {
     GMG_CUDA(h, copy_sync(h, dst, src, bytes, cudaMemcpyDeviceToHost));
     return GMG_OK;
@@ -178,7 +180,7 @@ int staged_d2h(gmg_context *h, void *dst, const void *src, size_t bytes) {
     const size_t off = (size_t)c * CHUNK, n = std::min(CHUNK, bytes - off);
     const char *s = h->pin[c % NBUF];
     char *d = (char *)dst + off;
-    std::thread th[NTHREADS];
+    std::thread th[MAXT];
     const size_t part = (n + NTHREADS - 1) / NTHREADS;
     for (int t = 0; t < NTHREADS; ++t) {
       const size_t a = std::min(n, part * t), b = std::min(n, part * (t + 1));
@@ -186,7 +188,7 @@ int staged_d2h(gmg_context *h, void *dst, const void *src, size_t bytes) {
         if (b > a) std::memcpy(d + a, s + a, b - a);
       });
     }
-    for (auto &t : th) t.join();
+    for (int t = 0; t < NTHREADS; ++t) th[t].join();
   }
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return GMG_OK;
@@ -470,6 +472,7 @@ static int build_pat(gmg_context *h, Sell &s) {
   int count = 0;
   GMG_CUDA(h, copy_sync(h, &count, d_count, sizeof(int), cudaMemcpyDeviceToHost));
   if (count > LIMIT) {
+    if (std::getenv("GMG_TRACE")) std::fprintf(stderr, "[gmg trace]     row patterns: more than %d distinct rows, not used\n", LIMIT);
     cleanup();
     return GMG_OK;
   }
@@ -513,6 +516,9 @@ static int build_pat(gmg_context *h, Sell &s) {
   }
   const int np = (int)h_pid_rep.size();
   if (covered * 4 < (int64_t)n * 3) {
+    if (std::getenv("GMG_TRACE"))
+      std::fprintf(stderr, "[gmg trace]     row patterns: %d distinct rows, the table covers only %lld of %d rows, not used\n", count,
+                   (long long)covered, n);
     cleanup();
     return GMG_OK;
   }
@@ -1267,6 +1273,11 @@ int gmg_create(int device, gmg_handle *out) {
       uint64_t keep = UINT64_MAX;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
+  }
+  {  // host threads that fill / drain the pinned staging ring (one memcpy thread tops out near 10 GB/s)
+    const unsigned hw = std::thread::hardware_concurrency();
+    h->stage_threads = std::getenv("GMG_STAGE_THREADS") ? std::atoi(std::getenv("GMG_STAGE_THREADS"))
+                                                        : (int)std::min(12u, std::max(4u, hw * 3 / 4));
   }
   h->cg_win = !(std::getenv("GMG_CG_WIN") && std::atoi(std::getenv("GMG_CG_WIN")) == 0);
   if (std::getenv("GMG_PERSISTENT_SSOR")) h->persistent_ssor = std::atoi(std::getenv("GMG_PERSISTENT_SSOR")) != 0;

@@ -226,6 +226,7 @@ struct gmg_context {
   char *pin[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t pin_free[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t pin_bytes = 0;
+  int stage_threads = 6;
   // CUDA graphs of the fine-level parts of the V-cycle (down sweep / up sweep), keyed by (src, dst)
   struct VcGraph {
     const double *src = nullptr;
