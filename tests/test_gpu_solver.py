@@ -263,3 +263,54 @@ def test_step16_uniform_hierarchy_jacobi(capi, goldens):
     assert r["its"] == gold["its"] == 8
     assert abs(r["res"] - gold["conv"]) <= 1e-3 * gold["conv"]
     assert abs(np.linalg.norm(r["x"]) - gold["sol_l2"]) < 1e-4
+
+
+def _chain_matrix(n, period, eliminated):
+    """1D Laplacian chains (-1, 2, -1).  eliminated=True: every `period`-th row is an eliminated Dirichlet row (identity,
+    the neighbours' couplings to it are dropped) -- the FE situation, the zeroed-operand set of pattern_win.cuh is
+    conflict-free.  eliminated=False: the coupling between rows i-1 and i is cut instead, so the column a shortened row
+    skips IS needed by its other neighbour: the conflict case (only exact dominant rows may use the windows)."""
+    import scipy.sparse as sp
+    main = np.full(n, 2.0)
+    lo = np.full(n - 1, -1.0)   # entry (i+1, i)
+    cut = np.arange(period, n - 1, period)
+    if eliminated:
+        lo[cut - 1] = 0.0       # (i, i-1)
+        lo[cut] = 0.0           # (i+1, i)
+        main[cut] = 1.0
+    else:
+        lo[cut - 1] = 0.0
+    A = sp.diags([lo, main, lo], [-1, 0, 1], format="csr")
+    A.eliminate_zeros()
+    return A
+
+
+@pytest.mark.parametrize("eliminated", [True, False])
+@pytest.mark.parametrize("windows", ["1", "0"])
+def test_row_pattern_cg_on_chains_with_shortened_rows(capi, eliminated, windows, monkeypatch):
+    """The row-pattern coarse CG (TMA-window kernel and its L1-gather fallback) on matrices whose shortened rows are
+    sub-sequences of the dominant row: same iteration count and solution as the plain format, with a right-hand side
+    that is NOT zero on the eliminated rows (their operand entries live in the side vector of the window kernel)."""
+    import scipy.sparse.linalg as spla
+    monkeypatch.setenv("GMG_CG_WIN", windows)
+    n = 150001
+    A = _chain_matrix(n, 97, eliminated)
+    rng = np.random.default_rng(2)
+    b = rng.standard_normal(n)
+    out = {}
+    for mode in (0, 2):
+        g = capi.Gmg()
+        g.set_compression(mode)
+        g.set_num_levels(1)
+        g.set_matrix(capi.GMG_SYSTEM, 0, A)
+        g.set_matrix(capi.GMG_LEVEL, 0, A)
+        g.set_copy_indices(0, np.arange(n), np.arange(n))
+        g.setup()
+        assert g.matrix_traffic(capi.GMG_LEVEL, 0)["format"] == mode
+        out[mode] = g.cg_solve(capi.GMG_LEVEL, 0, b, 1000, 1e-10)
+        y = g.spmv(capi.GMG_LEVEL, 0, b, n)
+        assert np.array_equal(y, out.setdefault("y", y))  # the SpMV is bit-identical across the formats
+        g.close()
+    assert out[0][1] == out[2][1]
+    assert rel_l2(out[2][0], out[0][0]) < 1e-11
+    assert rel_l2(out[2][0], spla.spsolve(A.tocsc(), b)) < 1e-8
