@@ -957,6 +957,26 @@ static int smooth(gmg_context *h, Level &L, double *&u, const double *rhs, bool 
   if (h->smoother == GMG_SMOOTHER_MC_SSOR || h->smoother == GMG_SMOOTHER_LEX_SSOR) {
     // a relaxation sweep applied to (u, rhs) equals u + sweep(0, rhs - A u): no residual needed
     const bool lex = h->smoother == GMG_SMOOTHER_LEX_SSOR;
+    if (h->cluster_ssor && L.d_fwd && L.cluster_blocks > 0) {
+      // small level: the whole smooth() call in one thread-block cluster (cluster barrier between the colours)
+      const ColorView *fw = (const ColorView *)L.d_fwd, *bw = (const ColorView *)L.d_bwd;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(L.cluster_blocks);
+      cfg.blockDim = dim3(1024);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = h->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = L.cluster_blocks;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      GMG_CUDA(h, cudaLaunchKernelEx(&cfg, ssor_cluster<1024>, fw, L.n_fwd, bw, L.n_bwd, lex ? 0 : 1, n, u, rhs,
+                                     (const double *)L.dinv, h->omega, h->steps, zero_start ? 1 : 0));
+      h->launches++;
+      return GMG_OK;
+    }
     if (h->persistent_ssor && L.d_fwd && L.ssor_grid > 0) {
       const ColorView *fw = (const ColorView *)L.d_fwd, *bw = (const ColorView *)L.d_bwd;
       int n_fwd = L.n_fwd, n_bwd = L.n_bwd, rev = lex ? 0 : 1, nn = n, steps = h->steps, zs = zero_start ? 1 : 0;
@@ -1280,6 +1300,7 @@ int gmg_create(int device, gmg_handle *out) {
                                                         : (int)std::min(12u, std::max(4u, hw * 3 / 4));
   }
   h->cg_win = !(std::getenv("GMG_CG_WIN") && std::atoi(std::getenv("GMG_CG_WIN")) == 0);
+  if (std::getenv("GMG_CLUSTER_SSOR")) h->cluster_ssor = std::atoi(std::getenv("GMG_CLUSTER_SSOR")) != 0;
   if (std::getenv("GMG_PERSISTENT_SSOR")) h->persistent_ssor = std::atoi(std::getenv("GMG_PERSISTENT_SSOR")) != 0;
   h->partials_cap = 1 << 16;
   bool ok = dalloc(&h->partials, 3 * h->partials_cap) == cudaSuccess && dalloc(&h->counter, 4) == cudaSuccess &&
@@ -1632,7 +1653,7 @@ int gmg_setup(gmg_handle h) {
     free_csr(L.rawA);
     dfree(L.d_fwd);
     dfree(L.d_bwd);
-    L.n_fwd = L.n_bwd = L.ssor_grid = 0;
+    L.n_fwd = L.n_bwd = L.ssor_grid = L.cluster_blocks = 0;
     if (l >= 1 && (h->smoother == GMG_SMOOTHER_MC_SSOR || h->smoother == GMG_SMOOTHER_LEX_SSOR)) {
       const bool lex = h->smoother == GMG_SMOOTHER_LEX_SSOR;
       auto &fw = lex ? L.wave_fwd : L.colors;
@@ -1662,6 +1683,8 @@ int gmg_setup(gmg_handle h) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ssor_persistent<256>, 256, 0) != cudaSuccess) per_sm = 0;
         h->ssor_blocks_per_sm = std::max(per_sm, 0);
       }
+      // small levels: one cluster of <= 8 blocks x 1024 threads (128 rows per block and pass), at most 4 passes per colour
+      L.cluster_blocks = (max_slices * 32 <= 4096) ? std::min(8, std::max(1, cdiv(max_slices * 32, 128))) : 0;
       // eight lanes per row: a block of 256 threads relaxes 32 rows per sweep
       L.ssor_grid = std::min(h->sm_count * std::min(h->ssor_blocks_per_sm, 4), std::max(1, max_slices));
     }

@@ -86,6 +86,7 @@ struct Level {
   std::vector<ColorSet> wave_fwd, wave_bwd;  // level-scheduled lexicographic SSOR
   void *d_fwd = nullptr, *d_bwd = nullptr;   // device arrays of ColorView for the persistent SSOR kernel
   int n_fwd = 0, n_bwd = 0, ssor_grid = 0;
+  int cluster_blocks = 0;            // > 0: small level, smooth() as one thread-block cluster of this many blocks
   double lambda_max = 0.0;           // Chebyshev
   std::vector<int32_t> user_color;   // optional colouring handed over by the host (gmg_set_level_coloring)
 };
@@ -236,6 +237,9 @@ struct gmg_context {
   };
   std::vector<VcGraph> vc_graphs;
   bool use_graphs = true;
+  bool cluster_ssor = false;     // small levels: one cluster launch per smooth() (GMG_CLUSTER_SSOR=1); measured slower than
+                                 // graph-replayed launches (level 2 of the 64k case: +2.8 ms per step): the colours' dependent
+                                 // L2 round trips serialise on 8 SMs
   bool persistent_ssor = false;  // measured slower than graph-replayed per-colour launches (60.4 vs 54.0 ms/step)
   int ssor_blocks_per_sm = 0;
 };

@@ -443,6 +443,36 @@ __global__ void __launch_bounds__(BLOCK) ssor_persistent(const ColorView *__rest
     }
 }
 
+// The same smooth() call for SMALL levels (a few thousand rows per colour) as ONE thread-block cluster: the colours
+// are separated by the hardware cluster barrier (~0.3 us) instead of kernel boundaries (~3 us in a CUDA graph) or
+// grid.sync() (~2 us).  The barrier's acquire at cluster scope invalidates the L1s, so the plain loads of u see
+// the other blocks' updates.  Launched with cluster dimension = grid dimension (<= 8 blocks).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) ssor_cluster(const ColorView *__restrict__ fwd, int n_fwd,
+                                                      const ColorView *__restrict__ bwd, int n_bwd, int bwd_reversed, int n,
+                                                      double *u, const double *__restrict__ rhs,
+                                                      const double *__restrict__ dinv, double omega, int steps, int zero_start) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int nthreads = (int)cluster.num_blocks() * BLOCK;
+  const int tid = (int)cluster.block_rank() * BLOCK + threadIdx.x;
+  if (zero_start) {
+    for (int i = tid; i < n; i += nthreads) u[i] = 0.0;
+    cluster.sync();
+  }
+  for (int s = 0; s < steps; ++s)
+    for (int pass = 0; pass < 2; ++pass) {
+      const ColorView *set = pass == 0 ? fwd : bwd;
+      const int nc = pass == 0 ? n_fwd : n_bwd;
+      for (int k = 0; k < nc; ++k) {
+        const ColorView &C = set[(pass == 1 && bwd_reversed) ? nc - 1 - k : k];
+        for (int r0 = 0; r0 < C.A.n_rows; r0 += nthreads >> 3)
+          color_relax_row8(C.A, C.rows, u, rhs, dinv, omega, r0 + (tid >> 3), threadIdx.x & 7);
+        cluster.sync();
+      }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // vector kernels
 // ------------------------------------------------------------------------------------------------
