@@ -285,6 +285,18 @@ def run_b200(args):
     msv, _, _, pv = timed(lambda: g.vcycle_dev(src, dst), 10)
     line["config"]["v_cycle_ms"] = msv / 10
     line["config"]["v_cycle_inner_iterations"] = pv["iterations"] / max(pv["launches"], 1)
+    # the one kernel of the step that still streams a matrix from HBM: the system-matrix SpMV of the outer PCG
+    # (SELL, 12 B per entry; the refined mesh makes its rows too irregular for the row-pattern format)
+    if world == 1:
+        trs = g.matrix_traffic(P.capi.GMG_SYSTEM, 0)
+        ms_s, _, _, _ = timed(lambda: g.spmv_dev(P.capi.GMG_SYSTEM, 0, src, dst), 20)
+        gbs = trs["spmv_bytes"] * 20 / (ms_s * 1e-3) / 1e9
+        line["roofline_level_spmv"] = {
+            "bound": "hbm", "kernel": "gmg::sell_spmv<0, 0> (system matrix, %d rows, %d stored entries, SELL-32)" % (
+                B.n_dofs, int(trs["nnz"])),
+            "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes_per_launch": trs["spmv_bytes"],
+            "avg_launch_ms": ms_s / 20, "format": trs.get("format", 0),
+            "note": "20 back-to-back launches; the 600 MB matrix exceeds the 126 MB L2, x and y (15 MB each) stay in it"}
     g.vec_free(src)
     g.vec_free(dst)
 
