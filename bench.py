@@ -251,9 +251,10 @@ def run_b200(args):
                           "bytes_per_inner_iteration": stored_bytes, "achieved_gbs": stored_bytes * per_s,
                           "frac_of_hbm_peak": stored_bytes * per_s / (peak * peak_scale)},
         "note": ("achieved = CSR-equivalent algorithmic bytes / time (SURVEY 8d).  With the row-pattern format the matrix is not "
-                 "streamed at all and the CG's four vectors (57 MB) stay in the 126 MB L2: frac > 1 means the kernel has left the HBM "
+                 "streamed at all and the CG's four vectors (%d MB) %s the 126 MB L2: frac > 1 means the kernel has left the HBM "
                  "roofline; it is bound by shared-memory/L1 wavefronts, L2 bandwidth (vector updates at ~10 TB/s) and three grid "
-                 "barriers per iteration (profiles/)") if fmt == 2 and world == 1 else None,
+                 "barriers per iteration (profiles/)" % (4 * 8 * B.level_n[0] // 10 ** 6, "stay in" if 4 * 8 * B.level_n[0] < 100e6
+                                                          else "no longer fit")) if fmt == 2 and world == 1 else None,
         "inner_iterations_per_launch": prof["iterations"] / max(prof["launches"], 1),
         "launches_in_timed_region": prof["launches"], "avg_launch_ms": prof["ms"] / max(prof["launches"], 1),
         "share_of_step": prof["ms"] / ms if ms > 0 else None,
@@ -296,7 +297,8 @@ def run_b200(args):
                 B.n_dofs, int(trs["nnz"])),
             "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes_per_launch": trs["spmv_bytes"],
             "avg_launch_ms": ms_s / 20, "format": trs.get("format", 0),
-            "note": "20 back-to-back launches; the 600 MB matrix exceeds the 126 MB L2, x and y (15 MB each) stay in it"}
+            "note": "20 back-to-back launches; the matrix (%d MB) exceeds the 126 MB L2, x and y stay in it" % (
+                trs["spmv_bytes"] // 10 ** 6)}
     g.vec_free(src)
     g.vec_free(dst)
 
