@@ -236,10 +236,14 @@ def run_b200(args):
     achieved = cg_bytes * per_s
     tr = profile_traffic()
     fmt = traffic.get("format", 0)
-    kernel = {2: "gmg::cg_persistent_win<2> (coarse-level CG on the row-pattern matrix, TMA-filled shared-memory windows; one "
+    kernel = {4: "gmg::cg_persistent_win<2> (coarse-level CG on the row-pattern matrix, TMA-filled shared-memory windows, row "
+                 "codes in global memory; one cooperative launch per V-cycle)",
+              3: "gmg::cg_persistent_win<2> (coarse-level CG on the row-pattern matrix, TMA-filled shared-memory windows; one "
                  "cooperative launch per V-cycle)",
+              2: "gmg::cg_persistent<512, PatView> (coarse-level CG on the row-pattern matrix, L1 gathers)",
               1: "gmg::cg_persistent<512, CsellView> (coarse-level CG, one cooperative launch per V-cycle)",
-              0: "gmg::cg_persistent<512, SellView> (coarse-level CG, one cooperative launch per V-cycle)"}[fmt]
+              0: "gmg::cg_persistent<512, SellView> (coarse-level CG, one cooperative launch per V-cycle)"}[
+        g.coarse_kernel(P.capi.GMG_LEVEL, 0)]
     if world > 1:
         kernel = "gmg::cg_persistent_dist<512> (distributed coarse-level CG, halo + all-reduce over peer memory inside the kernel)"
     roofline = {

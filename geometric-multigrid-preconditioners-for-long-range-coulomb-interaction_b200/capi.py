@@ -67,6 +67,7 @@ SIGNATURES = {
                                  C.POINTER(C.c_float)]),
     "gmg_debug_cg_phases": (_i, [_h, _i, _pd]),
     "gmg_debug_cg_blocks": (_i, [_h, _pd]),
+    "gmg_coarse_kernel": (_i, [_h, _i, _i, C.POINTER(_i)]),
     "gmg_debug_vcycle_profile": (_i, [_h, _i, _pd]),
     "gmg_coarse_profile": (_i, [_h, _i, _pd, _pi64, _pi64]),
     "gmg_launch_count": (_i64, [_h]),
@@ -329,6 +330,11 @@ class Gmg:
         out = np.zeros(4)
         self._ck(self.lib.gmg_debug_vcycle_profile(self.h, int(enable), _pd_of(out)))
         return dict(down_ms=out[0], coarse_ms=out[1], up_ms=out[2], vcycles=int(out[3]))
+
+    def coarse_kernel(self, which, level=0):
+        k = _i(0)
+        self._ck(self.lib.gmg_coarse_kernel(self.h, which, level, C.byref(k)))
+        return k.value
 
     def debug_cg_blocks(self):
         out = np.zeros(768)

@@ -49,6 +49,7 @@ static void free_sell(Sell &s) {
   dfree(s.rem_ccol);
   dfree(s.rem_cval);
   dfree(s.dom_mask);
+  dfree(s.row_code);
   s = Sell{};
 }
 static void free_csr(DevCsr &c) {
@@ -455,6 +456,7 @@ static int build_pat(gmg_context *h, Sell &s) {
     dfree(s.rem_ccol);
     dfree(s.rem_cval);
     dfree(s.dom_mask);
+    dfree(s.row_code);
   };
   GMG_CUDA(h, arena_alloc(h->scratch, &hash, n));
   GMG_CUDA(h, arena_alloc(h->scratch, &keys, (int64_t)mask + 1));
@@ -644,6 +646,10 @@ static int build_pat(gmg_context *h, Sell &s) {
       }
       GMG_CUDA(h, cudaStreamSynchronize(h->stream));
           if (std::getenv("GMG_TRACE")) std::fprintf(stderr, "[gmg trace]     zeroed-operand set: %s\n", hc ? "conflict (exact rows only)" : "ok");
+      GMG_CUDA(h, dalloc(&s.row_code, n_padded));
+      pat_row_codes<<<cdiv(n_padded, 256), 256, 0, h->stream>>>(s.pv, s.dom_mask, s.row_code);
+      GMG_LAUNCH_CHECK(h);
+      GMG_CUDA(h, cudaStreamSynchronize(h->stream));
     } else {
       s.dom.len = 0;
     }
@@ -866,6 +872,20 @@ static int spmv(gmg_context *h, const Sell &A, const double *x, double *y, const
 
 static int reduce_grid(gmg_context *h, int n) { return std::min(std::max(cdiv(n, 256 * 4), 1), h->sm_count * 4); }
 
+// Can the TMA-window kernel (pattern_win.cuh) run on A?  Shared-memory layout: the block's row codes go to shared
+// memory when they fit next to the windows and the table, else they are read from global memory.
+static bool window_plan(gmg_context *h, const Sell &A, int &rows_per_block, WinLayout &lay) {
+  if (!(A.patterned && h->compress >= 2 && A.dom.len > 0 && h->cg_win && A.pv.n_pat <= (int)RC_ID && A.row_code)) return false;
+  const int smem_cap = 232448 - 1024;
+  rows_per_block = (A.v.n_slices / h->sm_count + 1) * 32;
+  lay = win_layout(A.dom.win_elems, rows_per_block);
+  if (lay.total > smem_cap) {
+    rows_per_block = 0;
+    lay = win_layout(A.dom.win_elems, 0);
+  }
+  return lay.total <= smem_cap;
+}
+
 static int coarse_cg(gmg_context *h, const Sell &A, const double *b, double *x, int max_it, double tol) {
   if (A.v.n_rows > h->cg_n) return fail(h, GMG_EINVAL, "coarse CG work vectors too small");
   const int slot = h->cg_cursor % h->cg_ring;
@@ -883,13 +903,11 @@ static int coarse_cg(gmg_context *h, const Sell &A, const double *b, double *x, 
     ev = h->ev_used++;
     cudaEventRecord(h->ev_begin[ev], h->stream);
   }
-  bool win = pat && A.dom.len > 0 && h->cg_win && A.pv.n_pat <= (int)RC_ID;
+  int rows_per_block = 0;
+  WinLayout lay{};
+  bool win = pat && window_plan(h, A, rows_per_block, lay);
   if (win) {
     const int grid = h->sm_count;
-    const int smem_cap = 232448 - 1024;
-    int rows_per_block = (A.v.n_slices / grid + 1) * 32;
-    const WinLayout lay = win_layout(A.dom.win_elems, rows_per_block);
-    if (lay.total > smem_cap) win = false;  // (too many rows per block for the 16-bit row codes in shared memory)
     if (win) {
       if (lay.total > h->cg_win_smem) {
         GMG_CUDA(h, cudaFuncSetAttribute((const void *)cg_persistent_win<WIN_SPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -898,8 +916,9 @@ static int coarse_cg(gmg_context *h, const Sell &A, const double *b, double *x, 
       }
       DomPat dom = A.dom;
       const uint32_t *mask = A.dom_mask;
+      const unsigned short *gcode = A.row_code;
       void *wargs[] = {&pv, &dom, (void *)&mask, (void *)&b, &x, &h->cg_g, &h->cg_d, &h->cg_dz, &h->cg_h, &h->cg_partials,
-                       &max_it, &tol, &res, &rows_per_block, &h->cg_prof};
+                       &max_it, &tol, &res, &rows_per_block, (void *)&gcode, &h->cg_prof};
       GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_win<WIN_SPW>, dim3(grid), dim3(WIN_BLOCK), wargs,
                                               (size_t)lay.total, h->stream));
     }
@@ -2052,6 +2071,18 @@ int gmg_debug_cg_blocks(gmg_handle h, double out_ns[768]) {
   for (int i = 0; i < 768; ++i) out_ns[i] = (double)v[i];
   std::memset(v, 0, sizeof(v));
   GMG_CUDA(h, cudaMemcpyToSymbol(g_cg_block_ns, v, sizeof(v)));
+  return GMG_OK;
+}
+
+int gmg_coarse_kernel(gmg_handle h, int which, int level, int *kernel) {
+  if (!h || !kernel) return GMG_EINVAL;
+  Sell *A = pick(h, which, level, true);
+  if (!A) return fail(h, GMG_EINVAL, "matrix not available");
+  int rpb = 0;
+  WinLayout lay{};
+  if (h->dist.on) *kernel = (A->patterned && h->compress >= 2) ? 2 : (A->compressed && h->compress >= 1) ? 1 : 0;
+  else if (window_plan(h, *A, rpb, lay)) *kernel = rpb > 0 ? 3 : 4;
+  else *kernel = (A->patterned && h->compress >= 2) ? 2 : (A->compressed && h->compress >= 1) ? 1 : 0;
   return GMG_OK;
 }
 

@@ -65,6 +65,7 @@ struct Sell {
   // dominant pattern + TMA window plan for the persistent CG (pattern_win.cuh); dom.len == 0: not available
   DomPat dom{};
   uint32_t *dom_mask = nullptr;
+  unsigned short *row_code = nullptr;  // 16-bit row codes of the window kernel (pat_row_codes)
 };
 
 struct ColorSet {

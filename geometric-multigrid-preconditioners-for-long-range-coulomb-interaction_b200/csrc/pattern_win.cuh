@@ -164,6 +164,21 @@ __global__ void pat_apply_zero_set(int n, const int *__restrict__ colflag, uint3
   if (apply && f == 2) pat[r] |= PAT_ZEROED;
 }
 
+// the 16-bit row codes of the window kernel (pattern id + path flags) for every row: used from global memory when a
+// block's share of them does not fit next to the windows in shared memory (more than ~35 k rows per block)
+__global__ void pat_row_codes(PatView A, const uint32_t *__restrict__ dom_mask, unsigned short *__restrict__ code) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= A.n_slices * 32) return;
+  const uint32_t p = A.pat[r];
+  const uint32_t id = p & PAT_ID_MASK;
+  uint32_t c = id;
+  if (id == (uint32_t)(A.n_pat - 1)) c |= RC_EMPTY;
+  else if (!(p & PAT_GENERAL) && dom_mask[id] != 0u) c |= RC_DOM;
+  else if (A.ptr[id + 1] - A.ptr[id] == 1 && A.off[A.ptr[id]] == 0) c |= RC_DIAG;
+  if (p & PAT_ZEROED) c |= RC_Z;
+  code[r] = (unsigned short)c;
+}
+
 // optional phase timing (block 0, thread 0; globaltimer ns): [spmv, barrier 1, update, barrier 2, direction, barrier 3, iterations]
 __device__ unsigned long long g_cg_phase_ns[16];
 __device__ unsigned long long g_cg_block_ns[3][256];  // per block: SpMV, update, direction phase (prof != 0)
@@ -225,7 +240,7 @@ template <int SPW>
 __global__ void __launch_bounds__(WIN_BLOCK, 1)
     cg_persistent_win(PatView A, const __grid_constant__ DomPat D, const uint32_t *__restrict__ dom_mask, const double *__restrict__ b,
                       double *x, double *g, double *d, double *dt, double *h, double *partials /* 3 * gridDim.x */, int max_it,
-                      double tol, CgResult *result, int rows_per_block, int prof) {
+                      double tol, CgResult *result, int rows_per_block, const unsigned short *__restrict__ gcode, int prof) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char smem[];
@@ -242,7 +257,7 @@ __global__ void __launch_bounds__(WIN_BLOCK, 1)
   uint64_t *empty_bar = full + 2;                       // [2]
   double *win = reinterpret_cast<double *>(smem + lay.win_off);
   PatSmem &sm = *reinterpret_cast<PatSmem *>(smem + lay.table_off);
-  unsigned short *code = reinterpret_cast<unsigned short *>(smem + lay.code_off);
+  unsigned short *scode = reinterpret_cast<unsigned short *>(smem + lay.code_off);
 
   const int nb = gridDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -264,16 +279,12 @@ __global__ void __launch_bounds__(WIN_BLOCK, 1)
   for (int i = threadIdx.x; i < 2 * D.win_elems; i += BLOCK) win[i] = 0.0;  // (lanes off the dominant path read, but never use, window data)
   const PatTable T = pat_stage(A, sm);  // (ends with __syncthreads)
   // row codes of this block's rows (they never change): pattern id + which path the row takes.  RC_DIAG: the row is
-  // its diagonal entry only (eliminated Dirichlet rows): a . d[r], no table walk.
-  for (int i = threadIdx.x; i < (s_end - s_begin) * 32; i += BLOCK) {
-    const uint32_t p = __ldg(A.pat + s_begin * 32 + i);
-    const uint32_t id = p & PAT_ID_MASK;
-    uint32_t c = id;
-    if (id == empty_id) c |= RC_EMPTY;
-    else if (!(p & PAT_GENERAL) && dom_mask[id] != 0u) c |= RC_DOM;
-    else if (T.ptr[id + 1] - T.ptr[id] == 1 && T.off[T.ptr[id]] == 0) c |= RC_DIAG;
-    if (p & PAT_ZEROED) c |= RC_Z;
-    code[i] = (unsigned short)c;
+  // its diagonal entry only (eliminated Dirichlet rows): a . d[r], no table walk.  In shared memory when they fit
+  // (rows_per_block > 0), else read from the precomputed global array.
+  const unsigned short *code = gcode + (size_t)s_begin * 32;
+  if (rows_per_block > 0) {
+    for (int i = threadIdx.x; i < (s_end - s_begin) * 32; i += BLOCK) scode[i] = gcode[(size_t)s_begin * 32 + i];
+    code = scode;
   }
   __syncthreads();
   double *pa = partials, *pb = partials + nb, *pc = partials + 2 * nb;

@@ -153,6 +153,10 @@ int gmg_debug_cg_phases(gmg_handle h, int block_plus_1, double out_ns[16]);
 int gmg_debug_vcycle_profile(gmg_handle h, int enable, double out_ms[4]);
 /* ... and per block (256 slots each): time in the SpMV, update and direction phases while timing was on. */
 int gmg_debug_cg_blocks(gmg_handle h, double out_ns[768]);
+/* Which persistent CG kernel gmg_cg_solve / the coarse solve runs on this matrix: 0 plain SELL, 1 CSELL,
+ * 2 row patterns with L1 gathers (also the multi-GPU kernel), 3 row patterns with TMA-filled shared-memory windows,
+ * 4 the same with the row codes read from global memory (more than ~35 k rows per SM). */
+int gmg_coarse_kernel(gmg_handle h, int which, int level, int *kernel);
 /* accumulated device time (ms, CUDA events on the handle's stream) and launch count of the
  * persistent coarse-CG kernel since the last reset; inner iterations summed in *iters. */
 int gmg_coarse_profile(gmg_handle h, int reset, double *ms, int64_t *launches, int64_t *iters);
