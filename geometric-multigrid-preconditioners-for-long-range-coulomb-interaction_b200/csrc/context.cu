@@ -1009,10 +1009,29 @@ static int smooth(gmg_context *h, Level &L, double *&u, const double *rhs, bool 
     if (zero_start) GMG_CUDA(h, cudaMemsetAsync(u, 0, sizeof(double) * n, h->stream));
     auto &fwd = lex ? L.wave_fwd : L.colors;
     auto &bwd = lex ? L.wave_bwd : L.colors;
+    // every colour after the first of this call follows another relaxation kernel: programmatic dependent launch
+    bool after_relax = false;
     auto relax = [&](ColorSet &c) -> int {
       if (c.n == 0) return GMG_OK;
-      sell_color_relax<<<cdiv((int64_t)c.A.v.n_rows * 8, 256), 256, 0, h->stream>>>(c.A.v, c.rows, u, rhs, L.dinv, h->omega);
-      GMG_LAUNCH_CHECK(h);
+      const int grid = cdiv((int64_t)c.A.v.n_rows * 8, 256);
+      if (h->pdl && after_relax) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(256);
+        cfg.stream = h->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        GMG_CUDA(h, cudaLaunchKernelEx(&cfg, sell_color_relax_pdl, c.A.v, (const int *)c.rows, u, rhs, (const double *)L.dinv,
+                                       h->omega));
+        h->launches++;
+      } else {
+        sell_color_relax<<<grid, 256, 0, h->stream>>>(c.A.v, c.rows, u, rhs, L.dinv, h->omega);
+        GMG_LAUNCH_CHECK(h);
+      }
+      after_relax = true;
       return GMG_OK;
     };
     for (int s = 0; s < h->steps; ++s) {
@@ -1319,6 +1338,7 @@ int gmg_create(int device, gmg_handle *out) {
                                                         : (int)std::min(12u, std::max(4u, hw * 3 / 4));
   }
   h->cg_win = !(std::getenv("GMG_CG_WIN") && std::atoi(std::getenv("GMG_CG_WIN")) == 0);
+  if (std::getenv("GMG_PDL")) h->pdl = std::atoi(std::getenv("GMG_PDL")) != 0;
   if (std::getenv("GMG_CLUSTER_SSOR")) h->cluster_ssor = std::atoi(std::getenv("GMG_CLUSTER_SSOR")) != 0;
   if (std::getenv("GMG_PERSISTENT_SSOR")) h->persistent_ssor = std::atoi(std::getenv("GMG_PERSISTENT_SSOR")) != 0;
   h->partials_cap = 1 << 16;

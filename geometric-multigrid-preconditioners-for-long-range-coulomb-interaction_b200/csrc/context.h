@@ -238,6 +238,7 @@ struct gmg_context {
   };
   std::vector<VcGraph> vc_graphs;
   bool use_graphs = true;
+  bool pdl = true;               // colour sweeps as programmatic dependent launches (GMG_PDL=0 disables)
   bool cluster_ssor = false;     // small levels: one cluster launch per smooth() (GMG_CLUSTER_SSOR=1); measured slower than
                                  // graph-replayed launches (level 2 of the 64k case: +2.8 ms per step): the colours' dependent
                                  // L2 round trips serialise on 8 SMs

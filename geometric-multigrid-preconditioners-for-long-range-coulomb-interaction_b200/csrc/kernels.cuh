@@ -343,6 +343,10 @@ __global__ void __launch_bounds__(256) sell_spmv(SellView A, const double *__res
 // partial sum handed on by shuffle: same order, same bits as one lane per row.
 // (k: local row of the colour or out of range; sub: this lane's position among the eight lanes of the row; all
 // 32 lanes of a warp must call it)
+// PDL: the kernel was launched with programmatic stream serialisation (the previous colour may still be running):
+// the matrix entries, row indices and diagonals (never written during a solve) are fetched first, then
+// griddepcontrol.wait orders everything that touches u / rhs after the previous kernel; u is read past L1.
+template <bool PDL>
 __device__ __forceinline__ void color_relax_row8(const SellView &Ac, const int *__restrict__ rows, double *u,
                                                  const double *__restrict__ rhs, const double *__restrict__ dinv, double omega,
                                                  int k, int sub) {
@@ -351,13 +355,12 @@ __device__ __forceinline__ void color_relax_row8(const SellView &Ac, const int *
   int64_t b = 0;
   int npairs = 0;
   int i = 0;
-  double rv = 0.0, dv = 0.0;
+  double dv = 0.0;
   if (on) {
     b = Ac.slice_ptr[slice];
     npairs = (int)((Ac.slice_ptr[slice + 1] - b) >> 6);
     if (sub == 0) {
       i = rows[k];
-      rv = rhs[i];
       dv = dinv[i];
     }
   }
@@ -365,6 +368,7 @@ __device__ __forceinline__ void color_relax_row8(const SellView &Ac, const int *
   const int2 *c2 = reinterpret_cast<const int2 *>(Ac.col) + (b >> 1) + rlane;
   const int pmax = __reduce_max_sync(0xffffffffu, npairs);
   double acc = 0.0;
+  bool waited = !PDL;
   for (int base = 0; base < pmax; base += 32) {  // 32 pairs per round, 4 per lane
     const int n_here = min(max(npairs - base, 0), 32);
     const int chunk = (n_here + 7) >> 3;
@@ -379,11 +383,15 @@ __device__ __forceinline__ void color_relax_row8(const SellView &Ac, const int *
         v[q] = ld_stream_d2(v2 + (p0 + q) * 32);
         c[q] = ld_stream_i2(c2 + (p0 + q) * 32);
       }
+    if (!waited) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      waited = true;
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       if (q < cnt) {
-        x0[q] = u[c[q].x];
-        x1[q] = u[c[q].y];
+        x0[q] = PDL ? __ldcg(u + c[q].x) : u[c[q].x];
+        x1[q] = PDL ? __ldcg(u + c[q].y) : u[c[q].y];
       }
 #pragma unroll
     for (int cc = 0; cc < 8; ++cc) {
@@ -398,14 +406,29 @@ __device__ __forceinline__ void color_relax_row8(const SellView &Ac, const int *
       acc = __shfl_sync(0xffffffffu, acc, (threadIdx.x & 24) | cc);
     }
   }
-  if (on && sub == 0) u[i] += omega * (rv - acc) * dv;
+  if (!waited) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (on && sub == 0) {
+    const double ui = PDL ? __ldcg(u + i) : u[i];
+    u[i] = ui + omega * (rhs[i] - acc) * dv;
+  }
 }
 
 __global__ void __launch_bounds__(256) sell_color_relax(SellView Ac, const int *__restrict__ rows, double *u,
                                                         const double *__restrict__ rhs, const double *__restrict__ dinv,
                                                         double omega) {
+  asm volatile("griddepcontrol.launch_dependents;");  // (a following programmatic launch may start its prologue)
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  color_relax_row8(Ac, rows, u, rhs, dinv, omega, t >> 3, t & 7);
+  color_relax_row8<false>(Ac, rows, u, rhs, dinv, omega, t >> 3, t & 7);
+}
+
+// the same launched with programmatic stream serialisation after another relaxation kernel: lets the next colour
+// start launching at once and fetches this colour's matrix entries while the previous colour is still running
+__global__ void __launch_bounds__(256) sell_color_relax_pdl(SellView Ac, const int *__restrict__ rows, double *u,
+                                                            const double *__restrict__ rhs, const double *__restrict__ dinv,
+                                                            double omega) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  color_relax_row8<true>(Ac, rows, u, rhs, dinv, omega, t >> 3, t & 7);
 }
 
 // One smooth() call of the multicolour / level-scheduled SSOR as ONE cooperative launch: colours (or wavefronts)
@@ -437,7 +460,7 @@ __global__ void __launch_bounds__(BLOCK) ssor_persistent(const ColorView *__rest
         // eight lanes per row (color_relax_row8); whole warps iterate together
         const int rows_per_sweep = (gridDim.x * BLOCK) >> 3;
         for (int r0 = 0; r0 < C.A.n_rows; r0 += rows_per_sweep)
-          color_relax_row8(C.A, C.rows, u, rhs, dinv, omega, r0 + ((blockIdx.x * BLOCK + threadIdx.x) >> 3), threadIdx.x & 7);
+          color_relax_row8<false>(C.A, C.rows, u, rhs, dinv, omega, r0 + ((blockIdx.x * BLOCK + threadIdx.x) >> 3), threadIdx.x & 7);
         grid.sync();
       }
     }
@@ -467,7 +490,7 @@ __global__ void __launch_bounds__(BLOCK) ssor_cluster(const ColorView *__restric
       for (int k = 0; k < nc; ++k) {
         const ColorView &C = set[(pass == 1 && bwd_reversed) ? nc - 1 - k : k];
         for (int r0 = 0; r0 < C.A.n_rows; r0 += nthreads >> 3)
-          color_relax_row8(C.A, C.rows, u, rhs, dinv, omega, r0 + (tid >> 3), threadIdx.x & 7);
+          color_relax_row8<false>(C.A, C.rows, u, rhs, dinv, omega, r0 + (tid >> 3), threadIdx.x & 7);
         cluster.sync();
       }
     }
