@@ -3,12 +3,16 @@
 //
 // Why: with the matrix reduced to 4 bytes per row (pattern.cuh) the SpMV is bound by L1 wavefronts: a 27-point row
 // needs 27 gathers per lane, each a misaligned 256-byte warp load = 3 lines = ~6 LSU cycles.  The rows of a tile of
-// 1024 consecutive rows with the DOMINANT pattern (offsets o_0..o_L) read the ranges [r0 + o_k, r0 + o_k + 1024); their
-// union is a few contiguous segments (3 for a first-touch-numbered Q1 lattice: one per lattice plane).  One thread
-// issues one bulk copy per segment into shared memory (no LSU work, no registers, overlapped with the previous
-// tile: two stages), and the 27 gathers become conflict-free LDS.64 at constant window offsets.  The dominant
-// pattern itself (values, window offsets) is a kernel parameter: fully unrolled, its values and offsets are
-// constant-bank operands of the DFMA / address arithmetic, no table loads at all.
+// WIN_TILE_ROWS (1984) consecutive rows with the DOMINANT pattern (offsets o_0..o_L) read the ranges
+// [r0 + o_k, r0 + o_k + 1984); their union is a few contiguous segments (3 for a first-touch-numbered Q1 lattice: one
+// per lattice plane).  Warp 31 is the producer: one lane issues one bulk copy per segment into a two-stage
+// shared-memory window (no LSU work, no registers; full / empty mbarriers, no block barrier inside the SpMV);
+// warps 0..30 consume: the 27 gathers become conflict-free LDS.64 [R + UR + imm] at constant window offsets.  The
+// dominant pattern itself (values, window byte offsets) is a kernel parameter: fully unrolled, its values and
+// offsets are constant-bank operands of the DFMA / address arithmetic, no table loads at all, and each constant is
+// loaded once for the two rows a lane owns in a tile.  Which path a row takes (dominant loop / single diagonal entry /
+// general table walk / remainder) is a 16-bit row code, staged in shared memory for the block's rows (or read from
+// global memory when a block owns more than ~35 k rows).
 //
 // Rows whose pattern is a sub-sequence of the dominant one with the same values (rows next to an eliminated
 // Dirichlet boundary: the couplings to boundary columns are stored zeros) run the SAME unmasked loop: the operand
