@@ -785,17 +785,30 @@ static std::vector<int> greedy_coloring(const HostCsr &a, int &n_colors) {
 }
 
 static bool coloring_is_valid(const HostCsr &a, const std::vector<int32_t> &color, int &n_colors) {
+  // (a few million entries on the larger patch levels: checked by a handful of host threads)
+  const int nt = std::max(1, std::min(8, a.n_rows / 4096));
+  std::vector<int> ok(nt, 1), mx(nt, 0);
+  auto work = [&](int t) {
+    const int r0 = (int)((int64_t)a.n_rows * t / nt), r1 = (int)((int64_t)a.n_rows * (t + 1) / nt);
+    for (int r = r0; r < r1; ++r) {
+      if (color[r] < 0 || color[r] > 255) { ok[t] = 0; return; }
+      mx[t] = std::max(mx[t], color[r] + 1);
+      for (int64_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k)
+        if (a.col[k] != r && a.val[k] != 0.0 && color[a.col[k]] == color[r]) { ok[t] = 0; return; }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto &x : th) x.join();
   n_colors = 0;
-  for (int r = 0; r < a.n_rows; ++r) {
-    if (color[r] < 0 || color[r] > 255) return false;
-    n_colors = std::max(n_colors, color[r] + 1);
-    for (int64_t k = a.rowptr[r]; k < a.rowptr[r + 1]; ++k)
-      if (a.col[k] != r && a.val[k] != 0.0 && color[a.col[k]] == color[r]) return false;
+  for (int t = 0; t < nt; ++t) {
+    if (!ok[t]) return false;
+    n_colors = std::max(n_colors, mx[t]);
   }
   return true;
 }
 
-// wavefront ("level") schedule of the forward / backward Gauss-Seidel sweeps in natural row order
 static std::vector<std::vector<int>> wavefronts(const HostCsr &a, bool forward) {
   std::vector<int> lev(a.n_rows, 0);
   int maxl = 0;
@@ -1789,9 +1802,10 @@ int gmg_pcg_solve_dev(gmg_handle h, const double *b, double *x, int max_it, doub
 static int with_host_vectors(gmg_handle h, int64_t n_in, const double *in, int64_t n_out, double *inout,
                              bool upload_inout) {
   if (int rc = ensure_stage(h, std::max(n_in, n_out))) return rc;
-  if (in) GMG_CUDA(h, gmg::copy(h, h->stage_a, in, sizeof(double) * n_in, cudaMemcpyHostToDevice));
+  if (in)
+    if (int rc = staged_h2d(h, h->stage_a, in, sizeof(double) * n_in)) return rc;
   if (upload_inout)
-    GMG_CUDA(h, gmg::copy(h, h->stage_b, inout, sizeof(double) * n_out, cudaMemcpyHostToDevice));
+    if (int rc = staged_h2d(h, h->stage_b, inout, sizeof(double) * n_out)) return rc;
   return GMG_OK;
 }
 
@@ -1802,8 +1816,7 @@ int gmg_pcg_solve(gmg_handle h, const double *b, double *x, int max_it, double a
   const int n = h->n_sys;
   if (int rc = with_host_vectors(h, n, b, n, x, true)) return rc;
   int rc = gmg_pcg_solve_dev(h, h->stage_a, h->stage_b, max_it, abs_tol, iters, res0, res_final);
-  GMG_CUDA(h, gmg::copy(h, x, h->stage_b, sizeof(double) * n, cudaMemcpyDeviceToHost));
-  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (int rc2 = staged_d2h(h, x, h->stage_b, sizeof(double) * n)) return rc ? rc : rc2;
   return rc;
 }
 
@@ -1948,7 +1961,7 @@ int gmg_vector_norms(gmg_handle h, int64_t n, const double *v, double out[3]) {
   if (!h || !v || !out || n < 0) return GMG_EINVAL;
   gmg::enter(h);
   if (int rc = ensure_stage(h, n)) return rc;
-  GMG_CUDA(h, gmg::copy(h, h->stage_a, v, sizeof(double) * n, cudaMemcpyHostToDevice));
+  if (int rc = staged_h2d(h, h->stage_a, v, sizeof(double) * n)) return rc;
   const int grid = std::min(cdiv(std::max<int64_t>(n, 1), 256 * 4), h->partials_cap);
   vec_norm_partials<<<grid, 256, 0, h->stream>>>(n, h->stage_a, h->partials, h->partials + h->partials_cap,
                                                  h->partials + 2 * h->partials_cap);
