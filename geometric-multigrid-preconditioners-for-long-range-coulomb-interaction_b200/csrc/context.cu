@@ -8,6 +8,7 @@
 #include "context.h"
 #include <cub/device/device_select.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include "kernels.cuh"
 // (dist.cuh uses RowDot / CSELL_SMEM_DICT from kernels.cuh)
@@ -696,6 +697,45 @@ static int build_sum_on_device(gmg_context *h, const Sell &A, const HostCsr &I, 
   dfree(flag);
   free_csr(dI);
   ok = hf == 0;
+  return GMG_OK;
+}
+
+// t = a^T on the device (see csr_transpose_keys)
+static int transpose_on_device(gmg_context *h, const DevCsr &a, DevCsr &t) {
+  free_csr(t);
+  t.n_rows = a.n_cols;
+  t.n_cols = a.n_rows;
+  t.nnz = a.nnz;
+  unsigned long long *key = nullptr, *key_sorted = nullptr, *count = nullptr;
+  void *tmp = nullptr;
+  size_t tmp_bytes = 0, tmp2 = 0;
+  GMG_CUDA(h, dalloc(&key, a.nnz));
+  GMG_CUDA(h, dalloc(&key_sorted, a.nnz));
+  GMG_CUDA(h, dalloc(&count, (int64_t)t.n_rows + 1));
+  GMG_CUDA(h, dalloc(&t.rowptr, (int64_t)t.n_rows + 1));
+  GMG_CUDA(h, dalloc(&t.col, a.nnz));
+  GMG_CUDA(h, dalloc(&t.val, a.nnz));
+  GMG_CUDA(h, cudaMemsetAsync(count, 0, sizeof(unsigned long long) * ((size_t)t.n_rows + 1), h->stream));
+  if (a.n_rows > 0) {
+    csr_transpose_keys<<<cdiv(a.n_rows, 256), 256, 0, h->stream>>>(a.n_rows, a.rowptr, a.col, key, count);
+    GMG_LAUNCH_CHECK(h);
+  }
+  int end_bit = 32;
+  while (end_bit < 64 && ((unsigned long long)std::max(a.n_cols, 1) >> (end_bit - 32)) != 0ull) ++end_bit;
+  GMG_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, key_sorted, a.val, t.val, a.nnz, 0, end_bit, h->stream));
+  GMG_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, tmp2, count, (unsigned long long *)t.rowptr, t.n_rows + 1, h->stream));
+  tmp_bytes = std::max(tmp_bytes, tmp2);
+  GMG_CUDA(h, cudaMallocAsync(&tmp, std::max<size_t>(tmp_bytes, 1), h->stream));
+  GMG_CUDA(h, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key_sorted, a.val, t.val, a.nnz, 0, end_bit, h->stream));
+  GMG_CUDA(h, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, count, (unsigned long long *)t.rowptr, t.n_rows + 1, h->stream));
+  if (a.nnz > 0) {
+    csr_transpose_cols<<<cdiv(a.nnz, 256), 256, 0, h->stream>>>(a.nnz, key_sorted, t.col);
+    GMG_LAUNCH_CHECK(h);
+  }
+  cudaFreeAsync(tmp, h->stream);
+  dfree(key);
+  dfree(key_sorted);
+  dfree(count);
   return GMG_OK;
 }
 
@@ -1742,17 +1782,22 @@ int gmg_setup(gmg_handle h) {
     }
     if (!L.hP.empty()) {
       TraceScope trp("    P, R");
+      DevCsr dP, dR;
+      if ((rc = upload_host_csr(h, L.hP, dP))) return rc;
       {
         TraceScope t1("      P -> sell");
-        if ((rc = build_sell_host(h, L.hP, 0.0, L.P))) return rc;
+        if ((rc = build_sell(h, dP, 0.0, L.P))) return rc;
       }
-      HostCsr r;
       {
-        TraceScope t2("      transpose");
-        r = transpose(L.hP);
+        TraceScope t2("      transpose (device)");
+        if ((rc = transpose_on_device(h, dP, dR))) return rc;
       }
-      TraceScope t3("      R -> sell");
-      if ((rc = build_sell_host(h, r, 0.0, L.R))) return rc;
+      {
+        TraceScope t3("      R -> sell");
+        if ((rc = build_sell(h, dR, 0.0, L.R))) return rc;
+      }
+      free_csr(dP);
+      free_csr(dR);
     } else if (l + 1 < h->n_levels) {
       return fail(h, GMG_EINVAL, "prolongation from level " + std::to_string(l) + " missing");
     }

@@ -223,6 +223,23 @@ __global__ void csr_to_sell(int n_rows, int n_cols, const int *__restrict__ rows
   }
 }
 
+// CSR transpose on the device (R = P^T): 64-bit keys (column << 32 | row) of all entries, radix-sorted with their
+// values; the transposed row pointer from the per-column counts.  Entries of a transposed row come out in ascending
+// original-row order: the same (deterministic) order as a sequential transpose.
+__global__ void csr_transpose_keys(int n_rows, const int64_t *__restrict__ rowptr, const int *__restrict__ col,
+                                   unsigned long long *__restrict__ key, unsigned long long *__restrict__ count) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+    key[k] = ((unsigned long long)(unsigned int)col[k] << 32) | (unsigned int)r;
+    atomicAdd(count + col[k], 1ull);
+  }
+}
+__global__ void csr_transpose_cols(int64_t nnz, const unsigned long long *__restrict__ key, int *__restrict__ col) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k < nnz) col[k] = (int)(key[k] & 0xffffffffull);
+}
+
 // val(i, j) += v for the entries of a (small) CSR matrix whose pattern is contained in the SELL matrix's:
 // A + I of a level without a host round trip.  *flag != 0 if an entry has no slot.
 __global__ void sell_add_csr(SellView A, double *__restrict__ aval, int n_rows, const int64_t *__restrict__ rowptr,
