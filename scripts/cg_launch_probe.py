@@ -5,17 +5,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np
 from helpers import pkg
-from oracle.mesh import Forest
-from oracle.dofs import DoFs
-from oracle import assemble
+import scipy.sparse as sp
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-f = Forest(2 * (2 * n + 20), -5.0, n + 5.0); d = DoFs(f); ops = assemble.LevelOps(f, d)
-A = ops.A_stored[0]; N = A.shape[0]
+M = pkg().hostapi.Ministep(2 * (2 * n + 20), -5.0, n + 5.0); M.build()
+rp, col, val = M.csr("A", 0)
+A = sp.csr_matrix((val, col, rp)); N = A.shape[0]
+boundary = M.get("level_boundary", 0).astype(bool)
 capi = pkg().capi
 g = capi.Gmg(); g.set_num_levels(1)
 g.set_matrix(capi.GMG_SYSTEM, 0, A); g.set_matrix(capi.GMG_LEVEL, 0, A)
 g.set_copy_indices(0, np.arange(N), np.arange(N)); g.setup()
-rng = np.random.default_rng(0); b = rng.standard_normal(N); b[d.level_boundary[0]] = 0
+rng = np.random.default_rng(0); b = rng.standard_normal(N); b[boundary] = 0
 x = g.vec_alloc(N); y = g.vec_alloc(N); g.vec_upload(x, b)
 BLK = int(os.environ.get("PROBE_BLOCK", "74"))
 for its in (1, 1, 200, 200):

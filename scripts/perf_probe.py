@@ -1,21 +1,19 @@
 """Developer probe (not the bench): time level-0 SpMV and the persistent coarse CG on an n-atom lattice
-level-0 operator built by the oracle.  python scripts/perf_probe.py 20"""
+level-0 operator assembled by the host library (ministep).  python scripts/perf_probe.py 20"""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
 from helpers import pkg
-from oracle.mesh import Forest
-from oracle.dofs import DoFs
-from oracle import assemble
+import scipy.sparse as sp
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 reps = 2 * (2 * n + 20)
 t = time.time()
-f = Forest(reps, -5.0, n + 5.0)
-d = DoFs(f)
-ops = assemble.LevelOps(f, d)
-A = ops.A_stored[0]
+M = pkg().hostapi.Ministep(reps, -5.0, n + 5.0); M.build()
+rp, col, val = M.csr("A", 0)
+A = sp.csr_matrix((val, col, rp))
+boundary = M.get("level_boundary", 0).astype(bool)
 print("assembled", A.shape, A.nnz, "in %.1fs" % (time.time() - t), flush=True)
 capi = pkg().capi
 g = capi.Gmg()
@@ -25,7 +23,7 @@ g.set_matrix(capi.GMG_LEVEL, 0, A)
 g.set_copy_indices(0, np.arange(A.shape[0]), np.arange(A.shape[0]))
 N = A.shape[0]
 rng = np.random.default_rng(0)
-b = rng.standard_normal(N); b[d.level_boundary[0]] = 0
+b = rng.standard_normal(N); b[boundary] = 0
 xs = {}
 MODES = [int(c) for c in os.environ.get('PROBE_MODES', '012')]
 for comp in MODES:
