@@ -115,40 +115,34 @@ int ensure_stage(gmg_context *h, int64_t n) {
 
 // Large host->device copies from pageable memory: chunks are copied into a ring of pinned buffers by a few host
 // threads (one memcpy thread tops out near 10 GB/s) while the previous chunk is in flight on the copy engine.
-int staged_h2d(gmg_context *h, void *dst, const void *src, size_t bytes) {
+static int ensure_ring(gmg_context *h) {
   constexpr size_t CHUNK = 32u << 20;
-  constexpr int NBUF = 4, MAXT = 32;
-  const int NTHREADS = std::min(std::max(h->stage_threads, 1), MAXT);
-  if (bytes < (8u << 20)) {
-    GMG_CUDA(h, copy(h, dst, src, bytes, cudaMemcpyHostToDevice));
-    return GMG_OK;
-  }
   if (!h->pin[0]) {
-    for (int i = 0; i < NBUF; ++i) {
+    for (int i = 0; i < 4; ++i) {
       GMG_CUDA(h, cudaHostAlloc((void **)&h->pin[i], CHUNK, cudaHostAllocDefault));
       GMG_CUDA(h, cudaEventCreateWithFlags(&h->pin_free[i], cudaEventDisableTiming));
     }
     h->pin_bytes = CHUNK;
   }
+  if (!h->copy_pool) h->copy_pool.reset(new CopyPool(std::min(std::max(h->stage_threads, 1), 32)));
+  return GMG_OK;
+}
+
+int staged_h2d(gmg_context *h, void *dst, const void *src, size_t bytes) {
+  constexpr int NBUF = 4;
+  if (bytes < (8u << 20)) {
+    GMG_CUDA(h, copy(h, dst, src, bytes, cudaMemcpyHostToDevice));
+    return GMG_OK;
+  }
+  if (int rc = ensure_ring(h)) return rc;
+  const size_t CHUNK = h->pin_bytes;
   h->h2d_bytes += (int64_t)bytes;
   size_t off = 0;
   int buf = 0;
   while (off < bytes) {
     const size_t n = std::min(CHUNK, bytes - off);
     GMG_CUDA(h, cudaEventSynchronize(h->pin_free[buf]));  // previous DMA out of this buffer has finished
-    {
-      const char *s = (const char *)src + off;
-      char *d = h->pin[buf];
-      std::thread th[MAXT];
-      const size_t part = (n + NTHREADS - 1) / NTHREADS;
-      for (int t = 0; t < NTHREADS; ++t) {
-        const size_t a = std::min(n, part * t), b = std::min(n, part * (t + 1));
-        th[t] = std::thread([=]() {
-          if (b > a) std::memcpy(d + a, s + a, b - a);
-        });
-      }
-      for (int t = 0; t < NTHREADS; ++t) th[t].join();
-    }
+    h->copy_pool->copy(h->pin[buf], (const char *)src + off, n);
     GMG_CUDA(h, cudaMemcpyAsync((char *)dst + off, h->pin[buf], n, cudaMemcpyHostToDevice, h->stream));
     GMG_CUDA(h, cudaEventRecord(h->pin_free[buf], h->stream));
     off += n;
@@ -160,13 +154,13 @@ int staged_h2d(gmg_context *h, void *dst, const void *src, size_t bytes) {
 // Large device->host copies into pageable memory: DMA into the pinned ring, host threads copy out while the next
 // chunk is in flight.  Synchronous (the destination is complete on return).
 int staged_d2h(gmg_context *h, void *dst, const void *src, size_t bytes) {
-  constexpr size_t CHUNK = 32u << 20;
-  constexpr int NBUF = 4, MAXT = 32;
-  const int NTHREADS = std::min(std::max(h->stage_threads, 1), MAXT);
-  if (bytes < (8u << 20) || !h->pin[0]) {
+  constexpr int NBUF = 4;
+  if (bytes < (8u << 20)) {
     GMG_CUDA(h, copy_sync(h, dst, src, bytes, cudaMemcpyDeviceToHost));
     return GMG_OK;
   }
+  if (int rc = ensure_ring(h)) return rc;
+  const size_t CHUNK = h->pin_bytes;
   h->d2h_bytes += (int64_t)bytes;
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));  // (the ring may still be draining uploads)
   const int n_chunks = (int)((bytes + CHUNK - 1) / CHUNK);
@@ -180,17 +174,7 @@ int staged_d2h(gmg_context *h, void *dst, const void *src, size_t bytes) {
     if (c + NBUF - 1 < n_chunks) issue(c + NBUF - 1);  // its buffer was emptied in the previous iteration
     GMG_CUDA(h, cudaEventSynchronize(h->pin_free[c % NBUF]));
     const size_t off = (size_t)c * CHUNK, n = std::min(CHUNK, bytes - off);
-    const char *s = h->pin[c % NBUF];
-    char *d = (char *)dst + off;
-    std::thread th[MAXT];
-    const size_t part = (n + NTHREADS - 1) / NTHREADS;
-    for (int t = 0; t < NTHREADS; ++t) {
-      const size_t a = std::min(n, part * t), b = std::min(n, part * (t + 1));
-      th[t] = std::thread([=]() {
-        if (b > a) std::memcpy(d + a, s + a, b - a);
-      });
-    }
-    for (int t = 0; t < NTHREADS; ++t) th[t].join();
+    h->copy_pool->copy((char *)dst + off, h->pin[c % NBUF], n);
   }
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   return GMG_OK;
@@ -1465,6 +1449,7 @@ int gmg_destroy(gmg_handle h) {
   for (auto e : h->ev_begin) cudaEventDestroy(e);
   for (auto e : h->ev_end) cudaEventDestroy(e);
   for (auto e : h->vc_ev) cudaEventDestroy(e);
+  h->copy_pool.reset();
   for (int i = 0; i < 4; ++i) {
     if (h->pin[i]) cudaFreeHost(h->pin[i]);
     if (h->pin_free[i]) cudaEventDestroy(h->pin_free[i]);
