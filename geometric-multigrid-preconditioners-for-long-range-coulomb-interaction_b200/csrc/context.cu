@@ -916,7 +916,7 @@ static bool window_plan(gmg_context *h, const Sell &A, int &rows_per_block, WinL
   const int smem_cap = 232448 - 1024;
   rows_per_block = (A.v.n_slices / h->sm_count + 1) * 32;
   lay = win_layout(A.dom.win_elems, rows_per_block);
-  if (lay.total > smem_cap) {
+  if (lay.total > smem_cap || h->win_global_codes) {
     rows_per_block = 0;
     lay = win_layout(A.dom.win_elems, 0);
   }
@@ -1375,6 +1375,7 @@ int gmg_create(int device, gmg_handle *out) {
                                                         : (int)std::min(12u, std::max(4u, hw * 3 / 4));
   }
   h->cg_win = !(std::getenv("GMG_CG_WIN") && std::atoi(std::getenv("GMG_CG_WIN")) == 0);
+  h->win_global_codes = std::getenv("GMG_WIN_GLOBAL_CODES") && std::atoi(std::getenv("GMG_WIN_GLOBAL_CODES")) != 0;
   if (std::getenv("GMG_PDL")) h->pdl = std::atoi(std::getenv("GMG_PDL")) != 0;
   if (std::getenv("GMG_CLUSTER_SSOR")) h->cluster_ssor = std::atoi(std::getenv("GMG_CLUSTER_SSOR")) != 0;
   if (std::getenv("GMG_PERSISTENT_SSOR")) h->persistent_ssor = std::atoi(std::getenv("GMG_PERSISTENT_SSOR")) != 0;

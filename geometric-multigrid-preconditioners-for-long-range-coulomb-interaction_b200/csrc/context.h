@@ -285,6 +285,7 @@ struct gmg_context {
   int compress = 2;      // 0: plain SELL; 1: CSELL entries; 2: row-pattern dictionary (falls back to 1, then 0)
   int cg_grid_c = 0;     // cooperative grid of the compressed-format CG kernel
   int cg_grid_p = 0;     // cooperative grid of the row-pattern CG kernel
+  bool win_global_codes = false;  // force the large-level variant of the window kernel (tests: GMG_WIN_GLOBAL_CODES=1)
   bool cg_win = true;    // TMA-window variant of the row-pattern CG (pattern_win.cuh); GMG_CG_WIN=0 disables
   bool vc_prof = false;  // gmg_debug_vcycle_profile: events around down sweep / coarse solve / up sweep
   std::vector<cudaEvent_t> vc_ev;

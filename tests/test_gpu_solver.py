@@ -286,13 +286,15 @@ def _chain_matrix(n, period, eliminated):
 
 
 @pytest.mark.parametrize("eliminated", [True, False])
-@pytest.mark.parametrize("windows", ["1", "0"])
+@pytest.mark.parametrize("windows", ["1", "0", "global-codes"])
 def test_row_pattern_cg_on_chains_with_shortened_rows(capi, eliminated, windows, monkeypatch):
     """The row-pattern coarse CG (TMA-window kernel and its L1-gather fallback) on matrices whose shortened rows are
     sub-sequences of the dominant row: same iteration count and solution as the plain format, with a right-hand side
     that is NOT zero on the eliminated rows (their operand entries live in the side vector of the window kernel)."""
     import scipy.sparse.linalg as spla
-    monkeypatch.setenv("GMG_CG_WIN", windows)
+    monkeypatch.setenv("GMG_CG_WIN", "0" if windows == "0" else "1")
+    monkeypatch.setenv("GMG_WIN_GLOBAL_CODES", "1" if windows == "global-codes" else "0")  # the > 35 k rows / SM variant
+    expected_kernel = {"1": 3, "0": 2, "global-codes": 4}[windows]
     n = 150001
     A = _chain_matrix(n, 97, eliminated)
     rng = np.random.default_rng(2)
@@ -307,6 +309,7 @@ def test_row_pattern_cg_on_chains_with_shortened_rows(capi, eliminated, windows,
         g.set_copy_indices(0, np.arange(n), np.arange(n))
         g.setup()
         assert g.matrix_traffic(capi.GMG_LEVEL, 0)["format"] == mode
+        assert g.coarse_kernel(capi.GMG_LEVEL, 0) == (expected_kernel if mode == 2 else 0)
         out[mode] = g.cg_solve(capi.GMG_LEVEL, 0, b, 1000, 1e-10)
         y = g.spmv(capi.GMG_LEVEL, 0, b, n)
         assert np.array_equal(y, out.setdefault("y", y))  # the SpMV is bit-identical across the formats
