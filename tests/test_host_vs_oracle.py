@@ -155,3 +155,67 @@ def test_prm_grammar_defaults_and_errors():
         hostlib.check_prm("set No such key = 1\n")
     with pytest.raises(hostlib.HostError):
         hostlib.check_prm("subsection Geometry\n set Mesh size = 0.5\n")
+
+
+def test_indicator_topology_reproduces_the_sequential_indicator(pair):
+    """The face topology handed to gmg_error_indicator (ministep indicator_topology: same-level neighbour / fine side /
+    coarse side with its four fine neighbours) carries everything the indicator needs: a gather formulation over it in
+    numpy reproduces the sequential face loop of error_indicator (src/step-50.cc:1020-1090)."""
+    P, M = pair
+    nl = M.n_levels
+    nb = M.get("topo_face_nb").reshape(-1, 6)
+    kind = M.get("topo_face_kind").reshape(-1, 6)
+    hang = M.get("topo_hang_children").reshape(-1, 4)
+    h = np.concatenate([np.full(len(M.get("active_cells", l)), P.forest.h(l)) for l in range(nl)])
+    dofs = np.concatenate([M.get("cell_dofs", l).reshape(-1, 8) for l in range(nl)])
+    assert len(nb) == len(h) and (kind & 3 == 1).any() and (kind & 3 == 2).any()
+    assert np.array_equal(np.sort(hang, axis=1), hang)                       # children in ascending active order
+    fine_side = np.argwhere(kind & 3 == 1)
+    assert len(fine_side) == 4 * len(hang)                                   # every hanging subface is seen from both sides
+    rng = np.random.default_rng(4)
+    u = rng.standard_normal(len(M.get("boundary")))
+    gp, gw = hostlib.gauss(2)
+
+    def dn(U, hh, a, s, t):
+        o0, o1 = (1 if a == 0 else 0), (1 if a == 2 else 2)
+        r = 0.0
+        for v in range(8):
+            w = (1.0 if (v >> a) & 1 else -1.0) / hh
+            w *= s if (v >> o0) & 1 else 1.0 - s
+            w *= t if (v >> o1) & 1 else 1.0 - t
+            r += U[v] * w
+        return r
+
+    def face(U, hh, Un, hn, a, coarse, s0, s1):
+        I = 0.0
+        for t1 in range(2):
+            for t0 in range(2):
+                s, t = gp[t0], gp[t1]
+                oth = dn(Un, hn, a, (s0 + s) / 2, (s1 + t) / 2) if coarse else dn(Un, hn, a, s, t)
+                I += (dn(U, hh, a, s, t) - oth) ** 2 * gw[t0] * gw[t1] * hh * hh
+        return I
+
+    eta = np.zeros(len(h))
+    sample = rng.choice(len(h), size=min(len(h), 1500), replace=False)  # (pure-Python loops: a sample of the cells)
+    sample = np.unique(np.concatenate([sample, fine_side[:200, 0], np.argwhere(kind & 3 == 2)[:100, 0]]))
+    for c in sample:
+        U, err = u[dofs[c]], 0.0
+        for f in range(6):
+            a, n_, k = f >> 1, nb[c, f], kind[c, f]
+            if n_ < 0:
+                continue
+            if k & 3 == 0:
+                I = face(U, h[c], u[dofs[n_]], h[c], a, False, 0, 0)
+            elif k & 3 == 1:
+                I = face(U, h[c], u[dofs[n_]], 2 * h[c], a, True, (k >> 2) & 1, (k >> 3) & 1)
+            else:
+                I = 0.0
+                for ch in hang[n_]:
+                    ck = kind[ch, f ^ 1]
+                    assert ck & 3 == 1 and nb[ch, f ^ 1] == c             # the child points back at this coarse cell
+                    I += face(u[dofs[ch]], h[ch], U, 2 * h[ch], a, True, (ck >> 2) & 1, (ck >> 3) & 1)
+            err += I * np.sqrt(3.0) * h[c]
+        eta[c] = np.sqrt(err)
+    M.error_indicator(u, np.zeros(0), 2, False)
+    ref = np.concatenate([M.get("eta", l) for l in range(nl)]).astype(np.float64)
+    assert np.allclose(eta[sample], ref[sample], rtol=2e-6, atol=1e-12)
