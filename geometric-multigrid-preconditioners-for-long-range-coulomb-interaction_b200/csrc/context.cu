@@ -209,26 +209,37 @@ static int upload_host_csr(gmg_context *h, const HostCsr &m, DevCsr &out) {
 }
 
 // CSR (device) -> sliced ELL (device); `rows` (device, optional) selects / orders a subset of the CSR rows
-static int build_sell(gmg_context *h, const DevCsr &c, double drop_tol, Sell &out, const int *rows = nullptr, int n_sub = -1) {
+// host_width (optional): the slice widths, already known on the host (colour / wavefront sets cut out of a matrix
+// whose row pointer the host holds): no device round trip, no synchronisation.
+static int build_sell(gmg_context *h, const DevCsr &c, double drop_tol, Sell &out, const int *rows = nullptr, int n_sub = -1,
+                      const std::vector<int> *host_width = nullptr, int64_t host_nnz = 0) {
   free_sell(out);
   const int n_rows = rows ? n_sub : c.n_rows;
   const int n_slices = cdiv(n_rows, SLICE);
   TraceScope trb("        build_sell");
-  int *width = nullptr;
-  unsigned long long *total = nullptr;
-  GMG_CUDA(h, dalloc(&width, n_slices));
-  GMG_CUDA(h, dalloc(&total, 1));
-  GMG_CUDA(h, cudaMemsetAsync(total, 0, sizeof(unsigned long long), h->stream));
-  if (n_slices > 0) {
-    csr_slice_widths<<<cdiv((int64_t)n_slices * 32, 256), 256, 0, h->stream>>>(n_rows, n_slices, rows, c.rowptr, c.val,
-                                                                               drop_tol, width, total);
-    GMG_LAUNCH_CHECK(h);
-  }
-  std::vector<int> hw(n_slices);
+  std::vector<int> hw;
   unsigned long long htotal = 0;
-  GMG_CUDA(h, copy(h, hw.data(), width, sizeof(int) * n_slices, cudaMemcpyDeviceToHost));
-  GMG_CUDA(h, copy(h, &htotal, total, sizeof(htotal), cudaMemcpyDeviceToHost));
-  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (host_width) {
+    hw = *host_width;
+    htotal = (unsigned long long)host_nnz;
+  } else {
+    int *width = nullptr;
+    unsigned long long *total = nullptr;
+    GMG_CUDA(h, dalloc(&width, n_slices));
+    GMG_CUDA(h, dalloc(&total, 1));
+    GMG_CUDA(h, cudaMemsetAsync(total, 0, sizeof(unsigned long long), h->stream));
+    if (n_slices > 0) {
+      csr_slice_widths<<<cdiv((int64_t)n_slices * 32, 256), 256, 0, h->stream>>>(n_rows, n_slices, rows, c.rowptr, c.val,
+                                                                                 drop_tol, width, total);
+      GMG_LAUNCH_CHECK(h);
+    }
+    hw.resize(n_slices);
+    GMG_CUDA(h, copy(h, hw.data(), width, sizeof(int) * n_slices, cudaMemcpyDeviceToHost));
+    GMG_CUDA(h, copy(h, &htotal, total, sizeof(htotal), cudaMemcpyDeviceToHost));
+    GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    dfree(width);
+    dfree(total);
+  }
   std::vector<int64_t> sp(n_slices + 1, 0);
   for (int s = 0; s < n_slices; ++s) sp[s + 1] = sp[s] + (int64_t)hw[s] * SLICE;
   out.stored_nnz = (int64_t)htotal;
@@ -236,17 +247,15 @@ static int build_sell(gmg_context *h, const DevCsr &c, double drop_tol, Sell &ou
   GMG_CUDA(h, dalloc(&out.slice_ptr, n_slices + 1));
   GMG_CUDA(h, dalloc(&out.val, out.padded));
   GMG_CUDA(h, dalloc(&out.col, out.padded));
-  GMG_CUDA(h, copy(h, out.slice_ptr, sp.data(), sizeof(int64_t) * (n_slices + 1), cudaMemcpyHostToDevice));
+  out.h_slice_ptr = sp;  // (the copy below reads the member: it stays valid while the transfer is in flight)
+  GMG_CUDA(h, copy(h, out.slice_ptr, out.h_slice_ptr.data(), sizeof(int64_t) * (n_slices + 1), cudaMemcpyHostToDevice));
   if (n_slices > 0) {
     csr_to_sell<<<cdiv((int64_t)n_slices * 32, 256), 256, 0, h->stream>>>(n_rows, c.n_cols, rows, c.rowptr, c.col, c.val,
                                                                           drop_tol, out.slice_ptr, out.val, out.col);
     GMG_LAUNCH_CHECK(h);
   }
-  GMG_CUDA(h, cudaStreamSynchronize(h->stream));
-  dfree(width);
-  dfree(total);
+  if (!host_width) GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   out.v = SellView{n_rows, c.n_cols, n_slices, out.slice_ptr, out.val, out.col};
-  out.h_slice_ptr = sp;
   out.valid = true;
   return GMG_OK;
 }
@@ -859,11 +868,21 @@ static std::vector<std::vector<int>> wavefronts(const HostCsr &a, bool forward) 
 }
 
 // rows of one colour / wavefront as their own SELL matrix, cut out of the level's CSR on the device
-static int build_colorset(gmg_context *h, const DevCsr &a, const std::vector<int> &rows, ColorSet &cs) {
+static int build_colorset(gmg_context *h, const DevCsr &a, const HostCsr &ha, const std::vector<int> &rows, ColorSet &cs) {
   cs.n = (int)rows.size();
+  cs.h_rows = rows;  // (kept: the asynchronous upload below reads it)
   GMG_CUDA(h, dalloc(&cs.rows, cs.n));
-  GMG_CUDA(h, copy(h, cs.rows, rows.data(), sizeof(int) * cs.n, cudaMemcpyHostToDevice));
-  return build_sell(h, a, -1.0, cs.A, cs.rows, cs.n);
+  GMG_CUDA(h, copy(h, cs.rows, cs.h_rows.data(), sizeof(int) * cs.n, cudaMemcpyHostToDevice));
+  // slice widths from the host copy of the row pointer (all stored entries are kept: drop tolerance < 0)
+  const int n_slices = cdiv(cs.n, SLICE);
+  std::vector<int> width(n_slices, 0);
+  int64_t nnz = 0;
+  for (int k = 0; k < cs.n; ++k) {
+    const int w = (int)(ha.rowptr[rows[k] + 1] - ha.rowptr[rows[k]]);
+    nnz += w;
+    width[k >> 5] = std::max(width[k >> 5], (w + 1) & ~1);
+  }
+  return build_sell(h, a, -1.0, cs.A, cs.rows, cs.n, &width, nnz);
 }
 
 static void free_level(Level &L) {
@@ -1691,7 +1710,7 @@ int gmg_setup(gmg_handle h) {
         if (!L.rawA.rowptr)
           if ((rc = upload_host_csr(h, L.hA, L.rawA))) return rc;
         for (int c = 0; c < nc; ++c)
-          if ((rc = build_colorset(h, L.rawA, rows[c], L.colors[c]))) return rc;
+          if ((rc = build_colorset(h, L.rawA, L.hA, rows[c], L.colors[c]))) return rc;
       } else if (h->smoother == GMG_SMOOTHER_LEX_SSOR) {
         auto f = wavefronts(L.hA, true), b = wavefronts(L.hA, false);
         L.wave_fwd.resize(f.size());
@@ -1699,9 +1718,9 @@ int gmg_setup(gmg_handle h) {
         if (!L.rawA.rowptr)
           if ((rc = upload_host_csr(h, L.hA, L.rawA))) return rc;
         for (size_t c = 0; c < f.size(); ++c)
-          if ((rc = build_colorset(h, L.rawA, f[c], L.wave_fwd[c]))) return rc;
+          if ((rc = build_colorset(h, L.rawA, L.hA, f[c], L.wave_fwd[c]))) return rc;
         for (size_t c = 0; c < b.size(); ++c)
-          if ((rc = build_colorset(h, L.rawA, b[c], L.wave_bwd[c]))) return rc;
+          if ((rc = build_colorset(h, L.rawA, L.hA, b[c], L.wave_bwd[c]))) return rc;
       } else if (h->smoother == GMG_SMOOTHER_CHEBYSHEV) {
         // power iteration for lambda_max(D^-1 A) on the host copy (small levels), 20 steps
         const HostCsr &a = L.hA;

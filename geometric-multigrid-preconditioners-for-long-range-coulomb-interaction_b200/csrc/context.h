@@ -79,6 +79,7 @@ struct ColorSet {
   Sell A;          // rows of this colour
   int *rows = nullptr;
   int n = 0;
+  std::vector<int> h_rows;
 };
 
 struct Level {
