@@ -1388,10 +1388,12 @@ int gmg_create(int device, gmg_handle *out) {
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
   }
-  {  // host threads that fill / drain the pinned staging ring (one memcpy thread tops out near 10 GB/s)
-    const unsigned hw = std::thread::hardware_concurrency();
+  {  // host threads that fill / drain the pinned staging ring (one memcpy thread tops out near 10 GB/s); several
+     // ranks on one host (torchrun sets LOCAL_WORLD_SIZE) share the cores
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned ranks = std::getenv("LOCAL_WORLD_SIZE") ? (unsigned)std::max(1, std::atoi(std::getenv("LOCAL_WORLD_SIZE"))) : 1u;
     h->stage_threads = std::getenv("GMG_STAGE_THREADS") ? std::atoi(std::getenv("GMG_STAGE_THREADS"))
-                                                        : (int)std::min(12u, std::max(4u, hw * 3 / 4));
+                                                        : (int)std::min(12u, std::max(2u, hw * 3 / 4 / ranks));
   }
   h->cg_win = !(std::getenv("GMG_CG_WIN") && std::atoi(std::getenv("GMG_CG_WIN")) == 0);
   h->win_global_codes = std::getenv("GMG_WIN_GLOBAL_CODES") && std::atoi(std::getenv("GMG_WIN_GLOBAL_CODES")) != 0;
