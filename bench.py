@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--cycles", type=int, default=5)
     ap.add_argument("--smoother", default="MulticolourSSOR", choices=["MulticolourSSOR", "SSOR", "Jacobi", "Chebyshev"])
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--assembly", default="device", choices=["device", "host"],
+                    help="e2e leg: system / level-0 matrices assembled on the device at the hand-over (default) or handed over "
+                         "assembled (always measured as well)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     return ap.parse_args()
@@ -220,6 +223,24 @@ def run_b200(args):
     h2d, d2h = g.transfer_bytes(True)
     e2e_value = B.n_dofs * e2e_steps / (ms_e * 1e-3)
     ms_e2, _, _, _ = timed(lambda: B.step_host(False), e2e_steps)
+    # the same step with the system / level-0 matrices assembled on the device at the hand-over (gmg_assemble_matrix:
+    # cell -> dof maps H2D instead of 1.2 GB of assembled CSR; the CSR built there is bit-identical, tests/test_gpu_assembly.py)
+    e2e_dev = None
+    if full_e2e and args.assembly == "device":
+        try:
+            B.set_device_assembly(True)
+            for _ in range(3):  # (the arenas of the assembly reach their final size at the second hand-over)
+                B.step_host(True)
+            g.transfer_bytes(True)
+            ms_d, outs_d, _, _ = timed(lambda: B.step_host(True), e2e_steps)
+            h2d_d, d2h_d = g.transfer_bytes(True)
+            if [o[0] for o in outs_d] != [o[0] for o in outs_e]:
+                raise RuntimeError(f"device-assembled step took {outs_d} iterations, host-assembled {outs_e}")
+            e2e_dev = {"ms": ms_d, "h2d": h2d_d, "d2h": d2h_d}
+        except Exception as exc:  # the host-assembled hand-over above stays the reported number
+            print(f"bench.py: device assembly leg failed: {exc}", file=sys.stderr)
+        finally:
+            B.set_device_assembly(False)
 
     peak, peak_src = measured_peak()
     # algorithmic bytes per inner iteration: CSR-equivalent 12 B per stored entry + 4 (n + 1) + 88 n;
@@ -282,6 +303,16 @@ def run_b200(args):
                         "compute_charge_densities + rhs assembly + gmg_pcg_solve with host buffers (hierarchy partitioned at set-up)"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }
+    if e2e_dev:
+        host_leg = dict(line["e2e"])
+        line["e2e"].update({
+            "value": B.n_dofs * e2e_steps / (e2e_dev["ms"] * 1e-3), "ms_per_step": e2e_dev["ms"] / e2e_steps,
+            "h2d_bytes_per_step": e2e_dev["h2d"] // e2e_steps, "d2h_bytes_per_step": e2e_dev["d2h"] // e2e_steps,
+            "what": "compute_charge_densities + rhs assembly + solve() with host buffers and `Matrix assembly = Device`: "
+                    "atoms/cells/cell-dof maps/constraints/patch-level CSR/vectors H2D, system + level-0 matrices assembled on "
+                    "the device (bit-identical CSR), densities/rhs/solution D2H",
+            "host_assembled_matrices": {k: host_leg[k] for k in ("value", "ms_per_step", "h2d_bytes_per_step",
+                                                                 "d2h_bytes_per_step")}})
     # V-cycle time: first (largest) and mean over the solve, from the coarse profile + one direct measurement
     src, dst = g.vec_alloc(B.n_dofs), g.vec_alloc(B.n_dofs)
     g.vec_upload(src, B.get("rhs"))

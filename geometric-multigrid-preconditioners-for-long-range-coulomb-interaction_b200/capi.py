@@ -33,6 +33,8 @@ SIGNATURES = {
     "gmg_compiled_arch": (_i, []),
     "gmg_set_num_levels": (_i, [_h, _i]),
     "gmg_set_matrix": (_i, [_h, _i, _i, C.c_int32, C.c_int32, _pi64, _pi32, _pd]),
+    "gmg_assemble_matrix": (_i, [_h, _i, _i, C.c_int32, _i64, _pi32, _pd, _d, _pu8, _pi64, _pi32, _pd, _pd]),
+    "gmg_raw_matrix_get": (_i, [_h, _i, _i, _pi64, _pi64, _pi32, _pd]),
     "gmg_set_copy_indices": (_i, [_h, _i, C.c_int32, _pi32, _pi32]),
     "gmg_set_smoother": (_i, [_h, _i, _d, _i]),
     "gmg_set_coarse": (_i, [_h, _i, _d]),
@@ -169,6 +171,34 @@ class Gmg:
         val = _f64(csr.data)
         self._ck(self.lib.gmg_set_matrix(self.h, which, level, csr.shape[0], csr.shape[1], rp.ctypes.data_as(_pi64),
                                          col.ctypes.data_as(_pi32), _pd_of(val)))
+
+    def assemble_matrix(self, which, level, n_rows, cell_dofs, cell_h, row_flags, k_ref, hang=None, uniform_h=0.0):
+        """gmg_assemble_matrix: cell_h an array or None (uniform_h); hang = (rowptr, col, val) or None."""
+        cell_dofs = _i32(cell_dofs).reshape(-1, 8)
+        flags = np.ascontiguousarray(row_flags, dtype=np.uint8)
+        k_ref = _f64(k_ref).ravel()
+        assert k_ref.size == 64 and flags.size == n_rows
+        ch = _f64(cell_h) if cell_h is not None else None
+        hp = hc = hv = None
+        if hang is not None:
+            hp = np.ascontiguousarray(hang[0], dtype=np.int64)
+            hc, hv = _i32(hang[1]), _f64(hang[2])
+        self._ck(self.lib.gmg_assemble_matrix(
+            self.h, which, level, n_rows, cell_dofs.shape[0], cell_dofs.ctypes.data_as(_pi32),
+            _pd_of(ch) if ch is not None else None, float(uniform_h), flags.ctypes.data_as(_pu8),
+            hp.ctypes.data_as(_pi64) if hp is not None else None, hc.ctypes.data_as(_pi32) if hc is not None else None,
+            _pd_of(hv) if hv is not None else None, _pd_of(k_ref)))
+
+    def raw_matrix(self, which, level, n_rows):
+        """(rowptr, col, val) of a handed-over / assembled matrix before gmg_setup consumes it."""
+        nnz = _i64(0)
+        self._ck(self.lib.gmg_raw_matrix_get(self.h, which, level, C.byref(nnz), None, None, None))
+        rp = np.zeros(n_rows + 1, dtype=np.int64)
+        col = np.zeros(nnz.value, dtype=np.int32)
+        val = np.zeros(nnz.value, dtype=np.float64)
+        self._ck(self.lib.gmg_raw_matrix_get(self.h, which, level, C.byref(nnz), rp.ctypes.data_as(_pi64),
+                                             col.ctypes.data_as(_pi32), _pd_of(val)))
+        return rp, col, val
 
     def set_copy_indices(self, level, g, l):
         g, l = _i32(g), _i32(l)

@@ -1358,6 +1358,8 @@ static Sell *pick(gmg_context *h, int which, int level, bool local_ok = false) {
 
 }  // namespace gmg
 
+#include "assemble.inl"
+
 // =================================================================================== C ABI
 extern "C" {
 
@@ -1547,6 +1549,47 @@ int gmg_set_matrix(gmg_handle h, int which, int level, int32_t n_rows, int32_t n
     return GMG_OK;
   }
   return fail(h, GMG_EINVAL, "unknown matrix kind");
+}
+
+int gmg_assemble_matrix(gmg_handle h, int which, int level, int32_t n_rows, int64_t n_cells, const int32_t *cell_dofs,
+                        const double *cell_h, double uniform_h, const uint8_t *row_flags, const int64_t *hang_rowptr,
+                        const int32_t *hang_col, const double *hang_val, const double *k_ref) {
+  if (!h || n_rows < 0 || n_cells < 0 || !k_ref) return GMG_EINVAL;
+  if (n_cells > 0 && !cell_dofs) return GMG_EINVAL;
+  if (n_rows > 0 && !row_flags) return GMG_EINVAL;
+  if (hang_rowptr && hang_rowptr[n_rows] > 0 && (!hang_col || !hang_val)) return GMG_EINVAL;
+  gmg::enter(h);
+  if (n_cells >= (int64_t(1) << 57)) return fail(h, GMG_EINVAL, "gmg_assemble_matrix: too many cells");
+  if (h->dist.on)
+    return fail(h, GMG_EINVAL, "gmg_assemble_matrix: row-partitioned matrices are handed over assembled (gmg_set_matrix)");
+  h->is_setup = false;
+  if (which == GMG_SYSTEM) {
+    h->n_sys = n_rows;
+    return assemble_matrix_device(h, n_rows, n_cells, cell_dofs, cell_h, uniform_h, row_flags, hang_rowptr, hang_col,
+                                  hang_val, k_ref, h->rawS, h->upload[0]);
+  }
+  if (which != GMG_LEVEL || level != 0)
+    return fail(h, GMG_EINVAL, "gmg_assemble_matrix: the system matrix and the level-0 matrix are assembled on the device; "
+                               "patch levels are handed over assembled");
+  if (h->n_levels < 1) return fail(h, GMG_EINVAL, "level out of range (call gmg_set_num_levels)");
+  Level &L = h->levels[0];
+  L.n = n_rows;
+  return assemble_matrix_device(h, n_rows, n_cells, cell_dofs, cell_h, uniform_h, row_flags, hang_rowptr, hang_col, hang_val,
+                                k_ref, L.rawA, h->upload[1]);
+}
+
+int gmg_raw_matrix_get(gmg_handle h, int which, int level, int64_t *nnz, int64_t *rowptr, int32_t *col, double *val) {
+  if (!h || !nnz) return GMG_EINVAL;
+  gmg::enter(h);
+  const DevCsr *c = nullptr;
+  if (which == GMG_SYSTEM) c = &h->rawS;
+  else if (which == GMG_LEVEL && level >= 0 && level < h->n_levels) c = &h->levels[level].rawA;
+  if (!c || !c->rowptr) return fail(h, GMG_EINVAL, "no raw matrix (handed over matrices are consumed by gmg_setup)");
+  *nnz = c->nnz;
+  if (rowptr) GMG_CUDA(h, copy_sync(h, rowptr, c->rowptr, sizeof(int64_t) * ((size_t)c->n_rows + 1), cudaMemcpyDeviceToHost));
+  if (col && c->nnz) GMG_CUDA(h, copy_sync(h, col, c->col, sizeof(int32_t) * c->nnz, cudaMemcpyDeviceToHost));
+  if (val && c->nnz) GMG_CUDA(h, copy_sync(h, val, c->val, sizeof(double) * c->nnz, cudaMemcpyDeviceToHost));
+  return GMG_OK;
 }
 
 int gmg_set_copy_indices(gmg_handle h, int level, int32_t n, const int32_t *gi, const int32_t *li) {

@@ -7,6 +7,7 @@
 #include <sstream>
 
 #include "step_50.h"
+#include "../csrc/assemble_row.h"
 
 using namespace ministep;
 
@@ -138,6 +139,82 @@ int ms_get(void *p, const char *name, int l, const void **ptr, int64_t *count, i
     return -1;
   }
   return get_array(b->forest.get(), b->dofs.get(), &b->system, &b->ops, &b->eta, &b->flags, name, l, ptr, count, dtype);
+}
+
+// unit-cube Q1 Laplace cell matrix (row-major 8 x 8): the k_ref argument of gmg_assemble_matrix
+int ms_unit_stiffness(double *out64) {
+  double K[NV][NV];
+  unit_stiffness(K);
+  std::memcpy(out64, K, sizeof(K));
+  return 0;
+}
+
+// Sequential emulation of the device-side matrix assembly (csrc/assemble.inl runs the same row routines of
+// csrc/assemble_row.h, one thread per row): builds the matrix and compares it entry by entry -- row pointer, columns and
+// the BITS of the values -- with the host assembly.  which: 0 = system matrix, 1 = level matrix.  Returns the number of
+// differing words in *n_diff and the longest row in *max_row.
+int ms_assemble_emulate(void *p, int which, int level, int64_t *n_diff, int *max_row) {
+  Bundle *b = (Bundle *)p;
+  try {
+    if (!b->dofs) { g_err = "DoFs not built"; return -1; }
+    const DoFs &d = *b->dofs;
+    const AssemblyInputs in = which == 0 ? assembly_inputs_system(*b->forest, d) : assembly_inputs_level(*b->forest, d, level);
+    const Csr &ref = which == 0 ? b->system : b->ops.A.at(level);
+    const bool hang = which == 0 && in.hanging;
+    // incidence entries in slot order, then a stable sort by row (the device: radix sort)
+    std::vector<std::pair<int, uint64_t>> ent;
+    for (int64_t s = 0; s < 8 * in.n_cells; ++s)
+      gmg::asm_slot_entries(in.cell_dofs.data(), in.flags.data(), hang ? d.hang.rowptr.data() : nullptr,
+                            hang ? d.hang.col.data() : nullptr, s,
+                            [&](int row, uint64_t e) { ent.push_back({row, e}); });
+    std::stable_sort(ent.begin(), ent.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
+    std::vector<int64_t> inc_ptr(in.n_rows + 1, 0);
+    std::vector<uint64_t> inc(ent.size());
+    for (size_t k = 0; k < ent.size(); ++k) {
+      inc_ptr[ent[k].first + 1]++;
+      inc[k] = ent[k].second;
+    }
+    for (int i = 0; i < in.n_rows; ++i) inc_ptr[i + 1] += inc_ptr[i];
+    gmg::AsmView A{};
+    A.n_rows = in.n_rows;
+    A.n_cells = in.n_cells;
+    A.cell_dofs = in.cell_dofs.data();
+    A.cell_h = in.cell_h.empty() ? nullptr : in.cell_h.data();
+    A.uniform_h = in.uniform_h;
+    A.flags = in.flags.data();
+    A.hang_ptr = hang ? d.hang.rowptr.data() : nullptr;
+    A.hang_col = hang ? d.hang.col.data() : nullptr;
+    A.hang_val = hang ? d.hang.val.data() : nullptr;
+    A.inc_ptr = inc_ptr.data();
+    A.inc = inc.data();
+    double K[NV][NV];
+    unit_stiffness(K);
+    std::memcpy(A.kref, K, sizeof(K));
+    constexpr int MAXC = 1024;
+    int64_t diff = 0;
+    int longest = 0;
+    if (ref.n_rows != in.n_rows) { g_err = "row count differs"; return -1; }
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : diff) reduction(max : longest)
+    for (int i = 0; i < in.n_rows; ++i) {
+      int cols[MAXC];
+      double vals[MAXC];
+      const int n = gmg::asm_row_pattern(A, i, cols, MAXC);
+      const int64_t r0 = ref.rowptr[i], r1 = ref.rowptr[i + 1];
+      if (n < 0 || n != (int)(r1 - r0)) {
+        diff += 1 + (r1 - r0);
+        continue;
+      }
+      longest = std::max(longest, n);
+      gmg::asm_row_values(A, i, cols, n, vals);
+      for (int k = 0; k < n; ++k) {
+        if (cols[k] != ref.col[r0 + k]) ++diff;
+        if (std::memcmp(&vals[k], &ref.val[r0 + k], sizeof(double)) != 0) ++diff;
+      }
+    }
+    *n_diff = diff;
+    *max_row = longest;
+  } catch (std::exception &e) { g_err = e.what(); return -1; }
+  return 0;
 }
 
 int ms_error_indicator(void *p, const double *u, int64_t n_rho, const double *rho, int nq, int residual_term,
@@ -308,6 +385,8 @@ class BenchProblem : public Step50::LaplaceProblem<3> {
     *res = cycle_records.back().conv;
     sink.str("");
   }
+  // e2e leg with the matrices assembled on the device at the hand-over (the host copies built by the set-up stay unused)
+  void set_device_assembly(bool on) { device_assembly = on; }
   void info(int64_t *out) {
     out[0] = (int64_t)solution.size();
     out[1] = (int64_t)triangulation->n_active_cells();
@@ -384,6 +463,10 @@ void *step50_bench_create(const char *prm_text) {
     g_err = e.what();
     return nullptr;
   }
+}
+int step50_bench_set_device_assembly(void *p, int on) {
+  ((BenchHolder *)p)->problem->set_device_assembly(on != 0);
+  return 0;
 }
 int step50_bench_finish_setup(void *p) {
   try {

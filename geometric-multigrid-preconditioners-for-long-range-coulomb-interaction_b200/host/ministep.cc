@@ -517,15 +517,48 @@ Csr assemble_system_matrix(const Forest &f, const DoFs &d, const Coefficient &co
   return rows_to_csr(n, n, rows);
 }
 
+// =============================================================================== inputs of the device assembly
+AssemblyInputs assembly_inputs_system(const Forest &f, const DoFs &d) {
+  AssemblyInputs in;
+  in.n_rows = d.n;
+  for (int l = 0; l < f.n_levels(); ++l) in.n_cells += (int64_t)d.active_cells[l].size();
+  in.cell_dofs.reserve(8 * in.n_cells);
+  in.cell_h.reserve(in.n_cells);
+  for (int l = 0; l < f.n_levels(); ++l)
+    for (size_t p = 0; p < d.active_cells[l].size(); ++p) {
+      for (int a = 0; a < NV; ++a) in.cell_dofs.push_back(d.cell_dofs[l][p][a]);
+      in.cell_h.push_back(f.h(l));
+    }
+  in.flags.resize(d.n);
+  for (int i = 0; i < d.n; ++i) {
+    in.flags[i] = (uint8_t)((d.hanging[i] ? 2 : (d.dirichlet[i] ? 1 : 0)));
+    if (d.hanging[i]) in.hanging = true;
+  }
+  return in;
+}
+
+AssemblyInputs assembly_inputs_level(const Forest &f, const DoFs &d, int l) {
+  AssemblyInputs in;
+  in.n_rows = d.level_n[l];
+  in.n_cells = f.n_cells(l);
+  in.cell_dofs.resize(8 * in.n_cells);
+  for (int64_t c = 0; c < in.n_cells; ++c)
+    for (int a = 0; a < NV; ++a) in.cell_dofs[8 * c + a] = d.level_cell_dofs[l][c][a];
+  in.uniform_h = f.h(l);
+  in.flags.resize(in.n_rows);
+  for (int i = 0; i < in.n_rows; ++i) in.flags[i] = (uint8_t)((d.level_edge[l][i] || d.level_boundary[l][i]) ? 1 : 0);
+  return in;
+}
+
 // =============================================================================== level operators
-LevelOperators assemble_level_operators(const Forest &f, const DoFs &d, const Coefficient &coef) {
+LevelOperators assemble_level_operators(const Forest &f, const DoFs &d, const Coefficient &coef, int first_level) {
   const int nl = f.n_levels();
   LevelOperators ops;
   ops.A.resize(nl);
   ops.I.resize(nl);
   ops.P.resize(nl > 0 ? nl - 1 : 0);
   CellK cellK(coef);
-  for (int l = 0; l < nl; ++l) {
+  for (int l = first_level; l < nl; ++l) {
     const int n = d.level_n[l], nc = f.n_cells(l);
     const auto &cd = d.level_cell_dofs[l];
     const auto &edge = d.level_edge[l];

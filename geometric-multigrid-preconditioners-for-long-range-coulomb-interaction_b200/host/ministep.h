@@ -100,7 +100,23 @@ struct LevelOperators {
   std::vector<Csr> A, I, P;  // mg_matrices, mg_interface_matrices, prolongation l -> l+1
 };
 // assemble_multigrid (src/step-50.cc:835-933) + MGTransferPrebuilt::build_matrices (:957-958)
-LevelOperators assemble_level_operators(const Forest &f, const DoFs &d, const Coefficient &coef);
+// first_level > 0: A and I of the levels below it are left empty (assembled elsewhere: gmg_assemble_matrix)
+LevelOperators assemble_level_operators(const Forest &f, const DoFs &d, const Coefficient &coef, int first_level = 0);
+
+// Inputs of the device-side matrix assembly (gmg_assemble_matrix, include/gmg_b200.h): the cell -> dof map in the
+// order of the sequential cell loop, the cell sizes and one flag byte per row (bit 0: eliminated row / column =
+// Dirichlet dof, level boundary or refinement-edge dof; bit 1: hanging dof, constraint line in DoFs::hang).
+struct AssemblyInputs {
+  int n_rows = 0;
+  int64_t n_cells = 0;
+  std::vector<int32_t> cell_dofs;  // [n_cells][8]
+  std::vector<double> cell_h;      // [n_cells]; empty: uniform_h
+  double uniform_h = 0.0;
+  std::vector<uint8_t> flags;      // [n_rows]
+  bool hanging = false;            // any hanging dof (the constraint lines are DoFs::hang)
+};
+AssemblyInputs assembly_inputs_system(const Forest &f, const DoFs &d);          // active cells, level by level
+AssemblyInputs assembly_inputs_level(const Forest &f, const DoFs &d, int level);  // all cells of the level
 
 // b_i -= sum_j K_ij ghat_j over unconstrained rows is done on the device; the host only provides
 // ghat = T g (hanging nodes with Dirichlet parents get their interpolated value)

@@ -68,6 +68,9 @@ void ParameterReader::declare_parameters() {
   prm.declare_entry("Smoother relaxation", "0.5", Patterns::Double(), "Damping factor of the smoother");
   prm.declare_entry("Smoothing steps", "2", Patterns::Integer(), "Pre- and post-smoothing steps on every level");
   prm.declare_entry("GPU device", "0", Patterns::Integer(), "CUDA device ordinal");
+  prm.declare_entry("Matrix assembly", "Host", Patterns::Selection("Host | Device"),
+                    "Device: system and level-0 matrices are assembled on the GPU from the cell-dof maps "
+                    "(bit-identical to the host assembly) instead of being handed over assembled");
   prm.leave_subsection();
   prm.enter_subsection("Lammps data");
   prm.declare_entry("Lammps input file", "atom_8.data", Patterns::Anything(),
@@ -141,6 +144,7 @@ LaplaceProblem<dim>::LaplaceProblem(
     smoother_omega = prm.get_double("Smoother relaxation");
     smoothing_steps = (int)prm.get_integer("Smoothing steps");
     gpu_device = (int)prm.get_integer("GPU device");
+    device_assembly = prm.get("Matrix assembly") == "Device";
     prm.leave_subsection();
     prm.enter_subsection("Misc");
     energy_atom_limit = (unsigned int)prm.get_integer("Energy postprocessing atom limit");
@@ -346,6 +350,8 @@ template <int dim>
 void LaplaceProblem<dim>::setup_system(const unsigned int &cycle) {
   TimerOutput::Scope t(computing_timer, "Setup system");
   mg_dof_handler.reset(new DoFs(*triangulation));
+  asm_flags_system.clear();
+  asm_flags_level0.clear();
   active_cells_cache.reset(new ActiveCells(flatten(*triangulation, *mg_dof_handler, flag_rhs_assembly)));
   solution.assign(mg_dof_handler->n, 0.0);
   system_rhs.assign(mg_dof_handler->n, 0.0);
@@ -366,7 +372,8 @@ void LaplaceProblem<dim>::assemble_system() {
   Coefficient coef;
   if (Problemtype == "Step16")
     coef = [](double x, double y, double z) { return (x * x + y * y + z * z < 0.5 * 0.5) ? 5.0 : 1.0; };
-  system_matrix = assemble_system_matrix(f, d, coef);
+  if (assemble_on_device()) system_matrix = Csr{};  // built on the device at the hand-over (gmg_assemble_matrix)
+  else system_matrix = assemble_system_matrix(f, d, coef);
   assemble_rhs_on_device();
 }
 
@@ -434,7 +441,8 @@ void LaplaceProblem<dim>::assemble_multigrid() {
   Coefficient coef;
   if (Problemtype == "Step16")
     coef = [](double x, double y, double z) { return (x * x + y * y + z * z < 0.5 * 0.5) ? 5.0 : 1.0; };
-  mg_ops = assemble_level_operators(*triangulation, *mg_dof_handler, coef);
+  // Matrix assembly = Device: level 0 (all but a few percent of the level entries) is built on the device
+  mg_ops = assemble_level_operators(*triangulation, *mg_dof_handler, coef, assemble_on_device() ? 1 : 0);
 }
 
 
@@ -464,10 +472,47 @@ void LaplaceProblem<dim>::hand_over_hierarchy() {
     gmg_check(gmg_set_matrix(gmg, which, l, m.n_rows, m.n_cols, m.rowptr.data(), m.col.data(), m.val.data()),
               "gmg_set_matrix");
   };
-  set(GMG_SYSTEM, 0, system_matrix);
+  bool on_device = assemble_on_device();
+  if (on_device && dist_world > 1) {
+    // row-partitioned matrices are handed over assembled: build what the earlier stages left to the device
+    if (system_matrix.rowptr.empty()) system_matrix = assemble_system_matrix(*triangulation, d, Coefficient());
+    if (mg_ops.A[0].rowptr.empty()) mg_ops = assemble_level_operators(*triangulation, d, Coefficient(), 0);
+    on_device = false;
+  }
+  double Kref[NV][NV];
+  unit_stiffness(Kref);
+  if (on_device) {
+    HostTrace tr("  gmg_assemble_matrix (system)");
+    const ActiveCells &a = *active_cells_cache;
+    std::vector<uint8_t> &flags = asm_flags_system;  // per mesh (setup_system clears them)
+    if ((int)flags.size() != d.n) {
+      flags.resize(d.n);
+      for (int i = 0; i < d.n; ++i) flags[i] = (uint8_t)(d.hanging[i] ? 2 : (d.dirichlet[i] ? 1 : 0));
+    }
+    gmg_check(gmg_assemble_matrix(gmg, GMG_SYSTEM, 0, d.n, (int64_t)a.h.size(), a.dofs.data(), a.h.data(), 0.0, flags.data(),
+                                  d.hang.rowptr.data(), d.hang.col.data(), d.hang.val.data(), &Kref[0][0]),
+              "gmg_assemble_matrix");
+  } else {
+    set(GMG_SYSTEM, 0, system_matrix);
+  }
   if (mg) {
     for (int l = 0; l < nl; ++l) {
-      set(GMG_LEVEL, l, mg_ops.A[l]);
+      if (l == 0 && on_device) {
+        HostTrace tr("  gmg_assemble_matrix (level 0)");
+        const int n0 = d.level_n[0];
+        std::vector<uint8_t> &flags = asm_flags_level0;
+        if ((int)flags.size() != n0) {
+          flags.resize(n0);
+          for (int i = 0; i < n0; ++i) flags[i] = (uint8_t)((d.level_edge[0][i] || d.level_boundary[0][i]) ? 1 : 0);
+        }
+        static_assert(sizeof(Dofs8) == 8 * sizeof(int32_t), "cell dofs are handed over as int32[8]");
+        gmg_check(gmg_assemble_matrix(gmg, GMG_LEVEL, 0, n0, (int64_t)triangulation->n_cells(0),
+                                      d.level_cell_dofs[0].data()->data(), nullptr, triangulation->h(0), flags.data(),
+                                      nullptr, nullptr, nullptr, &Kref[0][0]),
+                  "gmg_assemble_matrix");
+      } else {
+        set(GMG_LEVEL, l, mg_ops.A[l]);
+      }
       if (l >= 1) set(GMG_EDGE, l, mg_ops.I[l]);
       if (l + 1 < nl) set(GMG_PROLONG, l, mg_ops.P[l]);
       gmg_check(gmg_set_copy_indices(gmg, l, (int)d.copy_global[l].size(), d.copy_global[l].data(),

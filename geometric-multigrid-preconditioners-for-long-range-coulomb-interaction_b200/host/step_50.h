@@ -147,6 +147,11 @@ class LaplaceProblem {
   int gpu_device = 0;
   unsigned int energy_atom_limit = 300;
   bool indicator_with_residual = true;  // false: Kelly part only (the build behind the cluster logs)
+  // Matrix assembly = Device: the system matrix and the level-0 matrix are assembled on the GPU from the cell -> dof
+  // maps (gmg_assemble_matrix: the same CSR, bit for bit) instead of on the host; patch levels stay on the host
+  bool device_assembly = false;
+  std::vector<uint8_t> asm_flags_system, asm_flags_level0;  // row flags of gmg_assemble_matrix, built once per mesh
+  bool assemble_on_device() const { return device_assembly && Problemtype != "Step16" && PreconditionerType == "GMG"; }
 
   std::unique_ptr<ministep::Forest> triangulation;
   std::unique_ptr<ministep::DoFs> mg_dof_handler;

@@ -29,6 +29,8 @@ def lib():
         L.ms_n_cells.restype = C.c_int64
         L.ms_n_cells.argtypes = [C.c_void_p, C.c_int]
         L.ms_get.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+        L.ms_assemble_emulate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+        L.ms_unit_stiffness.argtypes = [C.c_void_p]
         L.ms_error_indicator.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.ms_transfer.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ms_distribute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -42,6 +44,7 @@ def lib():
         L.step50_bench_create.argtypes = [C.c_char_p]
         L.step50_bench_destroy.argtypes = [C.c_void_p]
         L.step50_bench_finish_setup.argtypes = [C.c_void_p]
+        L.step50_bench_set_device_assembly.argtypes = [C.c_void_p, C.c_int]
         L.step50_bench_download_x.argtypes = [C.c_void_p, C.c_void_p]
         L.step50_bench_gmg.restype = C.c_void_p
         L.step50_bench_gmg.argtypes = [C.c_void_p]
@@ -77,6 +80,7 @@ class Ministep:
     def __init__(self, reps, lo, hi):
         self.L = lib()
         self.p = self.L.ms_create(reps, lo, hi)
+        self.h0 = (hi - lo) / reps  # edge of a base cell (Forest::H)
 
     def __del__(self):
         if getattr(self, "p", None):
@@ -108,6 +112,12 @@ class Ministep:
         rp, col, val = self.get(prefix + "_rowptr", level), self.get(prefix + "_col", level), self.get(prefix + "_val", level)
         return rp, col, val
 
+    def assemble_emulate(self, which, level=0):
+        """Sequential emulation of the device-side assembly against the host assembly: (differing words, longest row)."""
+        nd, mr = C.c_int64(-1), C.c_int(0)
+        _ck(self.L.ms_assemble_emulate(self.p, which, level, C.byref(nd), C.byref(mr)))
+        return nd.value, mr.value
+
     def error_indicator(self, u, rho, nq, residual_term=True):
         u = np.ascontiguousarray(u, dtype=np.float64)
         rho = np.ascontiguousarray(rho, dtype=np.float64).ravel()
@@ -126,6 +136,30 @@ class Ministep:
         x = np.ascontiguousarray(x, dtype=np.float64).copy()
         _ck(self.L.ms_distribute(self.p, g.ctypes.data, x.ctypes.data))
         return x
+
+
+def unit_stiffness():
+    """Q1 Laplace cell matrix of the unit cube (8 x 8), the host's bits."""
+    K = np.zeros((8, 8))
+    lib().ms_unit_stiffness(K.ctypes.data)
+    return K
+
+
+def assembly_inputs(M, which, level=0):
+    """Inputs of Gmg.assemble_matrix from a built Ministep: (n_rows, cell_dofs, cell_h or None, uniform_h, flags, hang)."""
+    if which == 0:
+        dofs, hs = [], []
+        for l in range(M.n_levels):
+            cd = M.get("cell_dofs", l).reshape(-1, 8)
+            dofs.append(cd)
+            hs.append(np.full(len(cd), M.h0 / (1 << l)))
+        hanging, dirichlet = M.get("hanging"), M.get("dirichlet")
+        flags = np.where(hanging != 0, 2, np.where(dirichlet != 0, 1, 0)).astype(np.uint8)
+        hang = (M.get("hang_rowptr"), M.get("hang_col"), M.get("hang_val")) if hanging.any() else None
+        return len(flags), np.concatenate(dofs), np.concatenate(hs), 0.0, flags, hang
+    cd = M.get("level_cell_dofs", level).reshape(-1, 8)
+    flags = ((M.get("level_edge", level) != 0) | (M.get("level_boundary", level) != 0)).astype(np.uint8)
+    return len(flags), cd, None, M.h0 / (1 << level), flags, None
 
 
 def gauss(n):
@@ -194,6 +228,10 @@ class BenchProblem:
         its, res = C.c_int(0), C.c_double(0)
         _ck(self.L.step50_bench_step_host(self.p, int(with_hierarchy), C.byref(its), C.byref(res)))
         return its.value, res.value
+
+    def set_device_assembly(self, on):
+        """step_host(True) hands the hierarchy over with the system / level-0 matrices assembled on the device."""
+        _ck(self.L.step50_bench_set_device_assembly(self.p, int(on)))
 
     def download_x(self):
         """Solution of the last step_device() (device -> host)."""

@@ -67,6 +67,27 @@ int gmg_set_num_levels(gmg_handle h, int n_levels);
 /* CSR, sorted or unsorted columns, explicit zeros allowed (Epetra keeps the pattern's zeros). */
 int gmg_set_matrix(gmg_handle h, int which, int level, int32_t n_rows, int32_t n_cols,
                    const int64_t *rowptr, const int32_t *col, const double *val);
+/* Device-side assembly of the Q1 Laplace matrix instead of handing it over assembled: replaces the
+ * matrix part of assemble_system (src/step-50.cc:771-795: cell matrices condensed through
+ * constraints.distribute_local_to_global into the pattern of make_sparsity_pattern(dof, dsp, constraints, true),
+ * :699-701) for which = GMG_SYSTEM, and the level-0 loop of assemble_multigrid (:855-889: boundary / refinement-edge
+ * dofs eliminated) for which = GMG_LEVEL, level = 0.  Patch levels (>= 1) are small and stay with gmg_set_matrix.
+ *   cell_dofs[n_cells][8]  dofs of the cells in the order of the reference's cell loop (vertex v: bit d = offset along d)
+ *   cell_h[n_cells]        edge length per cell, or NULL: every cell has uniform_h (cell matrix = h * k_ref)
+ *   row_flags[n_rows]      bit 0: eliminated row and column (Dirichlet dof, level boundary / refinement-edge dof);
+ *                          bit 1: hanging dof, constraint line in the CSR (hang_rowptr[n_rows + 1], hang_col, hang_val;
+ *                          at most 7 parents per line, no chains); hang_* may be NULL when nothing hangs
+ *   k_ref[64]              cell matrix of the unit cube, row-major (the host's bits)
+ * The result is the CSR the sequential assembly produces: same pattern (explicit zeros kept), same value bits (every
+ * entry is summed in the order of the cell loop, unfused).  Afterwards gmg_setup as usual. */
+int gmg_assemble_matrix(gmg_handle h, int which, int level, int32_t n_rows, int64_t n_cells,
+                        const int32_t *cell_dofs, const double *cell_h, double uniform_h,
+                        const uint8_t *row_flags, const int64_t *hang_rowptr, const int32_t *hang_col,
+                        const double *hang_val, const double *k_ref);
+/* Raw CSR of a matrix handed over (gmg_set_matrix) or assembled (gmg_assemble_matrix) but not yet consumed by
+ * gmg_setup: *nnz always; rowptr[n_rows + 1] / col[nnz] / val[nnz] when non-NULL (call twice: sizes, then arrays).
+ * which = GMG_SYSTEM or GMG_LEVEL (level 0).  For tests and debugging. */
+int gmg_raw_matrix_get(gmg_handle h, int which, int level, int64_t *nnz, int64_t *rowptr, int32_t *col, double *val);
 /* MGLevelGlobalTransfer::copy_indices[level]: (global dof, level dof) pairs. */
 int gmg_set_copy_indices(gmg_handle h, int level, int32_t n, const int32_t *global_idx,
                          const int32_t *level_idx);
