@@ -246,7 +246,9 @@ static int assemble_matrix_device(gmg_context *h, int n_rows, int64_t n_cells, c
       GMG_LAUNCH_CHECK(h);
     }
   }
-  GMG_CUDA(h, cudaStreamSynchronize(h->stream));  // the host buffers are only borrowed; errors surface here
+  // no synchronisation here: the borrowed host buffers were consumed by the staged copies above, and the fill kernels
+  // overlap with the caller's next hand-over call (the host-side staging of the next matrix); gmg_setup orders after them
+  ts.reset();
   return GMG_OK;
 }
 
