@@ -69,37 +69,36 @@ __global__ void asm_cell_hanging(int64_t n_cells, const int32_t *cell_dofs, cons
 
 template <int MAXC, bool LARGE>
 __global__ void __launch_bounds__(128) asm_rows_count(AsmView A, uint8_t *large, unsigned long long *cnt, int *err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n_rows) return;
+  if (LARGE && !large[i]) return;
   int cols[MAXC];
-  // grid-stride: the launch keeps few threads resident per SM so that their column arrays stay in L1
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n_rows; i += gridDim.x * blockDim.x) {
-    if (LARGE && !large[i]) continue;
-    const int n = asm_row_pattern(A, i, cols, MAXC);
-    if (n < 0) {
-      if (LARGE) *err = 3;
-      else large[i] = 1;
-      cnt[i] = 0;
-      continue;
-    }
-    if (!LARGE) large[i] = 0;
-    cnt[i] = (unsigned long long)n;
+  const int n = asm_row_pattern(A, i, cols, MAXC);
+  if (n < 0) {
+    if (LARGE) *err = 3;
+    else large[i] = 1;
+    cnt[i] = 0;
+    return;
   }
+  if (!LARGE) large[i] = 0;
+  cnt[i] = (unsigned long long)n;
 }
 
 template <int MAXC, bool LARGE>
 __global__ void __launch_bounds__(128) asm_rows_fill(AsmView A, const uint8_t *large, const int64_t *rowptr, int *col,
                                                      double *val) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n_rows) return;
+  if (LARGE != (large[i] != 0)) return;
   int cols[MAXC];
   double vals[MAXC];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n_rows; i += gridDim.x * blockDim.x) {
-    if (LARGE != (large[i] != 0)) continue;
-    const int n = asm_row_pattern(A, i, cols, MAXC);
-    if (n < 0) continue;  // (cannot happen: the count pass has sized the row)
-    asm_row_values(A, i, cols, n, vals);
-    const int64_t at = rowptr[i];
-    for (int k = 0; k < n; ++k) {
-      col[at + k] = cols[k];
-      val[at + k] = vals[k];
-    }
+  const int n = asm_row_pattern(A, i, cols, MAXC);
+  if (n < 0) return;  // (cannot happen: the count pass has sized the row)
+  asm_row_values(A, i, cols, n, vals);
+  const int64_t at = rowptr[i];
+  for (int k = 0; k < n; ++k) {
+    col[at + k] = cols[k];
+    val[at + k] = vals[k];
   }
 }
 
@@ -112,10 +111,6 @@ static int assemble_matrix_device(gmg_context *h, int n_rows, int64_t n_cells, c
   free_csr(out);
   arena_reset(arena);
   const int64_t n_slots = 8 * n_cells;
-  // resident 128-thread blocks per SM of the row kernels (GMG_ASM_BLOCKS_PER_SM; 16 = full occupancy)
-  int bps = 4;
-  if (const char *e = std::getenv("GMG_ASM_BLOCKS_PER_SM")) bps = std::min(std::max(std::atoi(e), 1), 16);
-  const int row_blocks = std::max(1, std::min(cdiv(n_rows, 128), h->sm_count * bps));
   const int64_t n_hang = hang_rowptr ? hang_rowptr[n_rows] : 0;
   const bool hanging = n_hang > 0;
   AsmView A{};
@@ -226,10 +221,10 @@ static int assemble_matrix_device(gmg_context *h, int n_rows, int64_t n_cells, c
   GMG_CUDA(h, arena_alloc(arena, &d_large, n_rows));
   GMG_CUDA(h, cudaMemsetAsync(row_cnt + n_rows, 0, sizeof(unsigned long long), h->stream));  // (reused as the row widths)
   if (n_rows > 0) {
-    asm_rows_count<ASM_SMALL, false><<<row_blocks, 128, 0, h->stream>>>(A, d_large, row_cnt, d_err);
+    asm_rows_count<ASM_SMALL, false><<<cdiv(n_rows, 128), 128, 0, h->stream>>>(A, d_large, row_cnt, d_err);
     GMG_LAUNCH_CHECK(h);
     {
-      asm_rows_count<ASM_LARGE, true><<<row_blocks, 128, 0, h->stream>>>(A, d_large, row_cnt, d_err);
+      asm_rows_count<ASM_LARGE, true><<<cdiv(n_rows, 128), 128, 0, h->stream>>>(A, d_large, row_cnt, d_err);
       GMG_LAUNCH_CHECK(h);
     }
   }
@@ -244,10 +239,10 @@ static int assemble_matrix_device(gmg_context *h, int n_rows, int64_t n_cells, c
   GMG_CUDA(h, arena_alloc(arena, &out.col, out.nnz));
   GMG_CUDA(h, arena_alloc(arena, &out.val, out.nnz));
   if (n_rows > 0) {
-    asm_rows_fill<ASM_SMALL, false><<<row_blocks, 128, 0, h->stream>>>(A, d_large, out.rowptr, out.col, out.val);
+    asm_rows_fill<ASM_SMALL, false><<<cdiv(n_rows, 128), 128, 0, h->stream>>>(A, d_large, out.rowptr, out.col, out.val);
     GMG_LAUNCH_CHECK(h);
     {
-      asm_rows_fill<ASM_LARGE, true><<<row_blocks, 128, 0, h->stream>>>(A, d_large, out.rowptr, out.col, out.val);
+      asm_rows_fill<ASM_LARGE, true><<<cdiv(n_rows, 128), 128, 0, h->stream>>>(A, d_large, out.rowptr, out.col, out.val);
       GMG_LAUNCH_CHECK(h);
     }
   }

@@ -15,16 +15,11 @@ for name, fn in (("step_host(hierarchy)", lambda: B.step_host(True)), ("step_hos
                  ("step_device", B.step_device)):
     t = time.time(); fn(); B.gmg.synchronize()
     print("== %s: %.1f ms" % (name, 1e3 * (time.time() - t)), file=sys.stderr)
-# the same with the system / level-0 matrices assembled on the device (Matrix assembly = Device), for several
-# residencies of the row kernels (GMG_ASM_BLOCKS_PER_SM: 128-thread blocks per SM; default 4)
+# the same with the system / level-0 matrices assembled on the device (Matrix assembly = Device)
+os.environ.pop("GMG_TRACE", None)
 B.set_device_assembly(True)
-for bps in (os.environ.get("ASM_BPS_SWEEP", "4").split(",")):
-    os.environ["GMG_ASM_BLOCKS_PER_SM"] = bps
-    os.environ.pop("GMG_TRACE", None)
-    B.step_host(True)
-    B.step_host(True)
-    t = time.time(); B.step_host(True); B.gmg.synchronize()
-    print("== step_host(hierarchy, device assembly, %s blocks/SM) untraced: %.1f ms" % (bps, 1e3 * (time.time() - t)), file=sys.stderr)
-    os.environ["GMG_TRACE"] = "1"
-    t = time.time(); B.step_host(True); B.gmg.synchronize()
-    print("== step_host(hierarchy, device assembly, %s blocks/SM): %.1f ms" % (bps, 1e3 * (time.time() - t)), file=sys.stderr)
+B.step_host(True)
+B.step_host(True)
+os.environ["GMG_TRACE"] = "1"
+t = time.time(); B.step_host(True); B.gmg.synchronize()
+print("== step_host(hierarchy, device assembly): %.1f ms" % (1e3 * (time.time() - t)), file=sys.stderr)

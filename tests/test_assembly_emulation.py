@@ -50,3 +50,11 @@ def test_assembly_inputs_helper_matches_the_host_structures():
     assert flags0.sum() == 5 ** 3 - 3 ** 3  # the boundary dofs of the base lattice
     K = hostlib.unit_stiffness()
     assert np.allclose(K, K.T) and abs(K.sum()) < 1e-14 and abs(K[0, 0] - 1.0 / 3.0) < 1e-15
+
+
+def test_matrix_assembly_prm_key_is_declared_with_a_selection_pattern():
+    from conftest import make_prm
+    ok = "subsection Solver input data\n set Matrix assembly = Device\nend\n"
+    hostlib.check_prm(make_prm(extra=ok))
+    with pytest.raises(hostlib.HostError):
+        hostlib.check_prm(make_prm(extra=ok.replace("Device", "Elsewhere")))
