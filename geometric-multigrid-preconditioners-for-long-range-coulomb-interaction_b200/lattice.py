@@ -30,7 +30,7 @@ def write_lammps(path, pos, q):
 
 
 def cluster_prm(atom_file, n, cycles=5, smoother="MulticolourSSOR", indicator="Kelly", nq_param=1, cutoff=3.5,
-                vacuum=10, mesh_size=0.25, device=0):
+                vacuum=10, mesh_size=0.25, device=0, assembly="Host"):
     """The parameter file of the reference's cluster runs for the n^3-unit-cell lattice (domain [0, n])."""
     return f"""
 subsection Geometry
@@ -54,6 +54,7 @@ subsection Solver input data
   set Preconditioner = GMG
   set Smoother = {smoother}
   set GPU device = {device}
+  set Matrix assembly = {assembly}
 end
 subsection Problem Selection
   set Problem = GaussianCharges

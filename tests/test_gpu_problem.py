@@ -69,15 +69,18 @@ def test_main_executable_lattice_8_atoms_reproduces_cluster_log(tmp_path, golden
     assert its[0] == 1
 
 
-def test_64k_atoms_five_cycles_reproduce_cluster_log(tmp_path, goldens):
+@pytest.mark.parametrize("assembly", ["Host", "Device"])
+def test_64k_atoms_five_cycles_reproduce_cluster_log(tmp_path, goldens, assembly):
     """BASELINE config 4 at full size (atom_n20_64000, the SSOR_64k_atoms.o876224 run): cell / DoF counts per level,
     ||b||_2 of cycle 0, starting residuals and solution norms of all 5 cycles to the printed digits; CG iteration
-    counts within +-2 (the log ran 20-rank block SSOR; here: multicolour SSOR)."""
+    counts within +-2 (the log ran 20-rank block SSOR; here: multicolour SSOR).  assembly = Device: system and level-0
+    matrices of every cycle assembled on the GPU (gmg_assemble_matrix) instead of on the host."""
     P = pkg()
     pos, q = P.lattice.nacl_lattice(20)
     atom = tmp_path / "atom_n20_64000.data"
     P.lattice.write_lammps(str(atom), pos, q)
-    text, recs = hostlib.run_problem(P.lattice.cluster_prm(str(atom), 20, cycles=5, smoother="MulticolourSSOR"))
+    text, recs = hostlib.run_problem(P.lattice.cluster_prm(str(atom), 20, cycles=5, smoother="MulticolourSSOR",
+                                                             assembly=assembly))
     g = goldens["cluster_ssor_64k"][0]["cycles"]
     assert goldens["cluster_ssor_64k"][0]["n_atoms"] == 64000 and len(recs) == 5
     for c, (rec, gold) in enumerate(zip(recs, g)):
