@@ -17,6 +17,11 @@ ParameterReader::ParameterReader(ParameterHandler &paramhandler) : prm(paramhand
 void ParameterReader::declare_parameters() {
   // the reference's 19 entries, names / defaults / patterns unchanged (src/step-50.cc:15-95)
   prm.enter_subsection("Geometry");
+  // new: k > 0 builds the base lattice as k global refinements of a lattice 2^k times coarser, so the
+  // multigrid hierarchy continues below the base mesh and the coarse-grid CG runs on (reps / 2^k + 1)^3 dofs instead of
+  // (reps + 1)^3.  0 = the reference's hierarchy (coarse solve on the base lattice).
+  prm.declare_entry("Coarse levels below the base mesh", "0", Patterns::Integer(),
+                    "Number of geometric coarsenings of the base lattice added below it as multigrid levels");
   prm.declare_entry("Number of global refinement", "2", Patterns::Integer(),
                     "The uniform global mesh refinement on the Domain in the power of 4");
   prm.declare_entry("Domain limit left", "-1", Patterns::Double(), "Left limit of domain");
@@ -146,6 +151,9 @@ LaplaceProblem<dim>::LaplaceProblem(
     gpu_device = (int)prm.get_integer("GPU device");
     device_assembly = prm.get("Matrix assembly") == "Device";
     prm.leave_subsection();
+    prm.enter_subsection("Geometry");
+    coarse_levels_below_base = (int)prm.get_integer("Coarse levels below the base mesh");
+    prm.leave_subsection();
     prm.enter_subsection("Misc");
     energy_atom_limit = (unsigned int)prm.get_integer("Energy postprocessing atom limit");
     indicator_with_residual = prm.get("Refinement indicator") == "KellyAndResidual";
@@ -219,7 +227,13 @@ void LaplaceProblem<dim>::make_mesh() {
     const double M = repetitions_for_vacuum;
     const double repetitions_in_each_direction = 2 * (N + 2 * M);
     const unsigned int reps = (unsigned int)repetitions_in_each_direction;
-    triangulation.reset(new Forest((int)reps, domain_size_left - (M * a), domain_size_right + (M * a)));
+    const int k = coarse_levels_below_base;
+    if (k < 0 || k > 8 || (k > 0 && (reps % (1u << k)) != 0))
+      throw ExcMessage("Coarse levels below the base mesh: the base lattice (" + std::to_string(reps) +
+                       " cells per direction) is not divisible by 2^" + std::to_string(k));
+    // (hi - lo) / (reps / 2^k) / 2^k == (hi - lo) / reps bit for bit: level k IS the reference's base lattice
+    triangulation.reset(new Forest((int)(reps >> k), domain_size_left - (M * a), domain_size_right + (M * a)));
+    if (k > 0) triangulation->refine_global(k);
   }
 }
 
@@ -242,7 +256,7 @@ struct ActiveCells {
   std::vector<int32_t> dofs, list;
 };
 namespace {
-ActiveCells flatten(const Forest &f, const DoFs &d, bool with_lists) {
+ActiveCells flatten(const Forest &f, const DoFs &d, bool with_lists, int base_level) {
   ActiveCells a;
   for (int l = 0; l < f.n_levels(); ++l)
     for (size_t p = 0; p < d.active_cells[l].size(); ++p) {
@@ -253,7 +267,7 @@ ActiveCells flatten(const Forest &f, const DoFs &d, bool with_lists) {
       a.h.push_back(h);
       for (int v = 0; v < NV; ++v) a.dofs.push_back(d.cell_dofs[l][p][v]);
       int anc = c;
-      for (int k = l; k > 0; --k) anc = f.L[k].parent[anc];  // children inherit the parent's list (:441-449)
+      for (int k = l; k > base_level; --k) anc = f.L[k].parent[anc];  // children inherit the parent's list (:441-449)
       a.list.push_back(with_lists ? anc : -1);
     }
   return a;
@@ -265,10 +279,12 @@ template <int dim>
 void LaplaceProblem<dim>::rhs_assembly_optimization() {
   TimerOutput::Scope t(computing_timer, "RHS assembly optimization");
   const Forest &f = *triangulation;
-  const int n = f.n_cells(0);
-  std::vector<double> lo(3 * (size_t)n), h(n, f.H);
+  const int bl = base_level();  // the cells of the reference's base lattice (level 0 unless coarser levels were added)
+  const int n = f.n_cells(bl);
+  const double hb = f.h(bl);
+  std::vector<double> lo(3 * (size_t)n), h(n, hb);
   for (int c = 0; c < n; ++c)
-    for (int k = 0; k < 3; ++k) lo[3 * (size_t)c + k] = f.lo + f.L[0].ijk[c][k] * f.H;
+    for (int k = 0; k < 3; ++k) lo[3 * (size_t)c + k] = f.lo + f.L[bl].ijk[c][k] * hb;
   charges_list_ptr.assign(n + 1, 0);
   gmg_check(gmg_bin_atoms(gmg, n, lo.data(), h.data(), (int)number_of_atoms, atom_positions.data(),
                           nonzero_density_radius_parameter * r_c, charges_list_ptr.data(), nullptr),
@@ -352,7 +368,7 @@ void LaplaceProblem<dim>::setup_system(const unsigned int &cycle) {
   mg_dof_handler.reset(new DoFs(*triangulation));
   asm_flags_system.clear();
   asm_flags_level0.clear();
-  active_cells_cache.reset(new ActiveCells(flatten(*triangulation, *mg_dof_handler, flag_rhs_assembly)));
+  active_cells_cache.reset(new ActiveCells(flatten(*triangulation, *mg_dof_handler, flag_rhs_assembly, base_level())));
   solution.assign(mg_dof_handler->n, 0.0);
   system_rhs.assign(mg_dof_handler->n, 0.0);
   if ((cycle == 0) && flag_rhs_assembly && lammpsinput) rhs_assembly_optimization();
@@ -459,6 +475,7 @@ void LaplaceProblem<dim>::hand_over_hierarchy() {
   gmg_dist_rank(gmg, &dist_rank, &dist_world);
   if (dist_world > 1) {
     if (!mg) throw ExcMessage("the multi-GPU path implements the GMG preconditioner");
+    if (base_level() > 0) throw ExcMessage("the multi-GPU path partitions level 0 = the base lattice (Coarse levels below the base mesh = 0)");
     const int res = triangulation->resolution();
     const int planes = triangulation->reps + 1;
     auto slab = [&](int z_fine) { return std::min(dist_world - 1, (int)(((long)(z_fine >> res)) * dist_world / planes)); };

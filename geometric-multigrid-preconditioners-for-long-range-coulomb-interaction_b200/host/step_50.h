@@ -150,6 +150,9 @@ class LaplaceProblem {
   // Matrix assembly = Device: the system matrix and the level-0 matrix are assembled on the GPU from the cell -> dof
   // maps (gmg_assemble_matrix: the same CSR, bit for bit) instead of on the host; patch levels stay on the host
   bool device_assembly = false;
+  // Coarse levels below the base mesh (0 = the reference's hierarchy): level base_level() is the base lattice
+  int coarse_levels_below_base = 0;
+  int base_level() const { return Problemtype == "Step16" ? 0 : coarse_levels_below_base; }
   std::vector<uint8_t> asm_flags_system, asm_flags_level0;  // row flags of gmg_assemble_matrix, built once per mesh
   bool assemble_on_device() const { return device_assembly && Problemtype != "Step16" && PreconditionerType == "GMG"; }
 

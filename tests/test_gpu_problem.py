@@ -103,3 +103,32 @@ def test_missing_parameter_file_and_bad_device_fail_loudly(tmp_path):
     extra = "subsection Solver input data\n set GPU device = 99\nend\n"
     with pytest.raises(hostlib.HostError, match="no CPU fallback"):
         hostlib.run_problem(make_prm(cycles=1, extra=extra))
+
+
+def test_coarse_levels_below_the_base_mesh_same_problem_fewer_coarse_iterations(tmp_path):
+    """`Coarse levels below the base mesh = 2` on atom_n1_8 with the cluster parameters (base lattice 44^3
+    = 4 x 11^3): same meshes, load vectors and solutions as the reference hierarchy (the dof numbering differs, so norms
+    agree to rounding / to the CG tolerance); the coarse-grid CG now runs on 12^3 instead of 45^3 dofs."""
+    P = pkg()
+    atom = os.path.join(GOLDEN, "atom_n1_8.data")
+    _, ref = hostlib.run_problem(P.lattice.cluster_prm(atom, 1, cycles=3, smoother="MulticolourSSOR"))
+    extra = "subsection Geometry\n set Coarse levels below the base mesh = 2\nend\n"
+    _, mg = hostlib.run_problem(P.lattice.cluster_prm(atom, 1, cycles=3, smoother="MulticolourSSOR") + extra)
+    assert len(mg) == len(ref) == 3
+    for a, b in zip(mg, ref):
+        assert a["n_active_cells"] == b["n_active_cells"] and a["n_dofs"] == b["n_dofs"]
+        assert a["n_dofs_level"][:2] == [12 ** 3, 23 ** 3] and a["n_dofs_level"][2:] == b["n_dofs_level"]
+        for k in ("rhs_l1", "rhs_l2", "rhs_linf", "mat_l1", "mat_linf", "mat_frob"):
+            assert abs(a[k] - b[k]) <= 1e-12 * abs(b[k]), k
+        assert abs(a["start"] - b["start"]) <= 1e-9 * abs(b["start"]) + 1e-12
+        for k in ("sol_l1", "sol_l2", "sol_linf"):
+            assert abs(a[k] - b[k]) <= 2e-7 * abs(b[k]), k
+        assert abs(a["threshold"] - b["threshold"]) <= 1e-5 * abs(b["threshold"])
+        assert a["its"] <= b["its"] + 6
+        assert max(a["coarse_its"]) < max(b["coarse_its"])
+    out = os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "coarse_levels.json"), "w") as f:
+            import json
+            json.dump({"reference_hierarchy": [{k: r[k] for k in ("its", "coarse_its", "solve_seconds")} for r in ref],
+                       "two_coarse_levels": [{k: r[k] for k in ("its", "coarse_its", "solve_seconds")} for r in mg]}, f)
