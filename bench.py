@@ -46,6 +46,9 @@ def parse_args():
     ap.add_argument("--assembly", default="device", choices=["device", "host"],
                     help="e2e leg: system / level-0 matrices assembled on the device at the hand-over (default) or handed over "
                          "assembled (always measured as well)")
+    ap.add_argument("--coarse-levels", type=int, default=0,
+                    help="experimental (SURVEY 8f N4): multigrid levels below the base lattice; 0 = the reference's hierarchy "
+                         "(the headline workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     return ap.parse_args()
@@ -64,6 +67,9 @@ def workload_config(args, extra=None):
                       "the RHS over 1.85 M cells / 118 M cell-atom pairs, so no coarse solve starts with a warm L2; inside a coarse "
                       "solve the row-pattern CG keeps its 57 MB working set L2-resident by design",
     }
+    if getattr(args, "coarse_levels", 0):
+        cfg["coarse"] = (f"EXPERIMENTAL, not the reference's algorithm: {args.coarse_levels} multigrid levels below the base "
+                         f"lattice, CG on the coarsest to 1e-10")
     if extra:
         cfg.update(extra)
     return cfg
@@ -162,7 +168,8 @@ def run_b200(args):
     P.load_library()
     atom_file, pos, q = write_atoms(args)
     t0 = time.time()
-    prm = P.lattice.cluster_prm(atom_file, args.atoms_n, cycles=args.cycles, smoother=args.smoother, device=local)
+    prm = P.lattice.cluster_prm(atom_file, args.atoms_n, cycles=args.cycles, smoother=args.smoother, device=local,
+                                coarse_levels=args.coarse_levels)
     connect = None
     if world > 1:
         def connect(gmg):

@@ -30,7 +30,7 @@ def write_lammps(path, pos, q):
 
 
 def cluster_prm(atom_file, n, cycles=5, smoother="MulticolourSSOR", indicator="Kelly", nq_param=1, cutoff=3.5,
-                vacuum=10, mesh_size=0.25, device=0, assembly="Host"):
+                vacuum=10, mesh_size=0.25, device=0, assembly="Host", coarse_levels=0):
     """The parameter file of the reference's cluster runs for the n^3-unit-cell lattice (domain [0, n])."""
     return f"""
 subsection Geometry
@@ -39,6 +39,7 @@ subsection Geometry
   set Domain limit right = {n}
   set Mesh size = {mesh_size}
   set Vacuum repetitions = {vacuum}
+  set Coarse levels below the base mesh = {coarse_levels}
 end
 subsection Misc
   set Number of Adaptive Refinement = {cycles}
