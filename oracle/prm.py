@@ -8,6 +8,9 @@ DECLARED = {
     ("Geometry", "Domain limit right"): ("1", "double"),
     ("Geometry", "Mesh size"): ("0.25", "double"),
     ("Geometry", "Vacuum repetitions"): ("1", "int"),
+    # not a key of the reference: the product's optional deeper hierarchy, restated here so that the
+    # option has an oracle too; 0 = the reference's behaviour
+    ("Geometry", "Coarse levels below the base mesh"): ("0", "int"),
     ("Problem Selection", "Problem"): ("Step16", ("Step16", "GaussianCharges")),
     ("Problem Selection", "Dimension"): ("2", "int"),
     ("Problem Selection", "Boundary conditions selection"): ("Inhomogeneous", ("Homogeneous", "Inhomogeneous", "Exact")),

@@ -40,6 +40,7 @@ class LaplaceProblem:
         self.left, self.right = g("Geometry", "Domain limit left"), g("Geometry", "Domain limit right")
         self.mesh_h = g("Geometry", "Mesh size")
         self.vacuum = g("Geometry", "Vacuum repetitions")
+        self.coarse_levels = p.get(("Geometry", "Coarse levels below the base mesh"), 0)
         self.n_cycles = g("Misc", "Number of Adaptive Refinement")
         self.r_c = g("Misc", "smoothing length")
         self.cutoff = g("Misc", "Nonzero Density radius parameter around each charge")
@@ -83,7 +84,14 @@ class LaplaceProblem:
             N = (self.right - self.left) / a
             M = self.vacuum
             reps = int(2 * (N + 2 * M))
-            self.forest = Forest(reps, self.left - M * a, self.right + M * a, self.dim)
+            k = self.coarse_levels  # the product's optional deeper hierarchy: level k is the reference's base lattice
+            assert reps % (1 << k) == 0
+            self.forest = Forest(reps >> k, self.left - M * a, self.right + M * a, self.dim)
+            if k:
+                self.forest.refine_global(k)
+
+    def base_level(self):
+        return 0 if self.problem == "Step16" else self.coarse_levels
 
     def boundary_values(self):
         d = self.dofs
@@ -111,9 +119,10 @@ class LaplaceProblem:
     def setup_system(self, cycle):
         self.dofs = DoFs(self.forest)
         if cycle == 0 and self.flag_rhs and self.lammps:
-            self.lists0 = rhs.bin_atoms_base(self.forest, self.pos, self.cutoff * self.r_c)
+            self.lists0 = rhs.bin_atoms_base(self.forest, self.pos, self.cutoff * self.r_c,
+                                             base_level=self.base_level())
         if self.lammps:
-            self.lists = rhs.inherit_lists(self.forest, self.lists0) if self.flag_rhs else None
+            self.lists = rhs.inherit_lists(self.forest, self.lists0, self.base_level()) if self.flag_rhs else None
             self.dens = rhs.charge_densities(self.forest, self.dofs, self.pos, self.charges, self.r_c, self.nq_rhs,
                                              self.lists)
         self.g = self.boundary_values()

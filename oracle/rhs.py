@@ -11,12 +11,13 @@ import numpy as np
 from . import fe
 
 
-def bin_atoms_base(forest, pos, radius, chunk=256):
+def bin_atoms_base(forest, pos, radius, chunk=256, base_level=0):
     """Cell k of level 0 lists atom i iff some vertex v of the cell has ||X_i - v||_2 < radius
     (strict, src/step-50.cc:278-283).  Returns CSR (ptr, idx) with ascending atom indices per cell
-    (std::set iteration order)."""
+    (std::set iteration order).  base_level > 0 (the product's `Coarse levels below the base mesh`): the base lattice
+    is level `base_level` of the forest (all of its cells exist); the lists are returned in that level's cell order."""
     assert forest.dim == 3
-    reps, H, lo = forest.reps, forest.H, forest.lo
+    reps, H, lo = forest.reps << base_level, forest.h(base_level), forest.lo
     nv = reps + 1
     w = int(math.ceil(radius / H)) + 1
     cells, atoms = [], []
@@ -45,9 +46,19 @@ def bin_atoms_base(forest, pos, radius, chunk=256):
     atoms = np.concatenate(atoms) if atoms else np.zeros(0, dtype=np.int64)
     order = np.lexsort((atoms, cells))
     cells, atoms = cells[order], atoms[order]
-    ptr = np.zeros(forest.n_cells(0) + 1, dtype=np.int64)
+    ptr = np.zeros(reps ** 3 + 1, dtype=np.int64)
     np.add.at(ptr, cells + 1, 1)
-    return np.cumsum(ptr), atoms.astype(np.int64)
+    ptr, atoms = np.cumsum(ptr), atoms.astype(np.int64)
+    if base_level == 0:
+        return ptr, atoms
+    # lexicographic lattice index -> cell order of the forest's level `base_level`
+    ijk = forest.ijk[base_level].astype(np.int64)
+    assert len(ijk) == reps ** 3
+    lex = ijk[:, 0] + reps * (ijk[:, 1] + reps * ijk[:, 2])
+    cnt = ptr[lex + 1] - ptr[lex]
+    out_ptr = np.concatenate([[0], np.cumsum(cnt)])
+    src = np.repeat(ptr[lex], cnt) + (np.arange(out_ptr[-1]) - np.repeat(out_ptr[:-1], cnt))
+    return out_ptr, atoms[src]
 
 
 def bin_atoms_bruteforce(forest, pos, radius):
@@ -62,10 +73,12 @@ def bin_atoms_bruteforce(forest, pos, radius):
     return np.array(ptr, dtype=np.int64), np.concatenate(idx).astype(np.int64)
 
 
-def inherit_lists(forest, lists0):
-    """Per-level CSR lists: every cell of level l+1 copies its parent's list (src/step-50.cc:441-449)."""
-    out = [lists0]
-    for l in range(1, forest.n_levels):
+def inherit_lists(forest, lists0, base_level=0):
+    """Per-level CSR lists: every cell of level l+1 copies its parent's list (src/step-50.cc:441-449).  Levels below
+    `base_level` (never active) get empty lists."""
+    out = [(np.zeros(forest.n_cells(l) + 1, dtype=np.int64), np.zeros(0, dtype=np.int64)) for l in range(base_level)]
+    out.append(lists0)
+    for l in range(base_level + 1, forest.n_levels):
         pptr, pidx = out[l - 1]
         par = forest.parent[l]
         cnt = pptr[par + 1] - pptr[par]

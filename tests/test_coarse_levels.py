@@ -66,3 +66,49 @@ def test_prm_key_is_declared_and_validated():
     hostlib.check_prm(make_prm(extra=ok))
     with pytest.raises(hostlib.HostError):
         hostlib.check_prm(make_prm(extra=ok.replace("= 2", "= two")))
+
+
+def test_oracle_and_host_agree_on_the_coarsened_hierarchy_and_the_solution_is_the_reference_one():
+    """The oracle restates the option too: with 2 coarse levels below the base mesh of the 2-atom golden case it produces,
+    on cycle 1 (hanging nodes present), the forest / numbering / constraints ministep produces (bit-exact), the load
+    vector of the reference hierarchy (norms to rounding) and the same solution (to the CG tolerance)."""
+    from helpers import oracle_cycle
+    two = dict(bc="Exact", atom="atom_n1_2.data", nq=4)
+    ref = oracle_cycle(make_prm(cycles=2, **two), 1, smoother="jacobi")
+    extra = "subsection Geometry\n set Coarse levels below the base mesh = 2\nend\n"
+    P = oracle_cycle(make_prm(cycles=2, extra=extra, **two), 1, smoother="jacobi")
+    f, d = P.forest, P.dofs
+    assert f.n_levels == ref.forest.n_levels + 2 and list(d.level_n[:3]) == [12 ** 3, 23 ** 3, 45 ** 3]
+    assert list(d.level_n[2:]) == list(ref.dofs.level_n)
+    # host substrate on the same flags
+    M = hostlib.Ministep(f.reps, f.lo, f.hi)
+    M.refine_global(2)
+    for flags in P.flag_history[:1]:
+        M.refine(flags)
+    M.build()
+    assert M.n_levels == f.n_levels
+    for l in range(M.n_levels):
+        assert np.array_equal(M.get("ijk", l).reshape(-1, 3), f.ijk[l])
+        assert np.array_equal(M.get("cell_dofs", l).reshape(-1, 8), d.cell_dofs[l])
+        assert np.array_equal(M.get("level_cell_dofs", l).reshape(-1, 8), d.level_cell_dofs[l])
+        assert np.array_equal(M.get("copy_global", l), d.copy_global[l])
+    assert np.array_equal(M.get("dof_xyz").reshape(-1, 3), d.xyz)
+    assert np.array_equal(M.get("hanging").astype(bool), d.hanging)
+    # same problem as the reference hierarchy
+    a, b = P.records[-1], ref.records[-1]
+    assert a["n_active_cells"] == b["n_active_cells"] and a["n_dofs"] == b["n_dofs"]
+    for k in ("rhs_l1", "rhs_l2", "rhs_linf", "mat_l1", "mat_linf", "mat_frob"):
+        assert abs(a[k] - b[k]) <= 1e-12 * abs(b[k]), k
+    for k in ("sol_l1", "sol_l2", "sol_linf"):
+        assert abs(a[k] - b[k]) <= 2e-7 * abs(b[k]), k
+    assert abs(a["its"] - b["its"]) <= 2 and max(a["coarse_its"]) < max(b["coarse_its"])
+    # the same cells carry the same atom lists (sets of atoms per active cell, compared through cell centres)
+    def lists_by_centre(Q):
+        out = {}
+        for l in range(Q.forest.n_levels):
+            ptr, idx = Q.lists[l]
+            for c in Q.dofs.active_cells[l]:
+                key = tuple(np.round((Q.forest.lo + (Q.forest.ijk[l][c] + 0.5) * Q.forest.h(l)) * 64).astype(int))
+                out[key] = tuple(idx[ptr[c]:ptr[c + 1]])
+        return out
+    assert lists_by_centre(P) == lists_by_centre(ref)
