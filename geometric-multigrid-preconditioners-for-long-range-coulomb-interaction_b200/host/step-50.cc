@@ -368,6 +368,7 @@ void LaplaceProblem<dim>::setup_system(const unsigned int &cycle) {
   mg_dof_handler.reset(new DoFs(*triangulation));
   asm_flags_system.clear();
   asm_flags_level0.clear();
+  rhs_constrained.clear();
   active_cells_cache.reset(new ActiveCells(flatten(*triangulation, *mg_dof_handler, flag_rhs_assembly, base_level())));
   solution.assign(mg_dof_handler->n, 0.0);
   system_rhs.assign(mg_dof_handler->n, 0.0);
@@ -439,10 +440,16 @@ void LaplaceProblem<dim>::assemble_rhs_on_device() {
   }
   double Kref[NV][NV];
   unit_stiffness(Kref);
-  std::vector<double> ghat = resolve_inhomogeneity(d, boundary_g);
-  bool inhom = false;
-  for (double v : ghat) inhom |= v != 0.0;
-  std::vector<uint8_t> constrained(d.constrained.begin(), d.constrained.end());
+  // derived per mesh (setup_system clears them): resolved inhomogeneities and the constraint flags as bytes
+  if ((int)rhs_constrained.size() != d.n) {
+    rhs_ghat = resolve_inhomogeneity(d, boundary_g);
+    rhs_inhom = false;
+    for (double v : rhs_ghat) rhs_inhom |= v != 0.0;
+    rhs_constrained.assign(d.constrained.begin(), d.constrained.end());
+  }
+  const std::vector<double> &ghat = rhs_ghat;
+  const bool inhom = rhs_inhom;
+  const std::vector<uint8_t> &constrained = rhs_constrained;
   gmg_check(gmg_assemble_rhs(gmg, nc, rho, a.h.data(), a.dofs.data(), nq3, shape.data(), weights.data(),
                              inhom ? &Kref[0][0] : nullptr, inhom ? ghat.data() : nullptr, d.n, d.hang.rowptr.data(),
                              d.hang.col.data(), d.hang.val.data(), constrained.data(), system_rhs.data()),

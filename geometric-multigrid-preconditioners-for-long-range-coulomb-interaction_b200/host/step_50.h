@@ -153,6 +153,9 @@ class LaplaceProblem {
   // Coarse levels below the base mesh (0 = the reference's hierarchy): level base_level() is the base lattice
   int coarse_levels_below_base = 0;
   int base_level() const { return Problemtype == "Step16" ? 0 : coarse_levels_below_base; }
+  std::vector<double> rhs_ghat;          // inhomogeneities resolved through the hanging-node lines, per mesh
+  std::vector<uint8_t> rhs_constrained;  // constraints.is_constrained(i) as bytes, per mesh
+  bool rhs_inhom = false;
   std::vector<uint8_t> asm_flags_system, asm_flags_level0;  // row flags of gmg_assemble_matrix, built once per mesh
   bool assemble_on_device() const { return device_assembly && Problemtype != "Step16" && PreconditionerType == "GMG"; }
 
