@@ -223,16 +223,17 @@ static int assemble_matrix_device(gmg_context *h, int n_rows, int64_t n_cells, c
   if (n_rows > 0) {
     asm_rows_count<ASM_SMALL, false><<<cdiv(n_rows, 128), 128, 0, h->stream>>>(A, d_large, row_cnt, d_err);
     GMG_LAUNCH_CHECK(h);
-    {
-      asm_rows_count<ASM_LARGE, true><<<cdiv(n_rows, 128), 128, 0, h->stream>>>(A, d_large, row_cnt, d_err);
-      GMG_LAUNCH_CHECK(h);
-    }
+    asm_rows_count<ASM_LARGE, true><<<cdiv(n_rows, 128), 128, 0, h->stream>>>(A, d_large, row_cnt, d_err);  // flagged rows
+    GMG_LAUNCH_CHECK(h);
   }
   GMG_CUDA(h, cub::DeviceScan::ExclusiveSum(tmp, scan_bytes, row_cnt, (unsigned long long *)out.rowptr, n_rows + 1,
                                             h->stream));
   GMG_CUDA(h, copy(h, &out.nnz, out.rowptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost));
   GMG_CUDA(h, copy_sync(h, &err, d_err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (err == 3) return fail(h, GMG_EINVAL, "gmg_assemble_matrix: a row has more than 320 columns");
+  if (err == 3) {
+    out = DevCsr{};  // (arena memory: nothing to free)
+    return fail(h, GMG_EINVAL, "gmg_assemble_matrix: a row has more than 320 columns");
+  }
   // ---- columns and values
   ts.reset();
   ts.reset(new TraceScope("  asm: columns + values"));
@@ -241,10 +242,8 @@ static int assemble_matrix_device(gmg_context *h, int n_rows, int64_t n_cells, c
   if (n_rows > 0) {
     asm_rows_fill<ASM_SMALL, false><<<cdiv(n_rows, 128), 128, 0, h->stream>>>(A, d_large, out.rowptr, out.col, out.val);
     GMG_LAUNCH_CHECK(h);
-    {
-      asm_rows_fill<ASM_LARGE, true><<<cdiv(n_rows, 128), 128, 0, h->stream>>>(A, d_large, out.rowptr, out.col, out.val);
-      GMG_LAUNCH_CHECK(h);
-    }
+    asm_rows_fill<ASM_LARGE, true><<<cdiv(n_rows, 128), 128, 0, h->stream>>>(A, d_large, out.rowptr, out.col, out.val);
+    GMG_LAUNCH_CHECK(h);
   }
   // no synchronisation here: the borrowed host buffers were consumed by the staged copies above, and the fill kernels
   // overlap with the caller's next hand-over call (the host-side staging of the next matrix); gmg_setup orders after them
