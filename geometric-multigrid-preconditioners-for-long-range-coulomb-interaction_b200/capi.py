@@ -65,6 +65,7 @@ SIGNATURES = {
     "gmg_cg_solve_dev": (_i, [_h, _i, _i, C.c_void_p, C.c_void_p, _i, _d, C.POINTER(_i), _pd]),
     "gmg_matrix_traffic": (_i, [_h, _i, _i, _pd]),
     "gmg_pair_energies": (_i, [_h, _d, _pd]),
+    "gmg_energy_norm_error": (_i, [_h, _pd, C.c_int32, _d, _pd, _pd, _pd]),
     "gmg_error_indicator": (_i, [_h, _i, _pi32, _pu8, _i, _pi32, _pd, _i, _pd, _i, _pd, _pd, C.POINTER(C.c_float),
                                  C.POINTER(C.c_float)]),
     "gmg_debug_cg_phases": (_i, [_h, _i, _pd]),
@@ -350,6 +351,12 @@ class Gmg:
         out = np.zeros(2)
         self._ck(self.lib.gmg_pair_energies(self.h, float(r_c), _pd_of(out)))
         return dict(analytic=out[0], short=out[1])
+
+    def energy_norm_error(self, u, r_c, gauss2_points, gauss2_weights):
+        u, gp, gw = _f64(u), _f64(gauss2_points), _f64(gauss2_weights)
+        out = np.zeros(1)
+        self._ck(self.lib.gmg_energy_norm_error(self.h, _pd_of(u), len(u), float(r_c), _pd_of(gp), _pd_of(gw), _pd_of(out)))
+        return float(out[0])
 
     def debug_cg_phases(self, block_plus_1=1):
         out = np.zeros(16)

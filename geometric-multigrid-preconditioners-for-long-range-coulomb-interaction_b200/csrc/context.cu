@@ -538,13 +538,16 @@ static int build_pat(gmg_context *h, Sell &s) {
                                                                 np, s.pat, irregular, d_count + 1);
   GMG_LAUNCH_CHECK(h);
   // remainder rows, ascending
+  // (selected into scratch sized for every row: a row that fails its entry-wise verification is flagged on top of the
+  // rows the table does not cover, and the count is only known afterwards)
   const int n_rem_max = (int)((int64_t)n - covered);
-  GMG_CUDA(h, dalloc(&s.rem_rows, n_rem_max));
+  int *rem_all = nullptr;
+  GMG_CUDA(h, arena_alloc(h->scratch, &rem_all, (int64_t)n));
   size_t tmp_bytes = 0;
   thrust::counting_iterator<int> iota(0);
-  GMG_CUDA(h, cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, irregular, s.rem_rows, d_count + 2, n, h->stream));
+  GMG_CUDA(h, cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, irregular, rem_all, d_count + 2, n, h->stream));
   GMG_CUDA(h, arena_alloc(h->scratch, (char **)&cub_tmp, (int64_t)tmp_bytes));
-  GMG_CUDA(h, cub::DeviceSelect::Flagged(cub_tmp, tmp_bytes, iota, irregular, s.rem_rows, d_count + 2, n, h->stream));
+  GMG_CUDA(h, cub::DeviceSelect::Flagged(cub_tmp, tmp_bytes, iota, irregular, rem_all, d_count + 2, n, h->stream));
   int flags[4] = {0, 0, 0, 0};
   GMG_CUDA(h, copy_sync(h, flags, d_count, 4 * sizeof(int), cudaMemcpyDeviceToHost));
   const int n_rem = flags[2];
@@ -552,6 +555,8 @@ static int build_pat(gmg_context *h, Sell &s) {
     drop();
     return GMG_OK;
   }
+  GMG_CUDA(h, dalloc(&s.rem_rows, n_rem));
+  GMG_CUDA(h, copy(h, s.rem_rows, rem_all, sizeof(int) * (size_t)n_rem, cudaMemcpyDeviceToDevice));
   const int rs = cdiv(n_rem, SLICE);
   std::vector<int64_t> rsp(rs + 1, 0);
   if (rs > 0) {
@@ -1527,7 +1532,12 @@ int gmg_set_matrix(gmg_handle h, int which, int level, int32_t n_rows, int32_t n
       h->dist.hS = make_host(n_rows, n_cols, rowptr, col, val);
       return GMG_OK;
     }
-    return upload_csr(h, n_rows, n_cols, rowptr, col, val, h->rawS, &h->upload[0]);
+    const int rc = upload_csr(h, n_rows, n_cols, rowptr, col, val, h->rawS, &h->upload[0]);
+    if (rc != GMG_OK) {  // no half-handed-over state: the previous system matrix must not be used with the new size
+      free_sell(h->S);
+      h->n_sys = 0;
+    }
+    return rc;
   }
   if (level < 0 || level >= h->n_levels) return fail(h, GMG_EINVAL, "level out of range (call gmg_set_num_levels)");
   Level &L = h->levels[level];
@@ -1565,8 +1575,13 @@ int gmg_assemble_matrix(gmg_handle h, int which, int level, int32_t n_rows, int6
   h->is_setup = false;
   if (which == GMG_SYSTEM) {
     h->n_sys = n_rows;
-    return assemble_matrix_device(h, n_rows, n_cells, cell_dofs, cell_h, uniform_h, row_flags, hang_rowptr, hang_col,
-                                  hang_val, k_ref, h->rawS, h->upload[0]);
+    const int rc = assemble_matrix_device(h, n_rows, n_cells, cell_dofs, cell_h, uniform_h, row_flags, hang_rowptr, hang_col,
+                                          hang_val, k_ref, h->rawS, h->upload[0]);
+    if (rc != GMG_OK) {
+      free_sell(h->S);
+      h->n_sys = 0;
+    }
+    return rc;
   }
   if (which != GMG_LEVEL || level != 0)
     return fail(h, GMG_EINVAL, "gmg_assemble_matrix: the system matrix and the level-0 matrix are assembled on the device; "
@@ -1873,6 +1888,8 @@ int gmg_setup(gmg_handle h) {
     h->cg_n = cg_n;
   }
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (!h->dist.on && h->S.valid && h->S.v.n_rows != h->n_sys)
+    return fail(h, GMG_EINVAL, "system matrix on the device does not match the announced size (failed hand-over?)");
   h->is_setup = true;
   return GMG_OK;
 }
@@ -1918,6 +1935,7 @@ int gmg_pcg_solve(gmg_handle h, const double *b, double *x, int max_it, double a
 int gmg_pcg_solve_jacobi(gmg_handle h, const double *b, double *x, double omega, int max_it, double abs_tol, int *iters,
                          double *res0, double *res_final) {
   if (!h || !b || !x || !h->S.valid) return h ? fail(h, GMG_EINVAL, "Jacobi-preconditioned CG needs the single-GPU system matrix") : GMG_EINVAL;
+  if (!h->is_setup || h->S.v.n_rows != h->n_sys) return fail(h, GMG_EINVAL, "gmg_setup has not been called");
   gmg::enter(h);
   const int n = h->n_sys;
   if (int rc = with_host_vectors(h, n, b, n, x, true)) return rc;

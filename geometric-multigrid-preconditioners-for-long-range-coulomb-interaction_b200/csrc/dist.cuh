@@ -125,7 +125,7 @@ __global__ void vec_take(int n, const int *__restrict__ idx, const double *__res
 
 // ---- "LL" words (as in NCCL's low-latency protocol): 8-byte stores carry 4 bytes of payload and a 4-byte tag,
 // so the payload needs no fence and no separate flag: a double travels as two tagged words in one 16-byte store.
-constexpr size_t DIST_OFF_LLRED = 4096;  // uint64 llred[2][8][2] in the header
+constexpr size_t DIST_OFF_LLRED = 4096;  // uint64 llred[4][8][2] in the header: [launch parity * 2 + reduction parity][rank]
 __device__ __forceinline__ void ll_store(uint64_t *p /*16-byte aligned pair*/, double v, uint32_t tag) {
   const uint64_t bits = (uint64_t)__double_as_longlong(v);
   const uint64_t w0 = ((uint64_t)tag << 32) | (bits & 0xffffffffull);
@@ -222,7 +222,11 @@ __global__ void __launch_bounds__(BLOCK, 2) cg_persistent_dist(MAT A, const doub
     if (aborted) return 0.0;
     ++nred;
     const uint32_t tag = D.tag_base + nred;
-    const int par = (int)(nred & 1);
+    // Slot group = launch parity x reduction parity.  Reductions restart at 1 in every launch, and a slow peer block may
+    // still be reading the LAST reduction of launch k when a fast rank starts launch k + 1: consecutive launches use
+    // disjoint slot groups, and a rank cannot be two launches ahead (its reductions of launch k + 1 need every peer's
+    // contribution of launch k + 1), so a slot is never rewritten while a peer still polls it for an older tag.
+    const int par = (int)(((D.tag_base >> 20) & 1u) * 2u + (nred & 1u));
     if (warp == 0) {
       if (blockIdx.x == 0) {
         const double s = warp_sum_partials(partials, nb);

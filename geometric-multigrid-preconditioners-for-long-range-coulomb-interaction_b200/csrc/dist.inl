@@ -353,8 +353,12 @@ static int dist_coarse_cg(gmg_context *h, const double *b, double *x) {
   D.send_block_ptr = d.cg_send_block_ptr;
   D.region_d = d.reg_cg_d;
   D.region_ll = d.reg_cg_ll;
-  D.tag_base = (uint32_t)(((++d.launch_id) & 0xfffu) << 20);  // tags stay unique for 4095 launches in a row, never 0
-  if (D.tag_base == 0) D.tag_base = (uint32_t)(((++d.launch_id) & 0xfffu) << 20);
+  // 12-bit launch id in the tag: a tag repeats only after 4096 launches, by when every slot it was used on has been
+  // overwritten hundreds of times (each launch rewrites its reduction slots and the whole halo area); 0 is skipped in a
+  // way that keeps the parity alternating (ids run 1, 2, ..., 4095, 4098 -> 2 would repeat: skip two at the wrap)
+  d.launch_id++;
+  if ((d.launch_id & 0xfffu) == 0) d.launch_id += 2;
+  D.tag_base = (uint32_t)((d.launch_id & 0xfffu) << 20);
   int max_it = h->coarse_max_it;
   double tol = h->coarse_tol;
   int grid = d.cg_grid;

@@ -99,6 +99,77 @@ __global__ void __launch_bounds__(PAIR_BLOCK) pair_energy_kernel(int n, const do
   }
 }
 
+// postprocess_error_in_energy_norm (src/step-50.cc:1423-1461): sqrt(sum_cells sum_q |grad u_h - grad u_exact|^2 JxW) with
+// QGauss<3>(2) and the exact gradient summed over ALL atoms (O(cells * 8 * atoms), the reference runs it every cycle).
+// One thread per (cell, quadrature point), atoms streamed through shared memory in tiles; per-block partial sums are
+// added on the host in block order.
+constexpr int ENORM_BLOCK = 128;
+__global__ void __launch_bounds__(ENORM_BLOCK) energy_norm_kernel(int n_cells, const double *__restrict__ cell_lo,
+                                                                    const double *__restrict__ cell_h, const int *__restrict__ cell_dofs,
+                                                                    const double *__restrict__ u, int n_atoms,
+                                                                    const double *__restrict__ pos, const double *__restrict__ q,
+                                                                    double r_c, double g0, double g1, double w0, double w1,
+                                                                    double *__restrict__ partial) {
+  __shared__ double sx[ENORM_BLOCK], sy[ENORM_BLOCK], sz[ENORM_BLOCK], sq[ENORM_BLOCK];
+  __shared__ double red[ENORM_BLOCK / 32];
+  const int64_t t = (int64_t)blockIdx.x * ENORM_BLOCK + threadIdx.x;
+  const int c = (int)(t >> 3), qp = (int)(t & 7);
+  const bool on = c < n_cells;
+  const int qx = qp & 1, qy = (qp >> 1) & 1, qz = qp >> 2;
+  const double xi[3] = {qx ? g1 : g0, qy ? g1 : g0, qz ? g1 : g0};
+  const double wq = (qx ? w1 : w0) * (qy ? w1 : w0) * (qz ? w1 : w0);
+  double gh[3] = {0.0, 0.0, 0.0}, x[3] = {0.0, 0.0, 0.0}, h = 1.0;
+  if (on) {
+    h = cell_h[c];
+    for (int v = 0; v < 8; ++v) {
+      const double uv = u[cell_dofs[8 * (size_t)c + v]];
+      for (int g = 0; g < 3; ++g) {
+        double w = 1.0;
+        for (int k = 0; k < 3; ++k) {
+          const bool hi = (v >> k) & 1;
+          w *= (k == g) ? (hi ? 1.0 : -1.0) / h : (hi ? xi[k] : 1.0 - xi[k]);
+        }
+        gh[g] += uv * w;
+      }
+    }
+    for (int k = 0; k < 3; ++k) x[k] = cell_lo[3 * (size_t)c + k] + xi[k] * h;
+  }
+  const double inv_constant = 1.0 / (sqrt(M_PI) * r_c), inv_rc = 1.0 / r_c;
+  double ga[3] = {0.0, 0.0, 0.0};
+  for (int j0 = 0; j0 < n_atoms; j0 += ENORM_BLOCK) {
+    const int j = j0 + threadIdx.x;
+    __syncthreads();
+    sx[threadIdx.x] = j < n_atoms ? pos[3 * (size_t)j] : 0.0;
+    sy[threadIdx.x] = j < n_atoms ? pos[3 * (size_t)j + 1] : 0.0;
+    sz[threadIdx.x] = j < n_atoms ? pos[3 * (size_t)j + 2] : 0.0;
+    sq[threadIdx.x] = j < n_atoms ? q[j] : 0.0;
+    __syncthreads();
+    const int m = min(ENORM_BLOCK, n_atoms - j0);
+    for (int k = 0; k < m; ++k) {
+      const double dx = x[0] - sx[k], dy = x[1] - sy[k], dz = x[2] - sz[k];
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      const double s = r * inv_rc;
+      const double fac = sq[k] * (((2.0 * r * exp(-(s * s)) * inv_constant) - erf(s)) / (r * r)) / r;
+      ga[0] += fac * dx;
+      ga[1] += fac * dy;
+      ga[2] += fac * dz;
+    }
+  }
+  double e = 0.0;
+  if (on) {
+    for (int g = 0; g < 3; ++g) e += (gh[g] - ga[g]) * (gh[g] - ga[g]);
+    e *= wq * h * h * h;
+  }
+  for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int w = 0; w < ENORM_BLOCK / 32; ++w) a += red[w];
+    partial[blockIdx.x] = a;
+  }
+}
+
 RhsState *state(gmg_context *h) {
   if (!h->rhs) h->rhs = new RhsState();
   return h->rhs;
@@ -924,6 +995,37 @@ int gmg_pair_energies(gmg_handle h, double r_c, double out[2]) {
     out[1] += hp[grid + b];
   }
   return GMG_OK;
+}
+
+int gmg_energy_norm_error(gmg_handle h, const double *u, int32_t n_dofs, double r_c, const double gauss2_points[2],
+                          const double gauss2_weights[2], double *out) {
+  if (!h || !u || !out || !gauss2_points || !gauss2_weights) return GMG_EINVAL;
+  gmg::enter(h);
+  RhsState *s = h->rhs;
+  if (!s || !s->cell_lo || !s->cell_dofs || s->n_cells != s->a_cells || n_dofs != s->n_dofs)
+    return fail(h, GMG_EINVAL, "energy norm: the cells of gmg_charge_density / gmg_assemble_rhs are not resident");
+  *out = 0.0;
+  const int64_t threads = 8 * (int64_t)s->n_cells;
+  if (threads == 0) return GMG_OK;
+  const int grid = cdiv(threads, ENORM_BLOCK);
+  double *d_u = nullptr, *partial = nullptr;
+  int rc = upload(h, d_u, u, (int64_t)n_dofs);
+  if (rc == GMG_OK && dalloc(&partial, grid) != cudaSuccess) rc = fail(h, GMG_ECUDA, "allocation failed");
+  if (rc == GMG_OK) {
+    energy_norm_kernel<<<grid, ENORM_BLOCK, 0, h->stream>>>(s->n_cells, s->cell_lo, s->cell_h, s->cell_dofs, d_u, h->n_atoms,
+                                                            h->atom_pos, h->atom_q, r_c, gauss2_points[0], gauss2_points[1],
+                                                            gauss2_weights[0], gauss2_weights[1], partial);
+    h->launches++;
+    std::vector<double> hp((size_t)grid);
+    const cudaError_t e = gmg::copy_sync(h, hp.data(), partial, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(h, GMG_ECUDA, std::string("energy norm: ") + cudaGetErrorString(e));
+    double sum = 0.0;
+    for (int b = 0; b < grid; ++b) sum += hp[b];
+    *out = std::sqrt(sum);
+  }
+  dfree(d_u);
+  dfree(partial);
+  return rc;
 }
 
 }  // extern "C"

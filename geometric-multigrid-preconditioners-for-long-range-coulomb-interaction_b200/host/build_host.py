@@ -1,4 +1,6 @@
-"""g++ build of the host library (`libstep50_b200.so`) and the `main` executable; both link the CUDA library."""
+"""g++ build of the host library (`libstep50_b200.so`) and the `main` executable (both link the CUDA library) and of
+`libministep_b200.so`: ministep + its C shim alone, no CUDA dependency (mesh / numbering / host assembly for the CPU
+arm of bench.py and the CPU tests)."""
 import os
 import subprocess
 
@@ -18,7 +20,15 @@ def _stale(target, sources):
 
 def build(force=False):
     os.makedirs(LIB, exist_ok=True)
-    srcs = [os.path.join(HERE, f) for f in ("ministep.cc", "step-50.cc", "capi_host.cc")]
+    srcs = [os.path.join(HERE, f) for f in ("ministep.cc", "step-50.cc", "capi_ministep.cc", "capi_host.cc")]
+    ms_srcs = [os.path.join(HERE, f) for f in ("ministep.cc", "capi_ministep.cc")]
+    ms_deps = ms_srcs + [os.path.join(HERE, f) for f in ("ministep.h", "capi_ministep.h")] + [
+        os.path.join(PKG, "csrc", "assemble_row.h")]
+    ms_lib = os.path.join(LIB, "libministep_b200.so")
+    if force or _stale(ms_lib, ms_deps):
+        cmd = [CXX] + FLAGS + ["-shared", "-o", ms_lib] + ms_srcs
+        print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
     deps = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".h", ".cc"))]
     deps.append(os.path.join(LIB, "libgmg_b200.so"))
     lib = os.path.join(LIB, "libstep50_b200.so")
@@ -33,7 +43,7 @@ def build(force=False):
                                "-Wl,-rpath,$ORIGIN"]
         print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
-    return [lib, exe]
+    return [lib, exe, ms_lib]
 
 
 if __name__ == "__main__":

@@ -60,7 +60,11 @@ class TimerOutput {
   std::chrono::steady_clock::time_point start = std::chrono::steady_clock::now();
 };
 
-struct ActiveCells;  // flattened active cells (lower corner, edge, dofs, atom-list id), cached per mesh
+// flattened active cells (lower corner, edge, dofs, atom-list id), cached per mesh
+struct ActiveCells {
+  std::vector<double> lo, h;
+  std::vector<int32_t> dofs, list;
+};
 
 // what one refinement cycle printed / computed (kept for the test shim)
 struct CycleRecord {
@@ -146,6 +150,7 @@ class LaplaceProblem {
   int smoothing_steps = 2;
   int gpu_device = 0;
   unsigned int energy_atom_limit = 300;
+  unsigned int energy_norm_atom_limit = 0;  // 0: always (reference source)
   bool indicator_with_residual = true;  // false: Kelly part only (the build behind the cluster logs)
   // Matrix assembly = Device: the system matrix and the level-0 matrix are assembled on the GPU from the cell -> dof
   // maps (gmg_assemble_matrix: the same CSR, bit for bit) instead of on the host; patch levels stay on the host

@@ -10,33 +10,53 @@ from . import capi
 
 _DT = {0: np.int32, 1: np.int64, 2: np.float64, 3: np.uint8, 4: np.float32}
 _lib = None
+_ms_lib = None
+
+
+def _declare_ms(L):
+    L.ms_create.restype = C.c_void_p
+    L.ms_create.argtypes = [C.c_int, C.c_double, C.c_double]
+    L.ms_destroy.argtypes = [C.c_void_p]
+    L.ms_refine.argtypes = [C.c_void_p, C.c_void_p]
+    L.ms_refine_global.argtypes = [C.c_void_p, C.c_int]
+    L.ms_build.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ms_n_levels.argtypes = [C.c_void_p]
+    L.ms_n_cells.restype = C.c_int64
+    L.ms_n_cells.argtypes = [C.c_void_p, C.c_int]
+    L.ms_get.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+    L.ms_assemble_emulate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+    L.ms_unit_stiffness.argtypes = [C.c_void_p]
+    L.ms_error_indicator.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.ms_transfer.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ms_distribute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ms_locate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
+    L.ms_gauss.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    L.ms_last_error.restype = C.c_char_p
+
+
+def ms_lib():
+    """libministep_b200.so: ministep alone (mesh, numbering, host assembly, indicator, transfer).  Links no CUDA
+    library, so the CPU arm of bench.py and the CPU tests never map the product's kernels."""
+    global _ms_lib
+    if _ms_lib is None:
+        path = os.path.join(os.path.dirname(capi.LIB_PATH), "libministep_b200.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run __graft_entry__.build()")
+        L = C.CDLL(path)
+        _declare_ms(L)
+        _ms_lib = L
+    return _ms_lib
 
 
 def lib():
+    """libstep50_b200.so: LaplaceProblem + bench hooks (links libgmg_b200.so, needs a B200 to run)."""
     global _lib
     if _lib is None:
         path = os.path.join(os.path.dirname(capi.LIB_PATH), "libstep50_b200.so")
         if not os.path.exists(path):
             raise RuntimeError(f"{path} missing: run __graft_entry__.build()")
         L = C.CDLL(path)
-        L.ms_create.restype = C.c_void_p
-        L.ms_create.argtypes = [C.c_int, C.c_double, C.c_double]
-        L.ms_destroy.argtypes = [C.c_void_p]
-        L.ms_refine.argtypes = [C.c_void_p, C.c_void_p]
-        L.ms_refine_global.argtypes = [C.c_void_p, C.c_int]
-        L.ms_build.argtypes = [C.c_void_p, C.c_int, C.c_int]
-        L.ms_n_levels.argtypes = [C.c_void_p]
-        L.ms_n_cells.restype = C.c_int64
-        L.ms_n_cells.argtypes = [C.c_void_p, C.c_int]
-        L.ms_get.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int)]
-        L.ms_assemble_emulate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
-        L.ms_unit_stiffness.argtypes = [C.c_void_p]
-        L.ms_error_indicator.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
-        L.ms_transfer.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        L.ms_distribute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        L.ms_locate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
-        L.ms_gauss.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
-        L.ms_last_error.restype = C.c_char_p
+        _declare_ms(L)
         L.step50_check_prm.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.step50_run_string.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.step50_free.argtypes = [C.c_void_p]
@@ -46,6 +66,8 @@ def lib():
         L.step50_bench_finish_setup.argtypes = [C.c_void_p]
         L.step50_bench_set_device_assembly.argtypes = [C.c_void_p, C.c_int]
         L.step50_bench_download_x.argtypes = [C.c_void_p, C.c_void_p]
+        L.step50_bench_download_b.argtypes = [C.c_void_p, C.c_void_p]
+        L.step50_bench_time_binning.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.step50_bench_gmg.restype = C.c_void_p
         L.step50_bench_gmg.argtypes = [C.c_void_p]
         L.step50_bench_info.argtypes = [C.c_void_p, C.c_void_p]
@@ -66,9 +88,14 @@ def _ck(rc):
         raise HostError(lib().ms_last_error().decode())
 
 
-def _fetch(fn, handle, name, level):
+def _ck_ms(rc):
+    if rc != 0:
+        raise HostError(ms_lib().ms_last_error().decode())
+
+
+def _fetch(fn, handle, name, level, ck=None):
     ptr, n, dt = C.c_void_p(), C.c_int64(), C.c_int()
-    _ck(fn(handle, name.encode(), level, C.byref(ptr), C.byref(n), C.byref(dt)))
+    (ck or _ck)(fn(handle, name.encode(), level, C.byref(ptr), C.byref(n), C.byref(dt)))
     dtype = np.dtype(_DT[dt.value])
     if n.value == 0:
         return np.zeros(0, dtype=dtype)
@@ -78,7 +105,7 @@ def _fetch(fn, handle, name, level):
 
 class Ministep:
     def __init__(self, reps, lo, hi):
-        self.L = lib()
+        self.L = ms_lib()
         self.p = self.L.ms_create(reps, lo, hi)
         self.h0 = (hi - lo) / reps  # edge of a base cell (Forest::H)
 
@@ -89,13 +116,13 @@ class Ministep:
 
     def refine(self, flags_per_level):
         flat = np.ascontiguousarray(np.concatenate([np.asarray(f, dtype=np.uint8) for f in flags_per_level]))
-        _ck(self.L.ms_refine(self.p, flat.ctypes.data))
+        _ck_ms(self.L.ms_refine(self.p, flat.ctypes.data))
 
     def refine_global(self, times):
-        _ck(self.L.ms_refine_global(self.p, times))
+        _ck_ms(self.L.ms_refine_global(self.p, times))
 
     def build(self, step16=False, matrices=True):
-        _ck(self.L.ms_build(self.p, int(step16), int(matrices)))
+        _ck_ms(self.L.ms_build(self.p, int(step16), int(matrices)))
 
     @property
     def n_levels(self):
@@ -105,7 +132,7 @@ class Ministep:
         return self.L.ms_n_cells(self.p, l)
 
     def get(self, name, level=0):
-        return _fetch(self.L.ms_get, self.p, name, level)
+        return _fetch(self.L.ms_get, self.p, name, level, _ck_ms)
 
     def csr(self, prefix, level=0):
         import scipy.sparse as sp
@@ -115,33 +142,33 @@ class Ministep:
     def assemble_emulate(self, which, level=0):
         """Sequential emulation of the device-side assembly against the host assembly: (differing words, longest row)."""
         nd, mr = C.c_int64(-1), C.c_int(0)
-        _ck(self.L.ms_assemble_emulate(self.p, which, level, C.byref(nd), C.byref(mr)))
+        _ck_ms(self.L.ms_assemble_emulate(self.p, which, level, C.byref(nd), C.byref(mr)))
         return nd.value, mr.value
 
     def error_indicator(self, u, rho, nq, residual_term=True):
         u = np.ascontiguousarray(u, dtype=np.float64)
         rho = np.ascontiguousarray(rho, dtype=np.float64).ravel()
         thr = C.c_double()
-        _ck(self.L.ms_error_indicator(self.p, u.ctypes.data, len(rho), rho.ctypes.data, nq, int(residual_term), C.byref(thr)))
+        _ck_ms(self.L.ms_error_indicator(self.p, u.ctypes.data, len(rho), rho.ctypes.data, nq, int(residual_term), C.byref(thr)))
         return thr.value
 
     def transfer_from(self, old, old_res, u_old):
         u_old = np.ascontiguousarray(u_old, dtype=np.float64)
         out = np.zeros(len(self.get("boundary")))
-        _ck(self.L.ms_transfer(self.p, old_res, old.p, u_old.ctypes.data, out.ctypes.data))
+        _ck_ms(self.L.ms_transfer(self.p, old_res, old.p, u_old.ctypes.data, out.ctypes.data))
         return out
 
     def distribute(self, g, x):
         g = np.ascontiguousarray(g, dtype=np.float64)
         x = np.ascontiguousarray(x, dtype=np.float64).copy()
-        _ck(self.L.ms_distribute(self.p, g.ctypes.data, x.ctypes.data))
+        _ck_ms(self.L.ms_distribute(self.p, g.ctypes.data, x.ctypes.data))
         return x
 
 
 def unit_stiffness():
     """Q1 Laplace cell matrix of the unit cube (8 x 8), the host's bits."""
     K = np.zeros((8, 8))
-    lib().ms_unit_stiffness(K.ctypes.data)
+    ms_lib().ms_unit_stiffness(K.ctypes.data)
     return K
 
 
@@ -164,7 +191,7 @@ def assembly_inputs(M, which, level=0):
 
 def gauss(n):
     p, w = np.zeros(n), np.zeros(n)
-    lib().ms_gauss(n, p.ctypes.data, w.ctypes.data)
+    ms_lib().ms_gauss(n, p.ctypes.data, w.ctypes.data)
     return p, w
 
 
@@ -213,6 +240,7 @@ class BenchProblem:
         self.n_dofs, self.n_cells, self.n_levels = int(info[0]), int(info[1]), int(info[2])
         self.level_n = [int(v) for v in info[3:3 + self.n_levels]]
         self.n_atoms, self.n_pairs, self.sys_nnz, self.nq = int(info[11]), int(info[12]), int(info[13]), int(info[14])
+        self.n_pairs_active = int(info[15])
 
     def close(self):
         if self.p:
@@ -238,6 +266,18 @@ class BenchProblem:
         out = np.zeros(self.n_dofs)
         _ck(self.L.step50_bench_download_x(self.p, out.ctypes.data))
         return out
+
+    def download_b(self):
+        """Load vector of the last step_device() (device -> host)."""
+        out = np.zeros(self.n_dofs)
+        _ck(self.L.step50_bench_download_b(self.p, out.ctypes.data))
+        return out
+
+    def time_binning(self):
+        """rhs_assembly_optimization() once more through its host-buffer entry point: (ms, cell-atom pairs)."""
+        ms, pairs = C.c_double(0), C.c_int64(0)
+        _ck(self.L.step50_bench_time_binning(self.p, C.byref(ms), C.byref(pairs)))
+        return ms.value, pairs.value
 
     def get(self, name, level=0):
         return _fetch(self.L.step50_bench_get, self.p, name, level)

@@ -30,8 +30,11 @@ def write_lammps(path, pos, q):
 
 
 def cluster_prm(atom_file, n, cycles=5, smoother="MulticolourSSOR", indicator="Kelly", nq_param=1, cutoff=3.5,
-                vacuum=10, mesh_size=0.25, device=0, assembly="Host", coarse_levels=0):
-    """The parameter file of the reference's cluster runs for the n^3-unit-cell lattice (domain [0, n])."""
+                vacuum=10, mesh_size=0.25, device=0, assembly="Host", coarse_levels=0, energy_limit=300, energy_norm_limit=300,
+                flag="true", n_gpus=1):
+    """The parameter file of the reference's cluster runs for the n^3-unit-cell lattice (domain [0, n]).  The builds behind
+    the cluster logs printed neither energies above 300 atoms nor the energy-norm error (no such line in the logs), hence the
+    two atom limits."""
     return f"""
 subsection Geometry
   set Number of global refinement = 0
@@ -45,10 +48,12 @@ subsection Misc
   set Number of Adaptive Refinement = {cycles}
   set smoothing length = 0.5
   set Nonzero Density radius parameter around each charge = {cutoff}
-  set Flag for RHS evaluation optimization = true
+  set Flag for RHS evaluation optimization = {flag}
   set Quadrature points for RHS function = {nq_param}
   set Output time summary table = false
   set Refinement indicator = {indicator}
+  set Energy postprocessing atom limit = {energy_limit}
+  set Energy norm error atom limit = {energy_norm_limit}
 end
 set Polynomial degree = 1
 subsection Solver input data

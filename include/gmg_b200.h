@@ -258,6 +258,11 @@ int gmg_error_indicator(gmg_handle h, int32_t n_cells, const int32_t *face_nb /*
 /* The O(N^2) pair sums of postprocess_electrostatic_energy (src/step-50.cc:1316-1332) over the atoms of gmg_set_atoms:
  * out[0] = sum_{i<j} q_i q_j / r_ij, out[1] = sum_{i<j} q_i q_j erfc(r_ij / r_c) / r_ij. */
 int gmg_pair_energies(gmg_handle h, double r_c, double out[2]);
+/* postprocess_error_in_energy_norm (src/step-50.cc:1423-1461): sqrt(int |grad u_h - grad u_exact|^2) with QGauss<3>(2),
+ * grad u_exact summed over all atoms of gmg_set_atoms (:1437-1452 via exact_solution->gradient_list).  Cells = those of the
+ * last gmg_charge_density / gmg_assemble_rhs calls (resident); u = solution after constraints.distribute. */
+int gmg_energy_norm_error(gmg_handle h, const double *u, int32_t n_dofs, double r_c, const double gauss2_points[2],
+                          const double gauss2_weights[2], double *out);
 /* fused device-resident RHS step used by the bench `value` leg: densities + load vector with the
  * inputs of the last gmg_charge_density / gmg_assemble_rhs calls kept on the device. */
 int gmg_rhs_step_dev(gmg_handle h, double *b_dev);

@@ -30,6 +30,11 @@ def max_threads():
     return lib().orc_max_threads()
 
 
+def set_threads(n):
+    """OpenMP threads of the port (bench.py: all cores of the affinity mask, whatever OMP_NUM_THREADS the launcher set)."""
+    lib().orc_set_threads(int(n))
+
+
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
@@ -148,3 +153,12 @@ def load_vector(rho, cell_h, cell_dofs, shape, weights, n_dofs, hang_ptr, hang_c
                           hc.ctypes.data_as(_pi32), hv.ctypes.data_as(_pd), cons.ctypes.data_as(C.POINTER(C.c_uint8)),
                           b.ctypes.data_as(_pd))
     return b
+
+
+def pair_energies(pos, q, r_c):
+    """(analytic, short-ranged) pair sums of postprocess_electrostatic_energy (src/step-50.cc:1315-1345)."""
+    pos, q = _f64(pos), _f64(q)
+    out = np.zeros(2)
+    lib().orc_pair_energies(C.c_int(len(q)), pos.ctypes.data_as(_pd), q.ctypes.data_as(_pd), C.c_double(r_c),
+                            out.ctypes.data_as(_pd))
+    return float(out[0]), float(out[1])

@@ -37,6 +37,14 @@ int orc_max_threads(void) {
 #endif
 }
 
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------ BLAS-1/2 */
 static void spmv(const csr_t *A, const double *x, double *y) {
 #pragma omp parallel for schedule(static)
@@ -457,4 +465,33 @@ void orc_load_vector(int n_cells, const double *rho, const double *cell_h, const
       }
     }
   }
+}
+
+/* postprocess_electrostatic_energy, pair sums (src/step-50.cc:1315-1345): out[0] = sum_{i<j} q_i q_j / r,
+ * out[1] = sum_{i<j} q_i q_j erfc(r / r_c) / r.  Row sums in parallel, rows added in index order. */
+void orc_pair_energies(int n, const double *pos, const double *q, double r_c, double *out) {
+  double *ra = (double *)malloc(sizeof(double) * (size_t)n), *rs = (double *)malloc(sizeof(double) * (size_t)n);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int i = 0; i < n; ++i) {
+    double a = 0.0, s = 0.0;
+    for (int j = i + 1; j < n; ++j) {
+      const double dx = pos[3 * (size_t)j] - pos[3 * (size_t)i], dy = pos[3 * (size_t)j + 1] - pos[3 * (size_t)i + 1],
+                   dz = pos[3 * (size_t)j + 2] - pos[3 * (size_t)i + 2];
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      const double c = q[i] * q[j] / r;
+      a += c;
+      s += c * erfc(r / r_c);
+    }
+    ra[i] = a;
+    rs[i] = s;
+  }
+  double a = 0.0, s = 0.0;
+  for (int i = 0; i < n; ++i) {
+    a += ra[i];
+    s += rs[i];
+  }
+  out[0] = a;
+  out[1] = s;
+  free(ra);
+  free(rs);
 }
