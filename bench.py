@@ -177,6 +177,10 @@ def write_atoms(args):
 
 
 KERNEL_NAMES = {
+    6: "gmg::cg_persistent_win2 (coarse-level CG on the row-pattern matrix: TMA-filled shared-memory windows, tagged-word grid "
+       "reductions, remainder rows on dedicated warps; h in global memory; one launch per V-cycle)",
+    5: "gmg::cg_persistent_win2 (coarse-level CG on the row-pattern matrix: TMA-filled shared-memory windows, tagged-word grid "
+       "reductions, remainder rows on dedicated warps, h = A d kept in shared memory; one launch per V-cycle)",
     4: "gmg::cg_persistent_win (coarse-level CG on the row-pattern matrix, TMA-filled shared-memory windows, row codes in "
        "global memory; one cooperative launch per V-cycle)",
     3: "gmg::cg_persistent_win (coarse-level CG on the row-pattern matrix, TMA-filled shared-memory windows; one cooperative "

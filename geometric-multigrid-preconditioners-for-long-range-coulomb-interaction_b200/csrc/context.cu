@@ -353,7 +353,7 @@ static int build_csell(gmg_context *h, Sell &s) {
 // Dominant pattern + TMA window plan (pattern_win.cuh) from the host copy of the pattern table.  mask[p] != 0: the
 // entries of pattern p are a sub-sequence (same offsets, same value bits) of the dominant pattern's.
 static void plan_windows(const std::vector<int> &ptr, const std::vector<int> &off, const std::vector<double> &val, int np,
-                         DomPat &D, std::vector<uint32_t> &mask) {
+                         DomPat &D, std::vector<uint32_t> &mask, const int TILE_ROWS = WIN_TILE_ROWS) {
   D = DomPat{};
   mask.assign(np + 1, 0u);
   if (np == 0) return;
@@ -369,14 +369,14 @@ static void plan_windows(const std::vector<int> &ptr, const std::vector<int> &of
   };
   std::vector<Seg> segs;
   for (int v : sorted) {
-    if (!segs.empty() && v <= segs.back().hi + WIN_TILE_ROWS + 64) segs.back().hi = std::max(segs.back().hi, v);
+    if (!segs.empty() && v <= segs.back().hi + TILE_ROWS + 64) segs.back().hi = std::max(segs.back().hi, v);
     else segs.push_back(Seg{v, v});
   }
   if ((int)segs.size() > WIN_MAX_SEG) return;
   int base = 0;
   for (size_t i = 0; i < segs.size(); ++i) {
     const int lo = segs[i].lo - (segs[i].lo & 1);  // even (also for negative offsets: two's complement)
-    const int n = (segs[i].hi - lo + WIN_TILE_ROWS + 1) & ~1;
+    const int n = (segs[i].hi - lo + TILE_ROWS + 1) & ~1;
     D.seg_lo[i] = lo;
     D.seg_len[i] = n;
     D.seg_base[i] = base;
@@ -387,7 +387,7 @@ static void plan_windows(const std::vector<int> &ptr, const std::vector<int> &of
   D.win_elems = base;
   auto widx = [&](int v) {
     for (int i = 0; i < D.nseg; ++i)
-      if (v >= D.seg_lo[i] && v - D.seg_lo[i] + WIN_TILE_ROWS <= D.seg_len[i]) return D.seg_base[i] + (v - D.seg_lo[i]);
+      if (v >= D.seg_lo[i] && v - D.seg_lo[i] + TILE_ROWS <= D.seg_len[i]) return D.seg_base[i] + (v - D.seg_lo[i]);
     return -1;
   };
   for (int k = 0; k < len; ++k) {
@@ -501,14 +501,61 @@ static int build_pat(gmg_context *h, Sell &s) {
   std::vector<int> hw(n_cand);
   GMG_CUDA(h, copy_sync(h, hw.data(), width, sizeof(int) * n_cand, cudaMemcpyDeviceToHost));
   // the table holds the most frequent patterns that fit the shared-memory budget; pattern np = the empty pattern
-  std::vector<int> hptr(1, 0), h_pid_rep, h_slot_pid((size_t)mask + 1, -1);
+  std::vector<int> hptr(1, 0), h_pid_rep, h_slot_pid((size_t)mask + 1, -1), cand_of_pid;
   int64_t covered = 0;
-  for (int p = 0; p < n_cand && (int)h_pid_rep.size() < PAT_MAX_PAT; ++p) {
-    if (hptr.back() + hw[p] > PAT_MAX_ENT) continue;
-    h_slot_pid[ents[p].slot] = (int)h_pid_rep.size();
-    h_pid_rep.push_back(ents[p].rep);
-    hptr.push_back(hptr.back() + hw[p]);
-    covered += ents[p].cnt;
+  auto select_table = [&](const std::vector<char> *keep) {
+    hptr.assign(1, 0);
+    h_pid_rep.clear();
+    cand_of_pid.clear();
+    std::fill(h_slot_pid.begin(), h_slot_pid.end(), -1);
+    covered = 0;
+    for (int p = 0; p < n_cand && (int)h_pid_rep.size() < PAT_MAX_PAT; ++p) {
+      if (keep && !(*keep)[p]) continue;
+      if (hptr.back() + hw[p] > PAT_MAX_ENT) continue;
+      h_slot_pid[ents[p].slot] = (int)h_pid_rep.size();
+      h_pid_rep.push_back(ents[p].rep);
+      cand_of_pid.push_back(p);
+      hptr.push_back(hptr.back() + hw[p]);
+      covered += ents[p].cnt;
+    }
+  };
+  select_table(nullptr);
+  if (h->cg_win >= 2 && s.v.n_rows == s.v.n_cols && !h_pid_rep.empty()) {
+    // Second-generation window kernel (pattern_win2.cuh): its tile warps know two kinds of rows, dominant-compatible
+    // ones and single diagonal entries; every other row is walked by the remainder warps.  Look at the candidate table
+    // and keep only those two kinds (the rows of the dropped patterns join the remainder: 1 % of the rows of a lattice).
+    const int np0 = (int)h_pid_rep.size(), ne0 = hptr.back();
+    int *t_ptr = nullptr, *t_off = nullptr, *t_rep = nullptr;
+    double *t_val = nullptr;
+    GMG_CUDA(h, arena_alloc(h->scratch, &t_ptr, np0 + 1));
+    GMG_CUDA(h, arena_alloc(h->scratch, &t_off, std::max(ne0, 1)));
+    GMG_CUDA(h, arena_alloc(h->scratch, &t_val, std::max(ne0, 1)));
+    GMG_CUDA(h, arena_alloc(h->scratch, &t_rep, np0));
+    GMG_CUDA(h, copy(h, t_ptr, hptr.data(), sizeof(int) * (np0 + 1), cudaMemcpyHostToDevice));
+    GMG_CUDA(h, copy(h, t_rep, h_pid_rep.data(), sizeof(int) * np0, cudaMemcpyHostToDevice));
+    pat_fill<<<cdiv(np0, 128), 128, 0, h->stream>>>(s.v, np0, t_rep, t_ptr, t_off, t_val);
+    GMG_LAUNCH_CHECK(h);
+    std::vector<int> toff(ne0);
+    std::vector<double> tval(ne0);
+    if (ne0 > 0) {
+      GMG_CUDA(h, copy(h, toff.data(), t_off, sizeof(int) * ne0, cudaMemcpyDeviceToHost));
+      GMG_CUDA(h, copy_sync(h, tval.data(), t_val, sizeof(double) * ne0, cudaMemcpyDeviceToHost));
+    }
+    DomPat probe{};
+    std::vector<uint32_t> pmask;
+    std::vector<int> pptr = hptr;
+    pptr.push_back(pptr.back());
+    plan_windows(pptr, toff, tval, np0, probe, pmask, WIN2_TILE_ROWS);
+    if (probe.len > 0) {
+      std::vector<char> keep(n_cand, 0);
+      bool dropped = false;
+      for (int p = 0; p < np0; ++p) {
+        const bool diag = hptr[p + 1] - hptr[p] == 1 && toff[hptr[p]] == 0;
+        if (pmask[p] != 0u || diag) keep[cand_of_pid[p]] = 1;
+        else dropped = true;
+      }
+      if (dropped) select_table(&keep);
+    }
   }
   const int np = (int)h_pid_rep.size();
   if (covered * 4 < (int64_t)n * 3) {
@@ -615,6 +662,11 @@ static int build_pat(gmg_context *h, Sell &s) {
     }
     std::vector<uint32_t> hmask;
     plan_windows(hptr, hoff, hval, np, s.dom, hmask);
+    {
+      std::vector<uint32_t> m2;
+      plan_windows(hptr, hoff, hval, np, s.dom2, m2, WIN2_TILE_ROWS);  // (same dominant pattern, the tile size differs)
+      if (m2 != hmask) s.dom2.len = 0;
+    }
     GMG_CUDA(h, dalloc(&s.dom_mask, np + 1));
     GMG_CUDA(h, copy_sync(h, s.dom_mask, hmask.data(), sizeof(uint32_t) * (np + 1), cudaMemcpyHostToDevice));
     if (s.dom.len > 0 && s.v.n_rows == s.v.n_cols) {
@@ -643,6 +695,10 @@ static int build_pat(gmg_context *h, Sell &s) {
           if (m != full) m = 0u;
         GMG_CUDA(h, copy_sync(h, s.dom_mask, hmask.data(), sizeof(uint32_t) * (np + 1), cudaMemcpyHostToDevice));
       }
+      // pattern_win2.cuh: every table pattern is dominant-compatible or a single diagonal entry
+      s.win2_ok = s.dom2.len > 0;
+      for (int p = 0; p < np; ++p)
+        if (hmask[p] == 0u && !(hptr[p + 1] - hptr[p] == 1 && hoff[hptr[p]] == 0)) s.win2_ok = false;
       GMG_CUDA(h, cudaStreamSynchronize(h->stream));
           if (std::getenv("GMG_TRACE")) std::fprintf(stderr, "[gmg trace]     zeroed-operand set: %s\n", hc ? "conflict (exact rows only)" : "ok");
       GMG_CUDA(h, dalloc(&s.row_code, n_padded));
@@ -651,6 +707,8 @@ static int build_pat(gmg_context *h, Sell &s) {
       GMG_CUDA(h, cudaStreamSynchronize(h->stream));
     } else {
       s.dom.len = 0;
+      s.dom2.len = 0;
+      s.win2_ok = false;
     }
     if (std::getenv("GMG_TRACE")) {
       int64_t n_compat = 0;
@@ -947,6 +1005,37 @@ static bool window_plan(gmg_context *h, const Sell &A, int &rows_per_block, WinL
   return lay.total <= smem_cap;
 }
 
+// The same question for the second-generation kernel (pattern_win2.cuh): h of the block's rows and the row codes go to
+// shared memory when they fit next to the windows (h first: it saves 16 bytes of L2 traffic per row and iteration).
+static bool window2_plan(gmg_context *h, const Sell &A, int &rows_per_block, int &h_smem, int &code_smem, Win2Layout &lay) {
+  if (!(A.patterned && h->compress >= 2 && A.dom2.len > 0 && A.win2_ok && h->cg_win >= 2 && A.pv.n_pat <= (int)RC_ID && A.row_code &&
+        h->sm_count <= WIN2_MAX_BLOCKS))
+    return false;
+  const int smem_cap = 232448 - 1024;
+  rows_per_block = (A.v.n_slices / h->sm_count + 1) * 32;
+  const int tries[4][2] = {{1, 1}, {1, 0}, {0, 1}, {0, 0}};
+  for (int i = h->win_global_codes ? 3 : 0; i < 4; ++i) {
+    h_smem = tries[i][0];
+    code_smem = tries[i][1];
+    lay = win2_layout(A.dom2.win_elems, A.pv.n_pat, rows_per_block, h_smem != 0, code_smem != 0, A.pv.rem.n_rows / h->sm_count + 1);
+    if (lay.total <= smem_cap) return true;
+  }
+  return false;
+}
+
+// variant 0 (default): 512 threads with 128 registers: 8 tile warps x 6 slices, 7 remainder warps, g of up to 24 slices per
+// thread in registers; 1: 1024 threads, 24 tile warps x 2 slices, g in global memory (GMG_WIN2_VARIANT; B200, 64k atoms:
+// 41.4 against 43.4 us per iteration, 12 tile warps x 4 slices with 3 remainder warps: 43.4 -- the remainder rows become the
+// critical path of the SpMV phase)
+static const void *win2_kernel(const gmg_context *h, int &block) {
+  if (h->cg_win2_variant == 1) {
+    block = 1024;
+    return (const void *)cg_persistent_win2<1024, 24, 2, 0, 6>;
+  }
+  block = 512;
+  return (const void *)cg_persistent_win2<512, 8, 6, 24, 6>;
+}
+
 static int coarse_cg(gmg_context *h, const Sell &A, const double *b, double *x, int max_it, double tol) {
   if (A.v.n_rows > h->cg_n) return fail(h, GMG_EINVAL, "coarse CG work vectors too small");
   const int slot = h->cg_cursor % h->cg_ring;
@@ -966,6 +1055,38 @@ static int coarse_cg(gmg_context *h, const Sell &A, const double *b, double *x, 
   }
   int rows_per_block = 0;
   WinLayout lay{};
+  {
+    int h_smem = 0, code_smem = 0;
+    Win2Layout lay2{};
+    if (pat && window2_plan(h, A, rows_per_block, h_smem, code_smem, lay2)) {
+      int win2_block = 0;
+      const void *win2_fn = win2_kernel(h, win2_block);
+      if (lay2.total > h->cg_win2_smem) {
+        GMG_CUDA(h, cudaFuncSetAttribute(win2_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, lay2.total));
+        h->cg_win2_smem = lay2.total;
+      }
+      // tags of this launch: 1 (|b|) + 3 per iteration + 1 (status); never 0, never reused while a slot still holds them
+      const uint32_t need = 3u * (uint32_t)std::max(max_it, 1) + 8u;
+      if (h->cg_ll_tag > 0xffffffffu - need - 1u) {
+        GMG_CUDA(h, cudaMemsetAsync(h->cg_ll, 0, sizeof(uint64_t) * WIN2_SLOT_U64_MAX * WIN2_CHANNELS * WIN2_MAX_BLOCKS, h->stream));
+        h->cg_ll_tag = 0;
+      }
+      uint32_t tag_base = h->cg_ll_tag;
+      h->cg_ll_tag += need;
+      DomPat dom = A.dom2;
+      const uint32_t *mask = A.dom_mask;
+      const unsigned short *gcode = A.row_code;
+      void *wargs[] = {&pv, &dom, (void *)&mask, (void *)&b, &x, &h->cg_g, &h->cg_d, &h->cg_dz, &h->cg_h, &h->cg_ll, &h->cg_ll_stride, &tag_base,
+                       &max_it, &tol, &res, &rows_per_block, &h_smem, &code_smem, (void *)&gcode, &h->cg_prof};
+      GMG_CUDA(h, cudaLaunchCooperativeKernel(win2_fn, dim3(h->sm_count), dim3(win2_block), wargs, (size_t)lay2.total, h->stream));
+      h->launches++;
+      if (ev >= 0) {
+        cudaEventRecord(h->ev_end[ev], h->stream);
+        h->ev_result_slot[ev] = slot;
+      }
+      return GMG_OK;
+    }
+  }
   bool win = pat && window_plan(h, A, rows_per_block, lay);
   if (win) {
     const int grid = h->sm_count;
@@ -1402,15 +1523,19 @@ int gmg_create(int device, gmg_handle *out) {
     h->stage_threads = std::getenv("GMG_STAGE_THREADS") ? std::atoi(std::getenv("GMG_STAGE_THREADS"))
                                                         : (int)std::min(12u, std::max(2u, hw * 3 / 4 / ranks));
   }
-  h->cg_win = !(std::getenv("GMG_CG_WIN") && std::atoi(std::getenv("GMG_CG_WIN")) == 0);
+  h->cg_win = std::getenv("GMG_CG_WIN") ? std::max(0, std::min(2, std::atoi(std::getenv("GMG_CG_WIN")))) : 2;
+  if (std::getenv("GMG_WIN2_VARIANT")) h->cg_win2_variant = std::atoi(std::getenv("GMG_WIN2_VARIANT"));
+  if (std::getenv("GMG_LL_STRIDE")) h->cg_ll_stride = std::max(2, std::min(WIN2_SLOT_U64_MAX, std::atoi(std::getenv("GMG_LL_STRIDE")) & ~1));
   h->win_global_codes = std::getenv("GMG_WIN_GLOBAL_CODES") && std::atoi(std::getenv("GMG_WIN_GLOBAL_CODES")) != 0;
   if (std::getenv("GMG_PDL")) h->pdl = std::atoi(std::getenv("GMG_PDL")) != 0;
   if (std::getenv("GMG_CLUSTER_SSOR")) h->cluster_ssor = std::atoi(std::getenv("GMG_CLUSTER_SSOR")) != 0;
   if (std::getenv("GMG_PERSISTENT_SSOR")) h->persistent_ssor = std::atoi(std::getenv("GMG_PERSISTENT_SSOR")) != 0;
   h->partials_cap = 1 << 16;
   bool ok = dalloc(&h->partials, 3 * h->partials_cap) == cudaSuccess && dalloc(&h->counter, 4) == cudaSuccess &&
-            dalloc(&h->scalars, 1) == cudaSuccess && dalloc(&h->cg_results, h->cg_ring) == cudaSuccess;
+            dalloc(&h->scalars, 1) == cudaSuccess && dalloc(&h->cg_results, h->cg_ring) == cudaSuccess &&
+            dalloc(&h->cg_ll, WIN2_SLOT_U64_MAX * WIN2_CHANNELS * WIN2_MAX_BLOCKS) == cudaSuccess;
   if (ok) {
+    cudaMemset(h->cg_ll, 0, sizeof(uint64_t) * WIN2_SLOT_U64_MAX * WIN2_CHANNELS * WIN2_MAX_BLOCKS);
     cudaMemset(h->counter, 0, 4 * sizeof(unsigned int));
     cudaMemset(h->scalars, 0, sizeof(PcgScalars));
     cudaMemset(h->cg_results, 0, sizeof(CgResult) * h->cg_ring);
@@ -1468,6 +1593,7 @@ int gmg_destroy(gmg_handle h) {
   dfree(h->counter);
   dfree(h->scalars);
   dfree(h->cg_partials);
+  dfree(h->cg_ll);
   dfree(h->cg_results);
   dfree(h->atom_pos);
   dfree(h->atom_q);
@@ -2226,6 +2352,12 @@ int gmg_coarse_kernel(gmg_handle h, int which, int level, int *kernel) {
   if (!A) return fail(h, GMG_EINVAL, "matrix not available");
   int rpb = 0;
   WinLayout lay{};
+  int hs = 0, cs = 0;
+  Win2Layout lay2{};
+  if (!h->dist.on && window2_plan(h, *A, rpb, hs, cs, lay2)) {
+    *kernel = 5 + (hs ? 0 : 1);  // 5: h of the block's rows in shared memory, 6: in global memory
+    return GMG_OK;
+  }
   if (h->dist.on) *kernel = (A->patterned && h->compress >= 2) ? 2 : (A->compressed && h->compress >= 1) ? 1 : 0;
   else if (window_plan(h, *A, rpb, lay)) *kernel = rpb > 0 ? 3 : 4;
   else *kernel = (A->patterned && h->compress >= 2) ? 2 : (A->compressed && h->compress >= 1) ? 1 : 0;

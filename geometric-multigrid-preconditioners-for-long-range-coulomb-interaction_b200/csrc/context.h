@@ -71,6 +71,8 @@ struct Sell {
   double *rem_cval = nullptr;
   // dominant pattern + TMA window plan for the persistent CG (pattern_win.cuh); dom.len == 0: not available
   DomPat dom{};
+  DomPat dom2{};         // the same pattern planned for the tile size of pattern_win2.cuh
+  bool win2_ok = false;  // every table pattern is dominant-compatible or a single diagonal entry
   uint32_t *dom_mask = nullptr;
   unsigned short *row_code = nullptr;  // 16-bit row codes of the window kernel (pat_row_codes)
 };
@@ -287,11 +289,17 @@ struct gmg_context {
   int cg_grid_c = 0;     // cooperative grid of the compressed-format CG kernel
   int cg_grid_p = 0;     // cooperative grid of the row-pattern CG kernel
   bool win_global_codes = false;  // force the large-level variant of the window kernel (tests: GMG_WIN_GLOBAL_CODES=1)
-  bool cg_win = true;    // TMA-window variant of the row-pattern CG (pattern_win.cuh); GMG_CG_WIN=0 disables
+  int cg_win = 2;        // TMA-window variants of the row-pattern CG: 2 = pattern_win2.cuh (default), 1 = pattern_win.cuh,
+                         // 0 = L1 gathers (GMG_CG_WIN)
+  uint64_t *cg_ll = nullptr;   // tagged words of the in-kernel reductions / barriers of pattern_win2.cuh
+  uint32_t cg_ll_tag = 0;
+  int cg_ll_stride = 32;       // distance of two blocks' slots in 64-bit words (256 B: the slots spread over the L2 slices)
   bool vc_prof = false;  // gmg_debug_vcycle_profile: events around down sweep / coarse solve / up sweep
   std::vector<cudaEvent_t> vc_ev;
   int vc_ev_used = 0;
   int cg_prof = 0;       // gmg_debug_cg_phases: per-phase timing inside the window kernel
+  int cg_win2_smem = 0;
+  int cg_win2_variant = 0;     // (GMG_WIN2_VARIANT: vector-phase unrolling under test)
   int cg_win_smem = 0;   // dynamic shared memory the window kernel is currently configured for
   bool is_setup = false;
 

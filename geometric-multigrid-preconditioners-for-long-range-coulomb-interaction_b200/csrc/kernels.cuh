@@ -781,3 +781,4 @@ __global__ void __launch_bounds__(BLOCK, 2) cg_persistent(MAT A, const double *_
 
 #include "pattern.cuh"
 #include "pattern_win.cuh"
+#include "pattern_win2.cuh"

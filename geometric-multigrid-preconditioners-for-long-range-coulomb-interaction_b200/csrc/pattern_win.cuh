@@ -201,6 +201,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 // Remainder rows (CSR, zeros dropped) with 4 lanes per row: every lane loads its quarter of the row's entries and
 // operands at once (two memory round trips per row instead of two per four entries), then the FMA chain runs through
 // the four lanes in entry order (the partial sum is handed on by shuffle): same order, same bits as the SELL path.
+__device__ __forceinline__ double rem_row_dot4_at(const PatView &A, int p0, int len, int c /* lane & 3 */, const double *__restrict__ x);
 __device__ __forceinline__ double rem_row_dot4(const PatView &A, int k /* remainder row or -1 */, int c /* lane & 3 */,
                                                const double *__restrict__ x) {
   int p0 = 0, len = 0;
@@ -208,6 +209,10 @@ __device__ __forceinline__ double rem_row_dot4(const PatView &A, int k /* remain
     p0 = __ldg(A.rem_ptr + k);
     len = __ldg(A.rem_ptr + k + 1) - p0;
   }
+  return rem_row_dot4_at(A, p0, len, c, x);
+}
+// (the row's entries are rem_ccol / rem_cval [p0, p0 + len); len == 0: no row)
+__device__ __forceinline__ double rem_row_dot4_at(const PatView &A, int p0, int len, int c, const double *__restrict__ x) {
   const int lmax = __reduce_max_sync(0xffffffffu, len);
   double acc = 0.0;
   for (int base = 0; base < lmax; base += 32) {  // 32 entries per round, 8 per lane

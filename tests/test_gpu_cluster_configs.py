@@ -116,7 +116,7 @@ def test_64k_atoms_energy_and_rhs_match_cpu_port(tmp_path):
     total = short + fe - self_e
     assert abs(e["analytic"] - analytic) <= 1e-11 * abs(analytic)
     assert abs(e["short"] - short) <= 1e-11 * abs(short)
-    assert abs(e["self"] - self_e) <= 1e-13 * self_e
+    assert abs(e["self"] - self_e) <= 1e-11 * self_e  # (64000 terms added one by one on the host)
     assert abs(e["fe"] - fe) <= 1e-9 * abs(fe)
     assert abs(e["total"] - total) <= 1e-9 * abs(total)
     assert "Total electrostatic energy with split in short- and long-ranged" in text
