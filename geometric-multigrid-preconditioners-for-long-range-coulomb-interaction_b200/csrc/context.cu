@@ -1465,6 +1465,7 @@ static int dist_setup(gmg_context *h);
 static int dist_pcg(gmg_context *h, const double *b_global, double *x_global, int max_it, double tol, int *iters,
                     double *res0_out, double *res_out);
 static int dist_vcycle(gmg_context *h, const double *src, double *dst);
+static int dist_matrix_norms(gmg_context *h, DistMat &M, double out[3]);
 static void dist_free(gmg_context *h);
 static int dist_gather(gmg_context *h, const GatherPlan &G, const double *src, int channel);
 
@@ -2171,6 +2172,7 @@ int gmg_smooth(gmg_handle h, int level, const double *rhs, double *u, int zero_s
 int gmg_matrix_norms(gmg_handle h, int which, int level, double out[3]) {
   if (!h || !out) return GMG_EINVAL;
   gmg::enter(h);
+  if (h->dist.on && which == GMG_SYSTEM) return dist_matrix_norms(h, h->dist.S, out);
   Sell *A = pick(h, which, level);
   if (!A) return fail(h, GMG_EINVAL, "matrix not available");
   const int n = A->v.n_rows, nc = A->v.n_cols;

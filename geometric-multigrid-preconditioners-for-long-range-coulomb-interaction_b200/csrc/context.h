@@ -110,6 +110,12 @@ struct DistMat {
   unsigned char *send_peer = nullptr;
   uint32_t dst_mask = 0, src_mask = 0;
   std::vector<int> h_send_src;  // host copy (sorted by source row)
+  // reverse halo exchange (gmg_matrix_norms: column sums of halo columns go back to their owners): every halo entry
+  // of my extended vector is pushed to its owner's staging area [sender rank][position in the sender's extended vector]
+  int n_rev = 0, rev_stride = 0;
+  int *rev_src = nullptr, *rev_dst = nullptr;
+  unsigned char *rev_peer = nullptr;
+  size_t rev_region = 0;
 };
 
 // "push my owned entries of a list to every rank" (all-gather over peer memory)

@@ -19,7 +19,7 @@ constexpr size_t DIST_HEADER_BYTES = 8192;
 // (area 0: stream-ordered dist_allreduce, area 1: the persistent CG kernel -- never share slots)
 constexpr size_t DIST_OFF_RED = 2048, DIST_OFF_GSUM = 3072;
 enum { CH_RED = 0, CH_HALO_SYS_X = 1, CH_HALO_SYS_D = 2, CH_GATHER_G = 3, CH_GATHER_C = 4, CH_CG_RED = 5, CH_CG_HALO = 6,
-       CH_GATHER_X = 7, CH_BARRIER = 8 };
+       CH_GATHER_X = 7, CH_BARRIER = 8, CH_REV = 9 };
 
 struct DistPeers {
   int rank, world;
@@ -110,6 +110,15 @@ __global__ void dist_allreduce(DistPeers P, double *v, int k, uint64_t seq, int 
       for (int r = 0; r < P.world; ++r) s += dist_red(P.peer[P.rank], par, r)[i];
       v[i] = s;
     }
+}
+
+// reverse halo exchange, receiving side: what peer p accumulated for my owned entry send_src[k] sits in my staging area
+// at [p][the position send_dst[k] of that entry in p's extended vector]
+__global__ void dist_rev_add(int n, const int *__restrict__ send_src, const unsigned char *__restrict__ send_peer,
+                             const int *__restrict__ send_dst, const double *__restrict__ staging, int stride,
+                             double *__restrict__ owned) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) atomicAdd(owned + send_src[k], staging[(size_t)send_peer[k] * stride + send_dst[k]]);
 }
 
 // scatter/gather helpers on local data

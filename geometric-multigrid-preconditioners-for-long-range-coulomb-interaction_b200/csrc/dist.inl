@@ -70,6 +70,10 @@ static int dist_gather(gmg_context *h, const GatherPlan &G, const double *src, i
 }
 
 static void free_distmat(DistMat &M) {
+  dfree(M.rev_src);
+  dfree(M.rev_dst);
+  dfree(M.rev_peer);
+  M.n_rev = 0;
   free_sell(M.A);
   dfree(M.send_src);
   dfree(M.send_dst);
@@ -85,7 +89,7 @@ static void free_gather(GatherPlan &G) {
 }
 
 static int build_distmat(gmg_context *h, const HostCsr &g, const std::vector<int32_t> &owner, DistMat &M, LocalMatrix &lm,
-                         ExchangePlan &plan) {
+                         ExchangePlan &plan, bool with_reverse = false) {
   DistData &d = h->dist;
   partition_matrix(d.rank, d.world, g.n_rows, g.n_cols, g.rowptr.data(), g.col.data(), g.val.data(), owner.data(),
                    owner.data(), lm, plan);
@@ -133,6 +137,25 @@ static int build_distmat(gmg_context *h, const HostCsr &g, const std::vector<int
       hpos[i] = sdst[i] - (d.rank > (int)speer[i] ? plan.n_owned_of[speer[i]] : 0);
     if (int rc = to_device(h, M.send_hpos, hpos)) return rc;
   }
+  if (with_reverse) {
+    int stride = 1;
+    for (int q = 0; q < d.world; ++q) stride = std::max(stride, plan.n_owned_of[q] + plan.n_halo_of[q]);
+    M.rev_stride = stride;
+    // (symmetric allocation: every rank reaches this point with the same sizes)
+    if (int rc = sym_alloc(h, sizeof(double) * (size_t)stride * d.world, M.rev_region)) return rc;
+    std::vector<int> rsrc, rdst;
+    std::vector<unsigned char> rpeer;
+    for (int e = 0; e < lm.n_halo; ++e) {
+      const int pos = e < lm.n_halo_lo ? e : lm.n_owned + e;  // position in my extended vector
+      rsrc.push_back(pos);
+      rdst.push_back(d.rank * stride + pos);
+      rpeer.push_back((unsigned char)lm.halo_owner[e]);
+    }
+    M.n_rev = (int)rsrc.size();
+    if (int rc = to_device(h, M.rev_src, rsrc)) return rc;
+    if (int rc = to_device(h, M.rev_dst, rdst)) return rc;
+    if (int rc = to_device(h, M.rev_peer, rpeer)) return rc;
+  }
   M.h_send_src = ssrc;
   M.n_send = (int)ssrc.size();
   if (int rc = to_device(h, M.send_src, ssrc)) return rc;
@@ -176,7 +199,7 @@ static int dist_setup(gmg_context *h) {
   int rc;
   {
     TraceScope tr("  dist: system matrix");
-    if ((rc = build_distmat(h, d.hS, d.sys_owner, d.S, lmS, plS))) return rc;
+    if ((rc = build_distmat(h, d.hS, d.sys_owner, d.S, lmS, plS, true))) return rc;
   }
   {
     TraceScope tr("  dist: level-0 matrix");
@@ -571,6 +594,61 @@ static int dist_pcg(gmg_context *h, const double *b_global, double *x_global, in
     GMG_LAUNCH_CHECK(h);
   }
   return finish();
+}
+
+// L1 / Linf / Frobenius norm of a row-partitioned matrix: row sums and squares are local; the column sums a rank
+// accumulates for its halo columns travel back to the columns' owners (reverse halo exchange), maxima and the sum of
+// squares are combined over the ranks in rank order (the same bits on every rank).
+static int dist_matrix_norms(gmg_context *h, DistMat &M, double out[3]) {
+  DistData &d = h->dist;
+  if (!M.A.valid || M.rev_stride == 0) return fail(h, GMG_EINVAL, "matrix norms: no reverse exchange plan for this matrix");
+  const int n = M.n_owned, ext = M.n_owned + M.n_halo;
+  const int grid = cdiv(std::max(n, 1), 256);
+  if (grid > h->partials_cap) return fail(h, GMG_EINVAL, "matrix too large for the partials buffer");
+  if (int rc = ensure_stage(h, ext)) return rc;
+  double *colsum = h->stage_a;
+  GMG_CUDA(h, cudaMemsetAsync(colsum, 0, sizeof(double) * std::max(ext, 1), h->stream));
+  sell_norm_partials<<<grid, 256, 0, h->stream>>>(M.A.v, colsum + M.n_halo_lo, h->partials, h->partials + h->partials_cap);
+  GMG_LAUNCH_CHECK(h);
+  if (int rc = dist_exchange(h, M.n_rev, M.rev_src, M.rev_peer, M.rev_dst, M.rev_region, colsum, CH_REV, M.src_mask, M.dst_mask))
+    return rc;
+  if (M.n_send > 0) {
+    dist_rev_add<<<cdiv(M.n_send, 256), 256, 0, h->stream>>>(M.n_send, M.send_src, M.send_peer, M.send_dst,
+                                                             reinterpret_cast<const double *>(d.buf + M.rev_region), M.rev_stride,
+                                                             colsum + M.n_halo_lo);
+    GMG_LAUNCH_CHECK(h);
+  }
+  const int g2 = std::min(cdiv(std::max(n, 1), 256), h->partials_cap);
+  vec_max_partials<<<g2, 256, 0, h->stream>>>(n, colsum + M.n_halo_lo, h->partials + 2 * h->partials_cap);
+  GMG_LAUNCH_CHECK(h);
+  std::vector<double> rowmax(grid), frob(grid), colmax(g2);
+  GMG_CUDA(h, copy(h, rowmax.data(), h->partials, sizeof(double) * grid, cudaMemcpyDeviceToHost));
+  GMG_CUDA(h, copy(h, frob.data(), h->partials + h->partials_cap, sizeof(double) * grid, cudaMemcpyDeviceToHost));
+  GMG_CUDA(h, copy_sync(h, colmax.data(), h->partials + 2 * h->partials_cap, sizeof(double) * g2, cudaMemcpyDeviceToHost));
+  double mine[3] = {n > 0 ? *std::max_element(colmax.begin(), colmax.end()) : 0.0,
+                    n > 0 ? *std::max_element(rowmax.begin(), rowmax.end()) : 0.0, 0.0};
+  for (double v : frob) mine[2] += v;
+  // every rank's three numbers on every rank: sums of vectors that are zero outside the contributing rank's slot
+  std::vector<double> all(3 * (size_t)d.world, 0.0);
+  double *dv = nullptr;
+  GMG_CUDA(h, dalloc(&dv, 4));
+  for (int r = 0; r < d.world; ++r) {
+    double v[4] = {0, 0, 0, 0};
+    if (r == d.rank) std::copy(mine, mine + 3, v);
+    GMG_CUDA(h, copy(h, dv, v, sizeof(v), cudaMemcpyHostToDevice));
+    if (int rc = dist_allreduce1(h, dv, 3)) return rc;
+    GMG_CUDA(h, copy_sync(h, &all[3 * (size_t)r], dv, sizeof(double) * 3, cudaMemcpyDeviceToHost));
+  }
+  dfree(dv);
+  if (int rc = dist_check_error(h)) return rc;
+  out[0] = out[1] = out[2] = 0.0;
+  for (int r = 0; r < d.world; ++r) {
+    out[0] = std::max(out[0], all[3 * r]);
+    out[1] = std::max(out[1], all[3 * r + 1]);
+    out[2] += all[3 * r + 2];
+  }
+  out[2] = std::sqrt(out[2]);
+  return GMG_OK;
 }
 
 static void dist_free(gmg_context *h) {

@@ -7,6 +7,9 @@
 #include <sstream>
 
 #include "step_50.h"
+
+#include <sys/wait.h>
+#include <unistd.h>
 #include "capi_ministep.h"
 
 using namespace ministep;
@@ -284,6 +287,43 @@ int step50_bench_time_binning(void *p, double *ms, int64_t *pairs) {
     *ms = ((BenchHolder *)p)->problem->time_binning(pairs);
   } catch (std::exception &e) { g_err = e.what(); return -1; }
   return 0;
+}
+// CPU self-test of the process rendezvous (host/rendezvous.h): forks world - 1 processes, every rank all-gathers a
+// 64-byte blob derived from its rank, twice, with a barrier in between.  0 = every rank saw every blob.
+int step50_rendezvous_selftest(int world, int port) {
+  if (world < 1 || world > 64) return -1;
+  setenv("MASTER_ADDR", "127.0.0.1", 1);
+  setenv("GMG_RENDEZVOUS_PORT", std::to_string(port).c_str(), 1);
+  setenv("WORLD_SIZE", std::to_string(world).c_str(), 1);
+  std::vector<pid_t> kids;
+  int rank = 0;
+  for (int r = 1; r < world; ++r) {
+    const pid_t pid = fork();
+    if (pid < 0) return -2;
+    if (pid == 0) { rank = r; kids.clear(); break; }
+    kids.push_back(pid);
+  }
+  setenv("RANK", std::to_string(rank).c_str(), 1);
+  setenv("LOCAL_RANK", std::to_string(rank).c_str(), 1);
+  int bad = 0;
+  try {
+    Step50::Rendezvous rv;
+    for (int round = 0; round < 2; ++round) {
+      std::vector<unsigned char> mine(64), all(64 * (size_t)world);
+      for (int i = 0; i < 64; ++i) mine[i] = (unsigned char)(rv.rank * 7 + i + round);
+      rv.all_gather(mine.data(), all.data(), 64);
+      for (int r = 0; r < world; ++r)
+        for (int i = 0; i < 64; ++i) bad += all[64 * (size_t)r + i] != (unsigned char)(r * 7 + i + round);
+      rv.barrier();
+    }
+  } catch (std::exception &e) { g_err = e.what(); bad = 1000; }
+  if (rank != 0) _exit(bad ? 1 : 0);
+  for (pid_t pid : kids) {
+    int st = 0;
+    if (waitpid(pid, &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) ++bad;
+  }
+  unsetenv("RANK"); unsetenv("LOCAL_RANK"); unsetenv("WORLD_SIZE"); unsetenv("GMG_RENDEZVOUS_PORT");
+  return bad;
 }
 int step50_bench_vectors(void *p, double *solution_out, double *rhs_out) {
   BenchProblem &b = *((BenchHolder *)p)->problem;

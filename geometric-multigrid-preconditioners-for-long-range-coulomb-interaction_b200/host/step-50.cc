@@ -8,6 +8,10 @@
 #include <cstring>
 #include <fstream>
 #include <iomanip>
+#include <thread>
+
+#include <signal.h>
+#include <sys/wait.h>
 
 using namespace ministep;
 
@@ -747,8 +751,26 @@ void LaplaceProblem<dim>::postprocess_error_in_energy_norm() {
 }
 
 // =============================================================================== run (src/step-50.cc:1463-1573)
+// One process per GPU: exchange the CUDA IPC handles of the ranks' communication buffers (host all-gather = control
+// plane), map the peers.  From here on gmg_set_ownership / gmg_setup partition the system matrix and level 0.
+template <int dim>
+void LaplaceProblem<dim>::connect_ranks() {
+  if (!ranks || ranks->world == 1) return;
+  const char *cb = std::getenv("GMG_COMM_BYTES");
+  const int64_t comm_bytes = cb ? std::atoll(cb) : (int64_t)512 << 20;
+  std::vector<char> mine(64), all(64 * (size_t)ranks->world);
+  gmg_check(gmg_dist_init(gmg, ranks->rank, ranks->world, comm_bytes, mine.data()), "gmg_dist_init");
+  ranks->all_gather(mine.data(), all.data(), 64);
+  gmg_check(gmg_dist_connect(gmg, all.data()), "gmg_dist_connect");
+  ranks->barrier();
+}
+
 template <int dim>
 void LaplaceProblem<dim>::begin_run() {
+  if (connect_in_run) {
+    ranks.reset(new Rendezvous());
+    if (ranks->rank != 0) pcout = &null_out;  // ConditionalOStream pcout(std::cout, this_mpi_process == 0)
+  }
   std::ostream &out = *pcout;
   out << "Problem type is:   " << Problemtype << std::endl;
   out << "Preconditioner :    " << PreconditionerType << std::endl;
@@ -756,10 +778,12 @@ void LaplaceProblem<dim>::begin_run() {
     out << "Rhs assembly optimization ENABLED" << std::endl;
   else
     out << "Without rhs assembly optimization" << std::endl;
-  out << "Running with B200 (sm_100a CUDA) on 1 GPU(s)..." << std::endl;
+  // the reference: "Running with Trilinos on N MPI rank(s)..." (src/step-50.cc:1476-1482)
+  out << "Running with B200 (sm_100a CUDA) on " << (ranks ? ranks->world : 1) << " GPU(s)..." << std::endl;
   if (dim != 3) throw ExcMessage("Only dim = 3 is implemented on the B200 path.");
-  if (gmg_create(gpu_device, &gmg) != GMG_OK)
+  if (gmg_create(gpu_device + (ranks ? ranks->local_rank : 0), &gmg) != GMG_OK)
     throw ExcMessage("gmg_create failed: no B200 (sm_100) CUDA device; this path has no CPU fallback.");
+  connect_ranks();
   computing_timer.reset();
   run_start = std::chrono::steady_clock::now();
   out << "Dimension:\t" << dim << std::endl;
@@ -808,6 +832,7 @@ template <int dim>
 void LaplaceProblem<dim>::end_run() {
   std::ostream &out = *pcout;
   rec = nullptr;
+  if (ranks) ranks->barrier();  // no rank unmaps its buffers while a peer may still store into them
   if (flag_output_time) computing_timer.print_summary(out);
   if (flag_output_time)
     out << "   \nTotal Elapsed wall time for solution: "
@@ -817,6 +842,7 @@ void LaplaceProblem<dim>::end_run() {
 
 template <int dim>
 void LaplaceProblem<dim>::run() {
+  connect_in_run = true;
   begin_run();
   for (unsigned int cycle = 0; cycle < number_of_adaptive_refinement_cycles; ++cycle) {
     cycle_until_solve(cycle);
@@ -899,14 +925,72 @@ void step50_run_from_string(const std::string &prm_text, std::ostream &out, std:
   });
 }
 
+// `main -np N file.prm`: what `mpirun -np N main file.prm` is for the reference, without an MPI installation: fork one
+// process per GPU (before anything touches CUDA), give each its RANK / LOCAL_RANK / WORLD_SIZE and a free rendezvous port.
+// Returns the rank of this process; `children` holds the pids rank 0 has to wait for.
+static int fork_ranks(int n, std::vector<pid_t> &children) {
+  int port = 0;
+  {
+    const int fd = ::socket(AF_INET, SOCK_STREAM, 0);
+    sockaddr_in sa{};
+    sa.sin_family = AF_INET;
+    sa.sin_addr.s_addr = htonl(INADDR_LOOPBACK);
+    socklen_t len = sizeof(sa);
+    if (fd >= 0 && ::bind(fd, (sockaddr *)&sa, sizeof(sa)) == 0 && ::getsockname(fd, (sockaddr *)&sa, &len) == 0)
+      port = ntohs(sa.sin_port);
+    if (fd >= 0) ::close(fd);
+  }
+  if (port == 0) throw Step50::ExcMessage("main -np: no free TCP port for the rendezvous");
+  ::setenv("MASTER_ADDR", "127.0.0.1", 1);
+  ::setenv("GMG_RENDEZVOUS_PORT", std::to_string(port).c_str(), 1);
+  ::setenv("WORLD_SIZE", std::to_string(n).c_str(), 1);
+  if (!std::getenv("OMP_NUM_THREADS")) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    ::setenv("OMP_NUM_THREADS", std::to_string(std::max(1u, hw / (unsigned)n)).c_str(), 1);
+  }
+  int rank = 0;
+  for (int r = 1; r < n; ++r) {
+    const pid_t pid = ::fork();
+    if (pid < 0) throw Step50::ExcMessage("main -np: fork failed");
+    if (pid == 0) {
+      rank = r;
+      children.clear();
+      break;
+    }
+    children.push_back(pid);
+  }
+  ::setenv("RANK", std::to_string(rank).c_str(), 1);
+  ::setenv("LOCAL_RANK", std::to_string(rank).c_str(), 1);
+  return rank;
+}
+
 int step50_main(int argc, char **argv, std::ostream &out) {
+  std::vector<pid_t> children;
+  int rank = 0;
   try {
     if (argc <= 1) throw Step50::ExcMessage("Invalid inputs. \nCall this program as <./main para_filename.prm>");
+    int file_arg = 1;
+    if (std::string(argv[1]) == "-np") {
+      if (argc <= 3 || std::atoi(argv[2]) < 1)
+        throw Step50::ExcMessage("Invalid inputs. \nCall this program as <./main -np N para_filename.prm>");
+      file_arg = 3;
+      if (std::atoi(argv[2]) > 1) rank = fork_ranks(std::atoi(argv[2]), children);
+    }
     ParameterHandler prm;
     ParameterReader param(prm);
     param.declare_parameters();
-    param.read_parameters(argv[1]);
+    param.read_parameters(argv[file_arg]);
     run_with(prm, out, [](const std::vector<Step50::CycleRecord> &) {});
+    int failed = 0;
+    for (pid_t pid : children) {
+      int status = 0;
+      if (::waitpid(pid, &status, 0) < 0 || !WIFEXITED(status) || WEXITSTATUS(status) != 0) ++failed;
+    }
+    if (failed) throw Step50::ExcMessage(std::to_string(failed) + " rank(s) of main -np failed");
+    if (rank != 0) {  // a forked rank: leave without running the parent's exit handlers twice
+      std::cout.flush();
+      ::_exit(0);
+    }
   } catch (std::exception &exc) {
     std::cerr << std::endl
               << std::endl
@@ -915,6 +999,8 @@ int step50_main(int argc, char **argv, std::ostream &out) {
               << exc.what() << std::endl
               << "Aborting!" << std::endl
               << "----------------------------------------------------" << std::endl;
+    if (rank != 0) ::_exit(1);
+    for (pid_t pid : children) ::kill(pid, SIGTERM);
     throw;
   }
   return 0;

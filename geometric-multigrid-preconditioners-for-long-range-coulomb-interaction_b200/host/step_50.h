@@ -19,6 +19,7 @@
 
 #include "../../include/gmg_b200.h"
 #include "ministep.h"
+#include "rendezvous.h"
 #include "parameter_handler.h"
 
 namespace Step50 {
@@ -176,6 +177,12 @@ class LaplaceProblem {
   std::vector<std::vector<float>> error_per_cell;
   std::vector<std::vector<char>> refine_flags;
   gmg_handle gmg = nullptr;
+  // multi-GPU run(): one process per GPU (the reference: one MPI rank per subdomain, src/step-50.cc:116-122); every
+  // rank keeps the whole mesh and the patch levels, the system matrix and level 0 are row-partitioned on the devices
+  std::unique_ptr<Rendezvous> ranks;
+  bool connect_in_run = false;  // run() joins the ranks the launcher started; the bench hooks connect through the caller
+  std::ostream null_out{nullptr};
+  void connect_ranks();
   std::chrono::steady_clock::time_point run_start;
   std::vector<CycleRecord> cycle_records;
   CycleRecord *rec = nullptr;

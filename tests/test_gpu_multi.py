@@ -1,11 +1,13 @@
 """Multi-GPU parity (needs >= 2 GPUs: `gpurun --gpus 2`): the row-partitioned solve over NVLink peer memory gives
 the single-GPU result -- same outer iteration count, same coarse iteration counts, solution to 1e-9 relative."""
 import os
+import re
+import subprocess
 
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, make_prm
 from helpers import pkg
 
 pytestmark = pytest.mark.gpu
@@ -76,3 +78,33 @@ def test_partitioned_solve_matches_single_gpu(world, smoother):
         assert coarse == coarse1
         assert abs(res - res1) <= 1e-6 * res1
     assert np.linalg.norm(x - x1) <= 1e-9 * np.linalg.norm(x1)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_main_np_reproduces_single_gpu_stdout(tmp_path, world):
+    """`main -np N file.prm` (the reference: `mpirun -np N main file.prm`, src/main.cc:8): LaplaceProblem::run() itself on
+    N GPUs, one forked process per GPU, system matrix and level 0 row-partitioned.  Rank 0's stdout carries the numbers
+    of the one-GPU run: mesh / DoF lines identical, norms of b and of the matrix identical (the same host assembly),
+    iteration counts equal, solution norms to 1e-9 relative."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    extra = "subsection Misc\n set Refinement indicator = Kelly\nend\nsubsection Solver input data\n set Smoother = MulticolourSSOR\nend\n"
+    prm = tmp_path / "gaussian-charges.prm"
+    prm.write_text(make_prm(cycles=3, atom=os.path.join(GOLDEN, "atom_n1_8.data"), extra=extra))
+    exe = os.path.join(os.path.dirname(pkg().capi.LIB_PATH), "main")
+    one = subprocess.run([exe, str(prm)], capture_output=True, text=True, timeout=900)
+    assert one.returncode == 0, one.stderr
+    many = subprocess.run([exe, "-np", str(world), str(prm)], capture_output=True, text=True, timeout=900)
+    assert many.returncode == 0, many.stderr
+    assert f"on {world} GPU(s)" in many.stdout and "on 1 GPU(s)" in one.stdout
+    assert many.stdout.count("Cycle ") == 3  # only rank 0 prints
+
+    def numbers(text, label):
+        return [float(x) for x in re.findall(label + r"\s+(\S+)", text)]
+    for label in ("Number of active cells:", "L2 rhs norm", "Frobenius Matrix norm", "Starting value", "CG converged in"):
+        assert numbers(one.stdout, label) == numbers(many.stdout, label), label
+    for label in ("L1 solution norm", "L2 solution norm", "LInfinity solution norm"):
+        a, b = numbers(one.stdout, label), numbers(many.stdout, label)
+        assert len(a) == 3 and len(b) == 3
+        assert all(abs(x - y) <= 1e-9 * abs(x) for x, y in zip(a, b)), (label, a, b)
