@@ -21,6 +21,50 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
+// One warp: wait until the first n (<= 32 * U) tagged 16-byte slots, `stride_u64` 64-bit words apart, carry `tag` in both
+// words; their payloads summed lane-strided first, then by the shuffle tree: the same bits for whoever adds them.
+// SYS: the slots are written by peer GPUs (system-scope loads).  All pending slots of a lane are read before any of
+// them is looked at (a load whose issue depends on the previous slot's tag would serialise the L2 round trips); the
+// loaded words themselves are the storage of the arrived values.  false: timed out (`limit` clocks).
+template <int U, bool SYS>
+__device__ __forceinline__ bool ll_collect_slots(const uint64_t *slots, size_t stride_u64, int n, uint32_t tag, long long limit,
+                                                 double &sum) {
+  const int lane = threadIdx.x & 31;
+  uint64_t w0[U], w1[U];
+  uint32_t pending = 0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    w0[u] = w1[u] = 0;
+    if (lane + 32 * u < n) pending |= 1u << u;
+  }
+  const long long t0 = clock64();
+  bool ok = true;
+  while (__any_sync(0xffffffffu, pending != 0u)) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (pending & (1u << u)) {
+        if (SYS)
+          asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[u]), "=l"(w1[u]) : "l"(slots + stride_u64 * (lane + 32 * u)) : "memory");
+        else
+          asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[u]), "=l"(w1[u]) : "l"(slots + stride_u64 * (lane + 32 * u)) : "memory");
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if ((uint32_t)(w0[u] >> 32) == tag && (uint32_t)(w1[u] >> 32) == tag) pending &= ~(1u << u);
+    if (clock64() - t0 > limit) {
+      ok = false;
+      break;
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  double s = 0.0;
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (lane + 32 * u < n) s += __longlong_as_double((long long)((w1[u] << 32) | (w0[u] & 0xffffffffull)));
+  sum = warp_sum(s);
+  return ok;
+}
+
 // Sum over the block; result valid in thread 0.  `red` needs blockDim.x/32 doubles.
 __device__ __forceinline__ double block_sum(double v, double *red) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

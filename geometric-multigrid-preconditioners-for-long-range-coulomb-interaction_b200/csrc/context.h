@@ -139,7 +139,7 @@ struct DistData {
   HostCsr hS, hA0;
   std::vector<std::vector<int32_t>> h_copy_g, h_copy_l;  // copy indices as handed over (global numbering)
   DistMat S, A0;
-  size_t reg_cg_d = 0, reg_cg_ll = 0, reg_pcg_d = 0, reg_pcg_x = 0;
+  size_t reg_cg_d = 0, reg_cg_ll = 0, reg_cg_slots = 0, reg_pcg_d = 0, reg_pcg_x = 0;
   int n_sys_owned = 0, n_l0_owned = 0, n_sys = 0, n_l0 = 0;
   int *sys_owned_global = nullptr;      // device: global index of each owned system dof
   // copy_to_mg / copy_from_mg

@@ -177,6 +177,9 @@ __global__ void dist_pingpong(DistPeers P, size_t region, int iters, int mode, u
   out[0] = clock64() - t0;
 }
 
+constexpr int DIST_CG_MAXB = 160;  // blocks of the distributed CG kernel a rank may run (one per SM; slots per rank and group)
+constexpr size_t DIST_CG_SLOT_BYTES = (size_t)6 * DIST_MAX_RANKS * DIST_CG_MAXB * 16;
+
 struct DistCgArgs {
   DistPeers P;
   int n_owned, n_halo, n_halo_lo;
@@ -187,74 +190,106 @@ struct DistCgArgs {
   const int *send_block_ptr;    // gridDim.x + 1: entries whose source row belongs to each block's slice range
   size_t region_d;     // symmetric offset of the extended direction vector [lower halo | owned | upper halo]
   size_t region_ll;    // symmetric offset of the LL receive area: 16 bytes per halo entry
+  int prof;            // gmg_debug_cg_phases: block (1-based) whose thread 0 times the phases of an iteration
+  size_t region_slots; // symmetric offset of the reduction / barrier slots: [6 groups][8 ranks][DIST_CG_MAXB] x 16 bytes
   uint32_t tag_base;   // launch id * 2^20: tags used inside the kernel are tag_base + counter (never 0)
 };
 
 // ------------------------------------------------------------------------------------------------
-// distributed persistent CG: the single-GPU cg_persistent plus, inside the same cooperative kernel,
-// the halo rows of d pushed straight into the neighbours (by the block that just updated them) and the
-// cross-GPU all-reduces of d.h and g.g, all as tagged LL words over NVLink: no fences, no flags, no extra
-// exchange kernels.  Per iteration: 3 grid.sync() exactly as on one GPU.
+// distributed persistent CG: the single-GPU cg_persistent plus, inside the same kernel, the halo rows of d pushed
+// straight into the neighbours (by the block that just updated them) and the all-reduces of d.h and g.g, all as tagged
+// LL words: no fences on the NVLink path, no flags, no extra exchange kernels, and NO grid.sync():
+//   * a reduction is ONE all-to-all step: every block stores {its partial sum, tag} into its slot on EVERY rank (W
+//     16-byte stores, W - 1 of them over NVLink); warp r of every block polls rank r's slots in local memory and adds
+//     them in a fixed order, the W totals are added in rank order: every block of every rank obtains the same bits one
+//     NVLink latency after the last block arrived (before: grid.sync + block 0 sums the partials + NVLink + poll);
+//   * the barrier after the direction update is rank-local (tagged slots of the rank's own blocks); the halo entries
+//     synchronise themselves through their tags.
+// The launch stays cooperative (co-residency of all blocks is what the spinning needs).
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK, class MAT>
-__global__ void __launch_bounds__(BLOCK, 2) cg_persistent_dist(MAT A, const double *__restrict__ b, double *x, double *g,
+__global__ void __launch_bounds__(BLOCK, 1) cg_persistent_dist(MAT A, const double *__restrict__ b, double *x, double *g,
                                                             double *h, double *partials, int max_it, double tol,
                                                             CgResult *result, DistCgArgs D, int *error) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
-  __shared__ double red[32];
-  __shared__ double s_bc;
+  __shared__ double red[64];
+  __shared__ double s_tot[2][DIST_MAX_RANKS];
   __shared__ RowSmem<MAT> row_smem;
   RowDot<MAT> row_dot;
   row_dot.init(A, row_smem);
   const int nb = gridDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int WPB = BLOCK / 32;
+  static_assert(WPB >= DIST_MAX_RANKS, "one polling warp per rank");
   const int s_begin = (int)(((int64_t)A.n_slices * blockIdx.x) / nb);
   const int s_end = (int)(((int64_t)A.n_slices * (blockIdx.x + 1)) / nb);
   char *mine = D.P.peer[D.P.rank];
   double *d_ext = reinterpret_cast<double *>(mine + D.region_d);
   double *d = d_ext + D.n_halo_lo;  // first owned entry; lower-rank halo entries sit at negative indices
   const uint64_t *ll_in = reinterpret_cast<const uint64_t *>(mine + D.region_ll);
-  uint32_t nred = 0, nhalo = 0;
-  // A wait that times out sets *error; control flow changes only at the check right after the NEXT grid.sync(),
-  // where every block reads the same value: no block ever leaves a barrier the others still need.
+  uint32_t nred = 0, nhalo = 0, nbar = 0;
+  const int prof = D.prof;
+  unsigned long long t_prev = 0;
+  // A wait that times out (~20 s) sets *error; every other wait of the kernel is bounded too, so all blocks leave.
   bool aborted = false;
   volatile int *abort_flag = error;
+  auto slot_of = [&](char *base, int group, int rank, int block) {
+    return reinterpret_cast<uint64_t *>(base + D.region_slots) + 2 * (((size_t)group * DIST_MAX_RANKS + rank) * DIST_CG_MAXB + block);
+  };
 
-  // sum over the grid and over the ranks: 1 grid sync; block 0 publishes the local total to every rank,
-  // every block reads all ranks' totals (local memory) and adds them in rank order
-  auto all_sum = [&](double block_value) -> double {
-    if (threadIdx.x == 0) partials[blockIdx.x] = block_value;
-    grid.sync();
-    if (*abort_flag) aborted = true;
-    if (aborted) return 0.0;
+  // sum over all blocks of all ranks; `fence`: the step also orders the rank's global writes before it against the
+  // reads after it (h of the remainder rows is written by one block and read by another)
+  auto all_sum = [&](double v, bool fence) -> double {
     ++nred;
     const uint32_t tag = D.tag_base + nred;
-    // Slot group = launch parity x reduction parity.  Reductions restart at 1 in every launch, and a slow peer block may
-    // still be reading the LAST reduction of launch k when a fast rank starts launch k + 1: consecutive launches use
-    // disjoint slot groups, and a rank cannot be two launches ahead (its reductions of launch k + 1 need every peer's
-    // contribution of launch k + 1), so a slot is never rewritten while a peer still polls it for an older tag.
-    const int par = (int)(((D.tag_base >> 20) & 1u) * 2u + (nred & 1u));
+    // Slot group = launch parity x reduction parity.  A block can be one reduction ahead of the slowest block (never
+    // two: reduction n + 1 completes only when every block has published it, i.e. has finished collecting n), and a rank
+    // one launch ahead of a slow peer block still polling the last reduction of the previous launch.
+    const int par = (int)(nred & 1u);
+    const int group = (int)(((D.tag_base >> 20) & 1u) * 2u) + par;
+    v = warp_sum(v);
+    if (lane == 0) red[par * 32 + warp] = v;
+    __syncthreads();
     if (warp == 0) {
-      if (blockIdx.x == 0) {
-        const double s = warp_sum_partials(partials, nb);
-        if (lane < D.P.world)
-          ll_store(reinterpret_cast<uint64_t *>(D.P.peer[lane] + DIST_OFF_LLRED) + (par * 8 + D.P.rank) * 2, s, tag);
-      }
-      double v = 0.0;
-      bool ok = true;
-      if (lane < D.P.world)
-        ok = ll_load(reinterpret_cast<const uint64_t *>(mine + DIST_OFF_LLRED) + (par * 8 + lane) * 2, tag, v);
-      if (!__all_sync(0xffffffffu, ok) && lane == 0) *abort_flag = 1;
-      double tot = 0.0;
-      for (int r = 0; r < D.P.world; ++r) tot += __shfl_sync(0xffffffffu, v, r);  // rank order
-      if (lane == 0) s_bc = tot;
+      double r = lane < WPB ? red[par * 32 + lane] : 0.0;
+      r = warp_sum(r);
+      if (fence && lane == 0) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      __syncwarp();
+      if (lane < D.P.world) ll_store(slot_of(D.P.peer[lane], group, D.P.rank, blockIdx.x), r, tag);
     }
+    if (warp < D.P.world) {
+      double s;
+      const bool ok = ll_collect_slots<DIST_CG_MAXB / 32, true>(slot_of(mine, group, warp, 0), 2, nb, tag, 40000000000LL, s);
+      if (lane == 0) {
+        if (fence && warp == D.P.rank) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        s_tot[par][warp] = s;
+        if (!ok) *abort_flag = 1;
+      }
+    }
+    if (__syncthreads_or(*abort_flag != 0)) aborted = true;  // (block-uniform)
+    double tot = 0.0;
+    for (int r = 0; r < D.P.world; ++r) tot += s_tot[par][r];  // rank order
+    return aborted ? 0.0 : tot;
+  };
+  // barrier over the blocks of this rank, with release / acquire of their global writes (the owned rows and the unpacked
+  // halo entries of d)
+  auto rank_barrier = [&]() {
+    ++nbar;
+    const uint32_t tag = D.tag_base + (1u << 18) + nbar;
+    const int group = 4 + (int)(nbar & 1u);
     __syncthreads();
-    const double r = s_bc;
-    __syncthreads();
-    return r;
+    if (warp == 0) {
+      if (lane == 0) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        ll_store(slot_of(mine, group, D.P.rank, blockIdx.x), 0.0, tag);
+      }
+      double s;
+      const bool ok = ll_collect_slots<DIST_CG_MAXB / 32, true>(slot_of(mine, group, D.P.rank, 0), 2, nb, tag, 40000000000LL, s);
+      if (lane == 0) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if (!ok) *abort_flag = 1;
+      }
+    }
+    if (__syncthreads_or(*abort_flag != 0)) aborted = true;
   };
   // after this block's rows of d are written: push its boundary rows, then help unpacking the incoming halo
   auto exchange_halo = [&]() {
@@ -285,8 +320,8 @@ __global__ void __launch_bounds__(BLOCK, 2) cg_persistent_dist(MAT A, const doub
     }
   }
   exchange_halo();
-  acc = block_sum(acc, red);
-  double res2 = all_sum(acc);  // its grid sync also publishes d (owned + halo) to every block
+  rank_barrier();  // d (owned rows and unpacked halo) visible to every block
+  double res2 = all_sum(acc, false);
   double res = sqrt(res2);
   const double res0 = res;
   int it = 0, status = 0;
@@ -295,6 +330,10 @@ __global__ void __launch_bounds__(BLOCK, 2) cg_persistent_dist(MAT A, const doub
     double gh = res * res;
     while (true) {
       ++it;
+      if (prof && blockIdx.x == prof - 1 && threadIdx.x == 0) {
+        t_prev = gtime();
+        g_cg_phase_ns[6] += 1;
+      }
       acc = 0.0;
       for (int s = s_begin + warp; s < s_end; s += WPB) {
         if (s + WPB < s_end) row_dot.prefetch(A, s + WPB, lane);
@@ -309,8 +348,9 @@ __global__ void __launch_bounds__(BLOCK, 2) cg_persistent_dist(MAT A, const doub
         h[r] = ad;
         acc += d[r] * ad;
       });
-      acc = block_sum(acc, red);
-      const double alpha = gh / all_sum(acc);
+      GMG_PHASE(0)
+      const double alpha = gh / all_sum(acc, true);
+      GMG_PHASE(1)
       if (aborted) { status = 2; break; }
       acc = 0.0;
       for (int s = s_begin + warp; s < s_end; s += WPB) {
@@ -322,8 +362,9 @@ __global__ void __launch_bounds__(BLOCK, 2) cg_persistent_dist(MAT A, const doub
           acc += gv * gv;
         }
       }
-      acc = block_sum(acc, red);
-      res2 = all_sum(acc);
+      GMG_PHASE(2)
+      res2 = all_sum(acc, false);
+      GMG_PHASE(3)
       res = sqrt(res2);
       if (aborted) { status = 2; break; }
       if (res <= tol) break;
@@ -334,9 +375,11 @@ __global__ void __launch_bounds__(BLOCK, 2) cg_persistent_dist(MAT A, const doub
         const int r = s * 32 + lane;
         if (r < A.n_rows) d[r] = beta * d[r] - g[r];
       }
+      GMG_PHASE(4)
       exchange_halo();
-      grid.sync();  // d (owned rows and unpacked halo) visible to every block
-      if (*abort_flag) aborted = true;
+      GMG_PHASE(7)
+      rank_barrier();  // d (owned rows and unpacked halo) visible to every block
+      GMG_PHASE(5)
       if (aborted) { status = 2; break; }
     }
   }

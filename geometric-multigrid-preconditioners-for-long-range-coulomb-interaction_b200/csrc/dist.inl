@@ -216,9 +216,9 @@ static int dist_setup(gmg_context *h) {
     int per_sm = 0;
     const bool pat = d.A0.A.patterned && h->compress >= 2;
     const bool comp = !pat && d.A0.A.compressed && h->compress;
-    cudaError_t e = pat    ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_dist<512, PatView>, 512, 0)
-                    : comp ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_dist<512, CsellView>, 512, 0)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_dist<512, SellView>, 512, 0);
+    cudaError_t e = pat    ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_dist<1024, PatView>, 1024, 0)
+                    : comp ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_dist<1024, CsellView>, 1024, 0)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_dist<1024, SellView>, 1024, 0);
     if (e != cudaSuccess || per_sm < 1) return fail(h, GMG_ECUDA, "occupancy query of the distributed CG kernel failed");
     d.cg_grid = h->sm_count * per_sm;
   }
@@ -247,6 +247,8 @@ static int dist_setup(gmg_context *h) {
     int halo_max = 0;
     for (int q = 0; q < d.world; ++q) halo_max = std::max(halo_max, plA.n_halo_of[q]);
     if ((rc = sym_alloc(h, 16 * (size_t)std::max(halo_max, 1), d.reg_cg_ll))) return rc;
+    if ((rc = sym_alloc(h, DIST_CG_SLOT_BYTES, d.reg_cg_slots))) return rc;
+    if (d.cg_grid > DIST_CG_MAXB) return fail(h, GMG_EINVAL, "distributed CG: more blocks than reduction slots");
   }
   if ((rc = to_device(h, d.sys_owned_global, lmS.owned_global))) return rc;
   std::vector<int> sys_g2l(d.n_sys, -1), l0_g2l(d.n_l0, -1);
@@ -376,6 +378,8 @@ static int dist_coarse_cg(gmg_context *h, const double *b, double *x) {
   D.send_block_ptr = d.cg_send_block_ptr;
   D.region_d = d.reg_cg_d;
   D.region_ll = d.reg_cg_ll;
+  D.region_slots = d.reg_cg_slots;
+  D.prof = h->cg_prof;
   // 12-bit launch id in the tag: a tag repeats only after 4096 launches, by when every slot it was used on has been
   // overwritten hundreds of times (each launch rewrites its reduction slots and the whole halo area); 0 is skipped in a
   // way that keeps the parity alternating (ids run 1, 2, ..., 4095, 4098 -> 2 would repeat: skip two at the wrap)
@@ -393,13 +397,13 @@ static int dist_coarse_cg(gmg_context *h, const double *b, double *x) {
     cudaEventRecord(h->ev_begin[ev], h->stream);
   }
   if (pat)
-    GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_dist<512, PatView>, dim3(grid), dim3(512), args, 0,
+    GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_dist<1024, PatView>, dim3(grid), dim3(1024), args, 0,
                                             h->stream));
   else if (comp)
-    GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_dist<512, CsellView>, dim3(grid), dim3(512), args, 0,
+    GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_dist<1024, CsellView>, dim3(grid), dim3(1024), args, 0,
                                             h->stream));
   else
-    GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_dist<512, SellView>, dim3(grid), dim3(512), args, 0,
+    GMG_CUDA(h, cudaLaunchCooperativeKernel((void *)cg_persistent_dist<1024, SellView>, dim3(grid), dim3(1024), args, 0,
                                             h->stream));
   h->launches++;
   if (ev >= 0) {

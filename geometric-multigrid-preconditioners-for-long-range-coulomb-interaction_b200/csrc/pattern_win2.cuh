@@ -35,44 +35,6 @@ __device__ __forceinline__ void llg_store(uint64_t *p /*16-byte aligned pair*/, 
   asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
 }
 
-// One warp: wait until the slots of all nb blocks carry `tag`; their sum in the order of warp_sum_partials (lane-strided
-// serial sums, then the shuffle tree), so every block obtains the same bits.  false: timed out (~2 s).
-__device__ __forceinline__ bool llg_collect(const uint64_t *slots, int slot_u64, int nb, uint32_t tag, double &sum) {
-  const int lane = threadIdx.x & 31;
-  constexpr int U = WIN2_MAX_BLOCKS / 32;
-  double v[U];
-  uint32_t pending = 0;
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    v[u] = 0.0;
-    if (lane + 32 * u < nb) pending |= 1u << u;
-  }
-  const long long t0 = clock64();
-  bool ok = true;
-  while (__any_sync(0xffffffffu, pending != 0u)) {
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (pending & (1u << u)) {
-        uint64_t w0, w1;
-        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slots + (size_t)slot_u64 * (lane + 32 * u)) : "memory");
-        if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag) {
-          v[u] = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
-          pending &= ~(1u << u);
-        }
-      }
-    if (clock64() - t0 > 4000000000LL) {
-      ok = false;
-      break;
-    }
-  }
-  ok = __all_sync(0xffffffffu, ok);
-  double s = 0.0;
-#pragma unroll
-  for (int u = 0; u < U; ++u) s += v[u];
-  sum = warp_sum(s);
-  return ok;
-}
-
 // Sum over all blocks + barrier, every thread contributes `v`.  FENCE: the barrier also orders the blocks' global
 // writes before it against the reads after it (release fence before the publish, acquire fence after the poll).
 // Two block barriers per call: the staging arrays alternate with the parity of the tag (`red`: [2][32], `bc`: [2]).
@@ -95,7 +57,7 @@ __device__ __forceinline__ double ll_grid_sum(uint64_t *slots, int slot_u64, int
       llg_store(slots + (size_t)slot_u64 * blockIdx.x, r, tag);
     }
     double s;
-    const bool ok = llg_collect(slots, slot_u64, nb, tag, s);
+    const bool ok = ll_collect_slots<WIN2_MAX_BLOCKS / 32, false>(slots, (size_t)slot_u64, nb, tag, 4000000000LL, s);
     if (lane == 0) {
       if (FENCE) asm volatile("fence.acq_rel.gpu;" ::: "memory");
       bc[par] = s;
