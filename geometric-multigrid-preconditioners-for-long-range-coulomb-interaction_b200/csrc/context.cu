@@ -880,6 +880,122 @@ static std::vector<int> greedy_coloring(const HostCsr &a, int &n_colors) {
   return color;
 }
 
+// entries of a patch-level matrix back on the host (greedy colouring, wavefronts, Chebyshev bound, host-side merge)
+static int ensure_host_entries(gmg_context *h, Level &L) {
+  const int64_t nnz = L.hA.nnz();
+  if ((int64_t)L.hA.col.size() == nnz) return GMG_OK;
+  if (!L.rawA.rowptr || L.rawA.nnz != nnz) return fail(h, GMG_EINVAL, "level matrix entries are neither on the host nor on the device");
+  L.hA.col.resize(nnz);
+  L.hA.val.resize(nnz);
+  if (nnz > 0) {
+    GMG_CUDA(h, copy(h, L.hA.col.data(), L.rawA.col, sizeof(int) * nnz, cudaMemcpyDeviceToHost));
+    GMG_CUDA(h, copy_sync(h, L.hA.val.data(), L.rawA.val, sizeof(double) * nnz, cudaMemcpyDeviceToHost));
+  }
+  return GMG_OK;
+}
+
+// flag[0] != 0: two rows coupled by a non-zero entry share a colour
+__global__ void color_check(int n, const int64_t *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
+                            const int *__restrict__ color, int *flag) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int c = color[r];
+  bool bad = false;
+  for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+    const int j = col[k];
+    if (j != r && val[k] != 0.0 && color[j] == c) bad = true;
+  }
+  if (bad) *flag = 1;
+}
+
+// the colouring handed over by the host, checked against the matrix on the device
+// (*dcolor_out: the colours on the device, to be released by the caller)
+static int device_coloring_is_valid(gmg_context *h, const DevCsr &a, const std::vector<int32_t> &color, int &n_colors, bool &valid,
+                                    int **dcolor_out) {
+  valid = false;
+  n_colors = 0;
+  *dcolor_out = nullptr;
+  for (int32_t c : color) {
+    if (c < 0 || c > 255) return GMG_OK;
+    n_colors = std::max(n_colors, c + 1);
+  }
+  int *dc = nullptr, *flag = nullptr;
+  GMG_CUDA(h, dalloc(&dc, a.n_rows));
+  GMG_CUDA(h, dalloc(&flag, 1));
+  GMG_CUDA(h, cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+  GMG_CUDA(h, copy(h, dc, color.data(), sizeof(int) * a.n_rows, cudaMemcpyHostToDevice));
+  if (a.n_rows > 0) {
+    color_check<<<cdiv(a.n_rows, 256), 256, 0, h->stream>>>(a.n_rows, a.rowptr, a.col, a.val, dc, flag);
+    GMG_LAUNCH_CHECK(h);
+  }
+  int bad = 0;
+  GMG_CUDA(h, copy_sync(h, &bad, flag, sizeof(int), cudaMemcpyDeviceToHost));
+  dfree(flag);
+  valid = bad == 0;
+  if (valid) *dcolor_out = dc;
+  else dfree(dc);
+  return GMG_OK;
+}
+
+__global__ void color_histogram(int n, const int *__restrict__ color, int *__restrict__ count /*[256]*/) {
+  __shared__ int loc[256];
+  loc[threadIdx.x] = 0;
+  __syncthreads();
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) atomicAdd(&loc[color[r] & 255], 1);
+  __syncthreads();
+  if (loc[threadIdx.x]) atomicAdd(&count[threadIdx.x], loc[threadIdx.x]);
+}
+__global__ void iota_kernel(int n, int *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+
+// The colour sets of a level cut out of its CSR matrix entirely on the device: rows grouped by colour with a stable
+// radix sort (ascending row order inside a colour, as the host path produces them), slice widths by csr_slice_widths.
+static int build_colorsets_device(gmg_context *h, const DevCsr &a, const int *dcolor, int nc, std::vector<ColorSet> &sets) {
+  const int n = a.n_rows;
+  int *keys_out = nullptr, *rows_in = nullptr, *rows_out = nullptr, *count = nullptr;
+  GMG_CUDA(h, dalloc(&keys_out, n));
+  GMG_CUDA(h, dalloc(&rows_in, n));
+  GMG_CUDA(h, dalloc(&rows_out, n));
+  GMG_CUDA(h, dalloc(&count, 256));
+  GMG_CUDA(h, cudaMemsetAsync(count, 0, 256 * sizeof(int), h->stream));
+  if (n > 0) {
+    iota_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(n, rows_in);
+    color_histogram<<<std::min(cdiv(n, 256), 1024), 256, 0, h->stream>>>(n, dcolor, count);
+    GMG_LAUNCH_CHECK(h);
+    size_t tmp_bytes = 0;
+    void *tmp = nullptr;
+    GMG_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dcolor, keys_out, rows_in, rows_out, n, 0, 8, h->stream));
+    GMG_CUDA(h, cudaMallocAsync(&tmp, std::max<size_t>(tmp_bytes, 1), h->stream));
+    GMG_CUDA(h, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dcolor, keys_out, rows_in, rows_out, n, 0, 8, h->stream));
+    cudaFreeAsync(tmp, h->stream);
+  }
+  int hc[256];
+  GMG_CUDA(h, copy_sync(h, hc, count, sizeof(hc), cudaMemcpyDeviceToHost));
+  sets.resize(nc);
+  int off = 0;
+  int rc = GMG_OK;
+  for (int c = 0; c < nc && rc == GMG_OK; ++c) {
+    ColorSet &cs = sets[c];
+    cs.n = hc[c];
+    cs.h_rows.clear();
+    if (cudaError_t e = dalloc(&cs.rows, cs.n); e != cudaSuccess) { rc = fail(h, GMG_ECUDA, cudaGetErrorString(e)); break; }
+    if (cs.n > 0)
+      if (cudaError_t e = copy(h, cs.rows, rows_out + off, sizeof(int) * cs.n, cudaMemcpyDeviceToDevice); e != cudaSuccess) {
+        rc = fail(h, GMG_ECUDA, cudaGetErrorString(e));
+        break;
+      }
+    off += cs.n;
+    rc = build_sell(h, a, -1.0, cs.A, cs.rows, cs.n);
+  }
+  dfree(keys_out);
+  dfree(rows_in);
+  dfree(rows_out);
+  dfree(count);
+  return rc;
+}
+
 static bool coloring_is_valid(const HostCsr &a, const std::vector<int32_t> &color, int &n_colors) {
   // (a few million entries on the larger patch levels: checked by a handful of host threads)
   const int nt = std::max(1, std::min(8, a.n_rows / 4096));
@@ -1674,7 +1790,14 @@ int gmg_set_matrix(gmg_handle h, int which, int level, int32_t n_rows, int32_t n
       h->dist.hA0 = make_host(n_rows, n_cols, rowptr, col, val);
       return GMG_OK;
     }
-    if (level >= 1) L.hA = make_host(n_rows, n_cols, rowptr, col, val);
+    if (level >= 1) {
+      // the host keeps the row pointer (slice widths of the colour sets); the entries stay on the device and are fetched
+      // back only by the set-up paths that walk them on the host (ensure_host_entries)
+      L.hA = HostCsr{};
+      L.hA.n_rows = n_rows;
+      L.hA.n_cols = n_cols;
+      L.hA.rowptr.assign(rowptr, rowptr + n_rows + 1);
+    }
     return upload_csr(h, n_rows, n_cols, rowptr, col, val, L.rawA, level == 0 ? &h->upload[1] : nullptr);
   }
   if (which == GMG_EDGE) {
@@ -1867,6 +1990,7 @@ int gmg_setup(gmg_handle h) {
         if (h->drop_tol < 0.0)
           if ((rc = build_sum_on_device(h, L.A, L.hI, L.AI, on_device))) return rc;
         if (!on_device) {  // an interface entry outside A's stored pattern (or entries were dropped): host merge
+          if ((rc = ensure_host_entries(h, L))) return rc;
           HostCsr ai = add(L.hA, L.hI);
           if ((rc = build_sell_host(h, ai, h->drop_tol, L.AI))) return rc;
         }
@@ -1874,8 +1998,14 @@ int gmg_setup(gmg_handle h) {
       TraceScope tr_s("    I^T, colours / wavefronts");
       free_sell(L.IT);
       if (!L.hI.empty() && L.hI.nnz() > 0) {
-        HostCsr it = transpose(L.hI);
-        if ((rc = build_sell_host(h, it, 0.0, L.IT))) return rc;
+        TraceScope tr_it("      I^T (device transpose)");
+        DevCsr dI, dIT;
+        if ((rc = upload_host_csr(h, L.hI, dI))) return rc;
+        rc = transpose_on_device(h, dI, dIT);
+        if (rc == GMG_OK) rc = build_sell(h, dIT, 0.0, L.IT);
+        free_csr(dI);
+        free_csr(dIT);
+        if (rc) return rc;
       }
       for (auto *set : {&L.colors, &L.wave_fwd, &L.wave_bwd}) {
         for (auto &c : *set) {
@@ -1887,18 +2017,37 @@ int gmg_setup(gmg_handle h) {
       if (h->smoother == GMG_SMOOTHER_MC_SSOR) {
         int nc = 0;
         std::vector<int> color;
-        if ((int)L.user_color.size() == L.n && coloring_is_valid(L.hA, L.user_color, nc))
-          color.assign(L.user_color.begin(), L.user_color.end());
-        else
-          color = greedy_coloring(L.hA, nc);
-        std::vector<std::vector<int>> rows(nc);
-        for (int r = 0; r < L.n; ++r) rows[color[r]].push_back(r);
-        L.colors.resize(nc);
-        if (!L.rawA.rowptr)
-          if ((rc = upload_host_csr(h, L.hA, L.rawA))) return rc;
-        for (int c = 0; c < nc; ++c)
-          if ((rc = build_colorset(h, L.rawA, L.hA, rows[c], L.colors[c]))) return rc;
+        TraceScope tr_c("      colour sets");
+        bool valid = false;
+        int *dcolor = nullptr;
+        if ((int)L.user_color.size() == L.n) {
+          if (L.rawA.rowptr) {
+            if ((rc = device_coloring_is_valid(h, L.rawA, L.user_color, nc, valid, &dcolor))) return rc;
+          } else {
+            valid = coloring_is_valid(L.hA, L.user_color, nc);
+          }
+        }
+        if (valid && dcolor) {  // the colouring the host handed over holds: everything else happens on the device
+          rc = build_colorsets_device(h, L.rawA, dcolor, nc, L.colors);
+          dfree(dcolor);
+          if (rc) return rc;
+        } else {
+          if (valid) {
+            color.assign(L.user_color.begin(), L.user_color.end());
+          } else {
+            if ((rc = ensure_host_entries(h, L))) return rc;
+            color = greedy_coloring(L.hA, nc);
+          }
+          std::vector<std::vector<int>> rows(nc);
+          for (int r = 0; r < L.n; ++r) rows[color[r]].push_back(r);
+          L.colors.resize(nc);
+          if (!L.rawA.rowptr)
+            if ((rc = upload_host_csr(h, L.hA, L.rawA))) return rc;
+          for (int c = 0; c < nc; ++c)
+            if ((rc = build_colorset(h, L.rawA, L.hA, rows[c], L.colors[c]))) return rc;
+        }
       } else if (h->smoother == GMG_SMOOTHER_LEX_SSOR) {
+        if ((rc = ensure_host_entries(h, L))) return rc;
         auto f = wavefronts(L.hA, true), b = wavefronts(L.hA, false);
         L.wave_fwd.resize(f.size());
         L.wave_bwd.resize(b.size());
@@ -1910,6 +2059,7 @@ int gmg_setup(gmg_handle h) {
           if ((rc = build_colorset(h, L.rawA, L.hA, b[c], L.wave_bwd[c]))) return rc;
       } else if (h->smoother == GMG_SMOOTHER_CHEBYSHEV) {
         // power iteration for lambda_max(D^-1 A) on the host copy (small levels), 20 steps
+        if ((rc = ensure_host_entries(h, L))) return rc;
         const HostCsr &a = L.hA;
         std::vector<double> v(L.n), w(L.n), dg(L.n, 1.0);
         for (int r = 0; r < L.n; ++r)
@@ -1934,7 +2084,9 @@ int gmg_setup(gmg_handle h) {
         L.lambda_max = lam;
       }
     }
-    free_csr(L.rawA);
+    // (a patch level whose entries the host does not hold keeps its CSR on the device: a later gmg_setup, after
+    // gmg_set_smoother, cuts its colour / wavefront sets out of it again)
+    if (l == 0 || (int64_t)L.hA.col.size() == L.hA.nnz()) free_csr(L.rawA);
     dfree(L.d_fwd);
     dfree(L.d_bwd);
     L.n_fwd = L.n_bwd = L.ssor_grid = L.cluster_blocks = 0;

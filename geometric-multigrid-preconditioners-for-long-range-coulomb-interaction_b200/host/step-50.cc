@@ -80,6 +80,8 @@ void ParameterReader::declare_parameters() {
   prm.declare_entry("Smoother relaxation", "0.5", Patterns::Double(), "Damping factor of the smoother");
   prm.declare_entry("Smoothing steps", "2", Patterns::Integer(), "Pre- and post-smoothing steps on every level");
   prm.declare_entry("GPU device", "0", Patterns::Integer(), "CUDA device ordinal");
+  prm.declare_entry("Keep densities on the host", "false", Patterns::Bool(),
+                    "compute_charge_densities also copies the densities back to the host (they are consumed on the device)");
   prm.declare_entry("Matrix assembly", "Host", Patterns::Selection("Host | Device"),
                     "Device: system and level-0 matrices are assembled on the GPU from the cell-dof maps "
                     "(bit-identical to the host assembly) instead of being handed over assembled");
@@ -156,6 +158,7 @@ LaplaceProblem<dim>::LaplaceProblem(
     smoother_omega = prm.get_double("Smoother relaxation");
     smoothing_steps = (int)prm.get_integer("Smoothing steps");
     gpu_device = (int)prm.get_integer("GPU device");
+    densities_on_host = prm.get_bool("Keep densities on the host");
     device_assembly = prm.get("Matrix assembly") == "Device";
     prm.leave_subsection();
     prm.enter_subsection("Geometry");
@@ -322,9 +325,17 @@ void LaplaceProblem<dim>::compute_charge_densities() {
     std::fprintf(stderr, "[step50 trace]   flatten %.3f ms\n",
                  1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   const int nc = (int)a.h.size();
-  density_values.resize((size_t)nc * nq * nq * nq);  // (every entry is written by the device call)
-  gmg_check(gmg_charge_density(gmg, nc, a.lo.data(), a.h.data(), a.list.data(), nq * nq * nq, qpts.data(), r_c,
-                               density_values.data()),
+  // density_values_for_each_cell of the reference feeds its host-side assembly (src/step-50.cc:813-816); here both
+  // consumers (load vector, residual term of the indicator) read the device-resident copy: nothing comes back
+  // (118 MB per call at 64k atoms) unless `Keep densities on the host` asks for it
+  double *rho_out = nullptr;
+  if (densities_on_host) {
+    density_values.resize((size_t)nc * nq * nq * nq);  // (every entry is written by the device call)
+    rho_out = density_values.data();
+  } else {
+    density_values.clear();
+  }
+  gmg_check(gmg_charge_density(gmg, nc, a.lo.data(), a.h.data(), a.list.data(), nq * nq * nq, qpts.data(), r_c, rho_out),
             "gmg_charge_density");
   if (rec) rec->rhs_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
@@ -373,6 +384,8 @@ void LaplaceProblem<dim>::setup_system(const unsigned int &cycle) {
   asm_flags_system.clear();
   asm_flags_level0.clear();
   rhs_constrained.clear();
+  hanging_list.clear();
+  hanging_list_n = -1;
   active_cells_cache.reset(new ActiveCells(flatten(*triangulation, *mg_dof_handler, flag_rhs_assembly, base_level())));
   solution.assign(mg_dof_handler->n, 0.0);
   system_rhs.assign(mg_dof_handler->n, 0.0);
@@ -601,7 +614,10 @@ void LaplaceProblem<dim>::solve() {
   if (trace)
     std::fprintf(stderr, "[step50 trace] through pcg %.3f ms\n",
                  1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
-  gmg_check(gmg_vector_norms(gmg, (int64_t)solution.size(), solution.data(), sn), "gmg_vector_norms");
+ gmg_check(gmg_vector_norms(gmg, (int64_t)solution.size(), solution.data(), sn), "gmg_vector_norms");
+  if (trace)
+    std::fprintf(stderr, "[step50 trace] through solution norms %.3f ms\n",
+                 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   out << "   Starting value " << std::fixed << res0 << std::endl;
   out << "   CG converged in " << its << " iterations." << std::endl;
   out << "   Convergence value " << std::scientific << res << std::endl;
@@ -619,8 +635,34 @@ void LaplaceProblem<dim>::solve() {
     rec->coarse_its.assign(buf, buf + std::min(n, 4096));
     rec->solve_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   }
-  distributed_solution = solution;
-  distribute(*mg_dof_handler, boundary_g, distributed_solution);  // constraints.distribute(solution)
+  if (trace)
+    std::fprintf(stderr, "[step50 trace] through records %.3f ms\n",
+                 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  {
+    // constraints.distribute(solution) = ministep::distribute on a copy, fused: one parallel pass writes the copy with
+    // the Dirichlet values in place, the hanging dofs follow in ascending order (sequential: same sums, same bits)
+    const DoFs &d = *mg_dof_handler;
+    if (hanging_list_n != d.n) {  // (setup_system resets it for every new mesh)
+      hanging_list.clear();
+      for (int i = 0; i < d.n; ++i)
+        if (d.hanging[i]) hanging_list.push_back(i);
+      hanging_list_n = d.n;
+    }
+    distributed_solution.resize(solution.size());
+    const double *src = solution.data(), *gv = boundary_g.data();
+    double *dst = distributed_solution.data();
+    const char *dir = d.dirichlet.data();
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < d.n; ++i) dst[i] = dir[i] ? gv[i] : src[i];
+    for (int i : hanging_list) {
+      double sum = 0.0;
+      for (int64_t e = d.hang.rowptr[i]; e < d.hang.rowptr[i + 1]; ++e) sum += d.hang.val[e] * dst[d.hang.col[e]];
+      dst[i] = sum;
+    }
+  }
+  if (trace)
+    std::fprintf(stderr, "[step50 trace] through distribute %.3f ms\n",
+                 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
 }
 
 // src/step-50.cc:1020-1090
@@ -639,7 +681,7 @@ void LaplaceProblem<dim>::estimate_error_and_mark_cells() {
     gauss_unit(2, gp2, gw2);
     std::vector<float> eta((size_t)nc);
     float eta_max = 0.0f;
-    const bool with_rho = indicator_with_residual && !density_values.empty();
+    const bool with_rho = indicator_with_residual && (lammpsinput || !density_values.empty());
     // GaussianCharges with atoms: the densities of compute_charge_densities are still on the device
     const double *rho = (with_rho && !lammpsinput) ? density_values.data() : nullptr;
     (void)nq;

@@ -150,6 +150,7 @@ class LaplaceProblem {
   double smoother_omega = 0.5;
   int smoothing_steps = 2;
   int gpu_device = 0;
+  bool densities_on_host = false;  // compute_charge_densities also downloads the densities (no consumer on the host)
   unsigned int energy_atom_limit = 300;
   unsigned int energy_norm_atom_limit = 0;  // 0: always (reference source)
   bool indicator_with_residual = true;  // false: Kelly part only (the build behind the cluster logs)
@@ -162,6 +163,8 @@ class LaplaceProblem {
   std::vector<double> rhs_ghat;          // inhomogeneities resolved through the hanging-node lines, per mesh
   std::vector<uint8_t> rhs_constrained;  // constraints.is_constrained(i) as bytes, per mesh
   bool rhs_inhom = false;
+  std::vector<int> hanging_list;  // hanging dofs, ascending (constraints.distribute), per mesh
+  int hanging_list_n = -1;
   std::vector<uint8_t> asm_flags_system, asm_flags_level0;  // row flags of gmg_assemble_matrix, built once per mesh
   bool assemble_on_device() const { return device_assembly && Problemtype != "Step16" && PreconditionerType == "GMG"; }
 
