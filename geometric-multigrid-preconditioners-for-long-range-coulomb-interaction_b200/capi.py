@@ -68,6 +68,8 @@ SIGNATURES = {
     "gmg_energy_norm_error": (_i, [_h, _pd, C.c_int32, _d, _pd, _pd, _pd]),
     "gmg_error_indicator": (_i, [_h, _i, _pi32, _pu8, _i, _pi32, _pd, _i, _pd, _i, _pd, _pd, C.POINTER(C.c_float),
                                  C.POINTER(C.c_float)]),
+    "gmg_mark_cells": (_i, [_h, _i, _d, _pu8, _pd]),
+    "gmg_transfer_solution": (_i, [_h, _i, _pd, _i, _i, _pi32, _pi32, _i, _pi64, _pi32, _pu8, _pd]),
     "gmg_debug_cg_phases": (_i, [_h, _i, _pd]),
     "gmg_debug_cg_blocks": (_i, [_h, _pd]),
     "gmg_coarse_kernel": (_i, [_h, _i, _i, C.POINTER(_i)]),
@@ -346,6 +348,26 @@ class Gmg:
             hang_children.ctypes.data_as(_pi32), _pd_of(u), len(u), _pd_of(rho_a) if rho_a is not None else None,
             int(residual_term), _pd_of(gp), _pd_of(gw), eta.ctypes.data_as(C.POINTER(C.c_float)), C.byref(mx)))
         return eta, mx.value
+
+    def mark_cells(self, n_cells, fraction=0.6):
+        """Refinement flags (uint8 per active cell of the last error_indicator call) and the threshold fraction * max."""
+        flags = np.zeros(n_cells, dtype=np.uint8)
+        thr = np.zeros(1)
+        self._ck(self.lib.gmg_mark_cells(self.h, int(n_cells), float(fraction), flags.ctypes.data_as(_pu8), _pd_of(thr)))
+        return flags, float(thr[0])
+
+    def transfer_solution(self, u_old, n_new, copy_old, copy_new, pass_ptr, parent_dofs, constrained):
+        """SolutionTransfer::interpolate + set_zero on the device (index tables from the host mesh)."""
+        u_old, copy_old, copy_new = _f64(u_old), _i32(copy_old), _i32(copy_new)
+        pass_ptr = np.ascontiguousarray(pass_ptr, dtype=np.int64)
+        pd = _i32(np.asarray(parent_dofs).ravel())
+        con = np.ascontiguousarray(constrained, dtype=np.uint8)
+        out = np.zeros(n_new)
+        self._ck(self.lib.gmg_transfer_solution(
+            self.h, len(u_old), _pd_of(u_old), int(n_new), len(copy_old), copy_old.ctypes.data_as(_pi32),
+            copy_new.ctypes.data_as(_pi32), len(pass_ptr) - 1, pass_ptr.ctypes.data_as(_pi64), pd.ctypes.data_as(_pi32),
+            con.ctypes.data_as(_pu8), _pd_of(out)))
+        return out
 
     def pair_energies(self, r_c):
         out = np.zeros(2)

@@ -1711,6 +1711,7 @@ int gmg_destroy(gmg_handle h) {
   dfree(h->scalars);
   dfree(h->cg_partials);
   dfree(h->cg_ll);
+  dfree(h->ind_eta);
   dfree(h->cg_results);
   dfree(h->atom_pos);
   dfree(h->atom_q);

@@ -116,9 +116,152 @@ __global__ void __launch_bounds__(256) float_max_kernel(int n, const float *__re
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(m));
 }
 
+// src/step-50.cc:1084-1090: a cell is flagged when its (float) indicator, widened to double, reaches the threshold
+__global__ void __launch_bounds__(256) mark_kernel(int n, const float *__restrict__ eta, double threshold, bool any, unsigned char *flags) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) flags[c] = (any && (double)eta[c] >= threshold) ? 1 : 0;
+}
+
+// ---- solution transfer (src/step-50.cc:1110-1119)
+__global__ void __launch_bounds__(256) xfer_init(int n, int *stamp, int *owner) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    stamp[i] = 0x7fffffff;  // unknown: later than any pass
+    owner[i] = 0x7fffffff;
+  }
+}
+__global__ void __launch_bounds__(256) xfer_copy(int n, const int *__restrict__ src, const int *__restrict__ dst,
+                                                 const double *__restrict__ u_old, double *x, int *stamp) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) {
+    x[dst[k]] = u_old[src[k]];
+    stamp[dst[k]] = -1;
+  }
+}
+// pass l, step 1: a refined cell whose corners are known claims its unknown points (lowest cell index wins)
+__global__ void __launch_bounds__(256) xfer_claim(int64_t p0, int64_t p1, const int *__restrict__ pd, int pass,
+                                                  const int *__restrict__ stamp, int *owner) {
+  const int64_t p = p0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= p1) return;
+  const int *q = pd + 27 * p;
+  for (int v = 0; v < 8; ++v) {
+    const int c = q[2 * (v & 1) + 6 * ((v >> 1) & 1) + 18 * ((v >> 2) & 1)];
+    if (c < 0 || stamp[c] >= pass) return;
+  }
+  for (int t = 0; t < 27; ++t) {
+    const int t0 = t % 3, t1 = (t / 3) % 3, t2 = t / 9;
+    if (t0 != 1 && t1 != 1 && t2 != 1) continue;
+    const int dof = q[t];
+    if (dof >= 0 && stamp[dof] >= pass) atomicMin(owner + dof, (int)(p - p0));
+  }
+}
+// step 2: the owner interpolates: val = sum_v w_v U_v over the corners with w_v != 0, in vertex order, unfused
+__global__ void __launch_bounds__(256) xfer_fill(int64_t p0, int64_t p1, const int *__restrict__ pd, int pass,
+                                                 const int *__restrict__ owner, double *x, int *stamp) {
+  const int64_t p = p0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= p1) return;
+  const int *q = pd + 27 * p;
+  double U[8];
+  for (int v = 0; v < 8; ++v) {
+    const int c = q[2 * (v & 1) + 6 * ((v >> 1) & 1) + 18 * ((v >> 2) & 1)];
+    if (c < 0 || stamp[c] >= pass) return;
+    U[v] = x[c];
+  }
+  for (int t = 0; t < 27; ++t) {
+    const int tt[3] = {t % 3, (t / 3) % 3, t / 9};
+    if (tt[0] != 1 && tt[1] != 1 && tt[2] != 1) continue;
+    const int dof = q[t];
+    if (dof < 0 || owner[dof] != (int)(p - p0) || stamp[dof] < pass) continue;
+    double val = 0.0;
+    for (int v = 0; v < 8; ++v) {
+      double w = 1.0;
+      for (int k = 0; k < 3; ++k) w = __dmul_rn(w, ((v >> k) & 1) ? tt[k] / 2.0 : 1.0 - tt[k] / 2.0);
+      if (w != 0.0) val = __dadd_rn(val, __dmul_rn(w, U[v]));
+    }
+    x[dof] = val;
+  }
+}
+// step 3 (after every owner has read the corner stamps): the claimed points are known from the next pass on
+__global__ void __launch_bounds__(256) xfer_stamp(int n, int pass, int *owner, int *stamp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && owner[i] != 0x7fffffff) {
+    stamp[i] = pass;
+    owner[i] = 0x7fffffff;
+  }
+}
+__global__ void __launch_bounds__(256) xfer_finish(int n, const unsigned char *__restrict__ constrained, const int *__restrict__ stamp,
+                                                   double *x, int *missing) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (stamp[i] == 0x7fffffff) atomicAdd(missing, 1);
+  if (constrained[i]) x[i] = 0.0;
+}
+
 }  // namespace
 
 extern "C" {
+
+int gmg_transfer_solution(gmg_handle h, int32_t n_old, const double *u_old, int32_t n_new, int32_t n_copy, const int32_t *copy_old,
+                          const int32_t *copy_new, int32_t n_pass, const int64_t *pass_ptr, const int32_t *parent_dofs,
+                          const uint8_t *constrained, double *u_new_out) {
+  if (!h || n_old < 0 || n_new < 0 || n_copy < 0 || n_pass < 0 || !u_old || !u_new_out || !constrained || !pass_ptr ||
+      (n_copy > 0 && (!copy_old || !copy_new)) || (pass_ptr[n_pass] > 0 && !parent_dofs))
+    return GMG_EINVAL;
+  gmg::enter(h);
+  const int64_t n_par = pass_ptr[n_pass];
+  double *d_old = nullptr, *d_x = nullptr;
+  int *d_src = nullptr, *d_dst = nullptr, *d_pd = nullptr, *d_stamp = nullptr, *d_owner = nullptr, *d_missing = nullptr;
+  unsigned char *d_con = nullptr;
+  auto cleanup = [&]() {
+    dfree(d_old); dfree(d_x); dfree(d_src); dfree(d_dst); dfree(d_pd); dfree(d_stamp); dfree(d_owner); dfree(d_missing); dfree(d_con);
+  };
+  cudaError_t e = cudaSuccess;
+  if ((e = dalloc(&d_old, n_old)) != cudaSuccess || (e = dalloc(&d_x, n_new)) != cudaSuccess || (e = dalloc(&d_src, n_copy)) != cudaSuccess ||
+      (e = dalloc(&d_dst, n_copy)) != cudaSuccess || (e = dalloc(&d_pd, 27 * n_par)) != cudaSuccess ||
+      (e = dalloc(&d_stamp, n_new)) != cudaSuccess || (e = dalloc(&d_owner, n_new)) != cudaSuccess ||
+      (e = dalloc(&d_missing, 1)) != cudaSuccess || (e = dalloc(&d_con, n_new)) != cudaSuccess) {
+    cleanup();
+    return gmg::fail(h, GMG_ECUDA, std::string("gmg_transfer_solution: ") + cudaGetErrorString(e));
+  }
+  int rc = GMG_OK;
+  if ((rc = staged_h2d(h, d_old, u_old, sizeof(double) * (size_t)n_old)) || (rc = staged_h2d(h, d_src, copy_old, sizeof(int) * (size_t)n_copy)) ||
+      (rc = staged_h2d(h, d_dst, copy_new, sizeof(int) * (size_t)n_copy)) ||
+      (rc = staged_h2d(h, d_pd, parent_dofs, sizeof(int) * 27 * (size_t)n_par)) || (rc = staged_h2d(h, d_con, constrained, (size_t)n_new))) {
+    cleanup();
+    return rc;
+  }
+  cudaMemsetAsync(d_x, 0, sizeof(double) * (size_t)std::max(n_new, 1), h->stream);
+  cudaMemsetAsync(d_missing, 0, sizeof(int), h->stream);
+  if (n_new > 0) {
+    xfer_init<<<cdiv(n_new, 256), 256, 0, h->stream>>>(n_new, d_stamp, d_owner);
+    h->launches++;
+  }
+  if (n_copy > 0) {
+    xfer_copy<<<cdiv(n_copy, 256), 256, 0, h->stream>>>(n_copy, d_src, d_dst, d_old, d_x, d_stamp);
+    h->launches++;
+  }
+  for (int l = 0; l < n_pass; ++l) {
+    const int64_t p0 = pass_ptr[l], p1 = pass_ptr[l + 1];
+    if (p1 <= p0) continue;
+    const int grid = (int)cdiv(p1 - p0, (int64_t)256);
+    xfer_claim<<<grid, 256, 0, h->stream>>>(p0, p1, d_pd, l, d_stamp, d_owner);
+    xfer_fill<<<grid, 256, 0, h->stream>>>(p0, p1, d_pd, l, d_owner, d_x, d_stamp);
+    xfer_stamp<<<cdiv(n_new, 256), 256, 0, h->stream>>>(n_new, l, d_owner, d_stamp);
+    h->launches += 3;
+  }
+  if (n_new > 0) {
+    xfer_finish<<<cdiv(n_new, 256), 256, 0, h->stream>>>(n_new, d_con, d_stamp, d_x, d_missing);
+    h->launches++;
+  }
+  int missing = 0;
+  if ((rc = staged_d2h(h, u_new_out, d_x, sizeof(double) * (size_t)n_new)) == GMG_OK) {
+    e = gmg::copy_sync(h, &missing, d_missing, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = gmg::fail(h, GMG_ECUDA, std::string("gmg_transfer_solution: ") + cudaGetErrorString(e));
+  }
+  cleanup();
+  if (rc == GMG_OK && missing > 0) return gmg::fail(h, GMG_EINVAL, "solution transfer left a dof without a value");
+  return rc;
+}
 
 int gmg_error_indicator(gmg_handle h, int32_t n_cells, const int32_t *face_nb, const uint8_t *face_kind, int32_t n_hang,
                         const int32_t *hang_children, const double *u, int32_t n_dofs, const double *rho, int residual_term,
@@ -191,7 +334,31 @@ int gmg_error_indicator(gmg_handle h, int32_t n_cells, const int32_t *face_nb, c
     if (e != cudaSuccess) rc = gmg::fail(h, GMG_ECUDA, std::string("gmg_error_indicator: ") + cudaGetErrorString(e));
   }
   if (max_out) *max_out = mx;
+  if (rc == GMG_OK) {  // the indicators stay on the device for gmg_mark_cells
+    dfree(h->ind_eta);
+    h->ind_eta = d_eta;
+    h->ind_n = n_cells;
+    h->ind_max = mx;
+    d_eta = nullptr;
+  }
   cleanup();
+  return rc;
+}
+
+int gmg_mark_cells(gmg_handle h, int32_t n_cells, double fraction, uint8_t *flags_out, double *threshold_out) {
+  if (!h || n_cells < 0 || !flags_out) return GMG_EINVAL;
+  gmg::enter(h);
+  if (!h->ind_eta || h->ind_n != n_cells) return gmg::fail(h, GMG_EINVAL, "gmg_mark_cells: call gmg_error_indicator on the same cells first");
+  const double threshold = fraction * (double)h->ind_max;  // (src/step-50.cc:1084: 0.6 * estimated_error_per_cell.linfty_norm())
+  if (threshold_out) *threshold_out = threshold;
+  unsigned char *d_flags = nullptr;
+  if (cudaError_t e = dalloc(&d_flags, n_cells); e != cudaSuccess) return gmg::fail(h, GMG_ECUDA, cudaGetErrorString(e));
+  if (n_cells > 0) {
+    mark_kernel<<<cdiv(n_cells, 256), 256, 0, h->stream>>>(n_cells, h->ind_eta, threshold, h->ind_max > 0.0f, d_flags);
+    h->launches++;
+  }
+  int rc = staged_d2h(h, flags_out, d_flags, (size_t)n_cells);
+  dfree(d_flags);
   return rc;
 }
 

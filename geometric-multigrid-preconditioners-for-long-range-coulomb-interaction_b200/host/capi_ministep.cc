@@ -249,6 +249,23 @@ int ms_transfer(void *p_new, int old_res, void *p_old, const double *u_old, doub
   return 0;
 }
 
+// index tables of the device solution transfer (gmg_transfer_solution); arrays owned by the new bundle until the next call
+int ms_transfer_tables(void *p_new, int old_res, void *p_old, int64_t *n_copy, const int32_t **copy_old, const int32_t **copy_new,
+                       int64_t *n_pass, const int64_t **pass_ptr, const int32_t **parent_dofs) {
+  Bundle *nb = (Bundle *)p_new, *ob = (Bundle *)p_old;
+  try {
+    static thread_local TransferTables T;
+    T = transfer_tables(old_res, *ob->dofs, *nb->forest, *nb->dofs);
+    *n_copy = (int64_t)T.copy_old.size();
+    *copy_old = T.copy_old.data();
+    *copy_new = T.copy_new.data();
+    *n_pass = (int64_t)T.pass_ptr.size() - 1;
+    *pass_ptr = T.pass_ptr.data();
+    *parent_dofs = T.parent_dofs.data();
+  } catch (std::exception &e) { g_err = e.what(); return -1; }
+  return 0;
+}
+
 int ms_distribute(void *p, const double *g, double *x_inout) {
   Bundle *b = (Bundle *)p;
   std::vector<double> gg(g, g + b->dofs->n), x(x_inout, x_inout + b->dofs->n);

@@ -878,6 +878,35 @@ std::vector<double> transfer_solution(int old_res, const DoFs &od, const std::ve
   return x;
 }
 
+TransferTables transfer_tables(int old_res, const DoFs &od, const Forest &f, const DoFs &d) {
+  TransferTables T;
+  const int shift = f.resolution() - old_res;
+  for (int i = 0; i < od.n; ++i) {
+    const Int3 q = {od.xyz[i][0] << shift, od.xyz[i][1] << shift, od.xyz[i][2] << shift};
+    const int j = d.lookup(q);
+    if (j >= 0) {
+      T.copy_old.push_back(i);
+      T.copy_new.push_back(j);
+    }
+  }
+  const int res = f.resolution();
+  T.pass_ptr.push_back(0);
+  for (int l = 0; l + 1 < f.n_levels(); ++l) {
+    const int half = 1 << (res - l - 1);
+    for (int p = 0; p < f.n_cells(l); ++p) {
+      if (f.L[l].child0[p] < 0) continue;
+      const Int3 &ijk = f.L[l].ijk[p];
+      const Int3 base = {ijk[0] << (res - l), ijk[1] << (res - l), ijk[2] << (res - l)};
+      for (int t2 = 0; t2 <= 2; ++t2)
+        for (int t1 = 0; t1 <= 2; ++t1)
+          for (int t0 = 0; t0 <= 2; ++t0)
+            T.parent_dofs.push_back(d.lookup({base[0] + t0 * half, base[1] + t1 * half, base[2] + t2 * half}));
+    }
+    T.pass_ptr.push_back((int64_t)(T.parent_dofs.size() / 27));
+  }
+  return T;
+}
+
 void locate(const Forest &f, const DoFs &, const double X[3], int &level, int &cell, double xi[3]) {
   int ijk[3];
   for (int k = 0; k < 3; ++k) {

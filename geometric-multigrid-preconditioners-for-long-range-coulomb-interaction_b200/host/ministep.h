@@ -142,6 +142,14 @@ double mark_cells(const Forest &f, const DoFs &d, const std::vector<std::vector<
 // SolutionTransfer::interpolate + constraints.set_zero (src/step-50.cc:1118-1119)
 std::vector<double> transfer_solution(int old_res, const DoFs &old_dofs, const std::vector<double> &u_old,
                                       const Forest &f, const DoFs &d);
+// The index side of the same transfer for the device (gmg_transfer_solution): which old dof lands on which new dof, and
+// per level (coarse to fine) the 27 new dofs (t0 + 3 t1 + 9 t2, -1: no such dof) of every refined cell, in cell order.
+struct TransferTables {
+  std::vector<int32_t> copy_old, copy_new;
+  std::vector<int64_t> pass_ptr;      // [levels]: first refined cell of each pass in parent_dofs
+  std::vector<int32_t> parent_dofs;   // [refined cells][27]
+};
+TransferTables transfer_tables(int old_res, const DoFs &old_dofs, const Forest &f, const DoFs &d);
 // find_active_cell_around_point + unit-cell coordinates (src/step-50.cc:1353-1356)
 void locate(const Forest &f, const DoFs &d, const double X[3], int &level, int &cell, double xi[3]);
 

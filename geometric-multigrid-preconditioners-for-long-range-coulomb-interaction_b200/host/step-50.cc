@@ -696,7 +696,24 @@ void LaplaceProblem<dim>::estimate_error_and_mark_cells() {
       off += d.active_cells[l].size();
     }
   }
-  const double threshold = mark_cells(*triangulation, *mg_dof_handler, error_per_cell, refine_flags);
+  // marking on the device too (gmg_mark_cells: float indicator widened to double >= 0.6 * max, src/step-50.cc:1084-1090);
+  // the host only scatters the per-active-cell flags into the forest's per-level flag arrays
+  double threshold = 0.0;
+  {
+    const Forest &f = *triangulation;
+    const DoFs &d = *mg_dof_handler;
+    size_t nc = 0;
+    for (int l = 0; l < f.n_levels(); ++l) nc += d.active_cells[l].size();
+    std::vector<uint8_t> marked(nc);
+    gmg_check(gmg_mark_cells(gmg, (int)nc, 0.6, marked.data(), &threshold), "gmg_mark_cells");
+    refine_flags.assign(f.n_levels(), {});
+    size_t off = 0;
+    for (int l = 0; l < f.n_levels(); ++l) {
+      refine_flags[l].assign(f.n_cells(l), 0);
+      for (size_t p = 0; p < d.active_cells[l].size(); ++p) refine_flags[l][d.active_cells[l][p]] = (char)marked[off + p];
+      off += d.active_cells[l].size();
+    }
+  }
   *pcout << "Threshold value for refinement:\t" << threshold << std::endl;
   if (rec) {
     rec->threshold = threshold;
@@ -714,7 +731,16 @@ void LaplaceProblem<dim>::refine_grid(const unsigned int &cycle) {
   const std::vector<double> previous_solution = distributed_solution;
   triangulation->refine(refine_flags);
   setup_system(cycle);
-  solution = transfer_solution(old_res, *old_dofs, previous_solution, *triangulation, *mg_dof_handler);
+  // SolutionTransfer::interpolate + set_zero on the device (gmg_transfer_solution): the host provides the index tables
+  // (which old dof is which new dof, the 27 dofs of every refined cell), the values never pass through host arithmetic
+  const TransferTables T = transfer_tables(old_res, *old_dofs, *triangulation, *mg_dof_handler);
+  const DoFs &d = *mg_dof_handler;
+  std::vector<uint8_t> constrained(d.constrained.begin(), d.constrained.end());
+  solution.assign(d.n, 0.0);
+  gmg_check(gmg_transfer_solution(gmg, old_dofs->n, previous_solution.data(), d.n, (int)T.copy_old.size(), T.copy_old.data(),
+                                  T.copy_new.data(), (int)T.pass_ptr.size() - 1, T.pass_ptr.data(), T.parent_dofs.data(),
+                                  constrained.data(), solution.data()),
+            "gmg_transfer_solution");
 }
 
 // VTU / PVTU / VisIt output (src/step-50.cc:1149-1308) is visualisation, out of scope of this path

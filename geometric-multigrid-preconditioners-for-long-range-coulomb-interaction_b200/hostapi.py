@@ -28,6 +28,7 @@ def _declare_ms(L):
     L.ms_unit_stiffness.argtypes = [C.c_void_p]
     L.ms_error_indicator.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.ms_transfer.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ms_transfer_tables.argtypes = [C.c_void_p, C.c_int, C.c_void_p] + [C.c_void_p] * 6
     L.ms_distribute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ms_locate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
     L.ms_gauss.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
@@ -157,6 +158,18 @@ class Ministep:
         out = np.zeros(len(self.get("boundary")))
         _ck_ms(self.L.ms_transfer(self.p, old_res, old.p, u_old.ctypes.data, out.ctypes.data))
         return out
+
+    def transfer_tables(self, old, old_res):
+        """Index tables of the device solution transfer: (copy_old, copy_new, pass_ptr, parent_dofs[.., 27])."""
+        nc, npass = C.c_int64(), C.c_int64()
+        co, cn, pd = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+        pp = C.POINTER(C.c_int64)()
+        _ck_ms(self.L.ms_transfer_tables(self.p, int(old_res), old.p, C.byref(nc), C.byref(co), C.byref(cn), C.byref(npass),
+                                         C.byref(pp), C.byref(pd)))
+        take = lambda ptr, n, dt: np.ctypeslib.as_array(ptr, shape=(max(n, 1),)).astype(dt)[:n].copy()
+        pass_ptr = take(pp, npass.value + 1, np.int64)
+        return (take(co, nc.value, np.int32), take(cn, nc.value, np.int32), pass_ptr,
+                take(pd, 27 * int(pass_ptr[-1]), np.int32).reshape(-1, 27))
 
     def distribute(self, g, x):
         g = np.ascontiguousarray(g, dtype=np.float64)

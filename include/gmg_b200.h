@@ -255,6 +255,21 @@ int gmg_error_indicator(gmg_handle h, int32_t n_cells, const int32_t *face_nb /*
                         const uint8_t *face_kind /*[n_cells][6]*/, int32_t n_hang, const int32_t *hang_children /*[n_hang][4]*/,
                         const double *u, int32_t n_dofs, const double *rho, int residual_term,
                         const double gauss2_points[2], const double gauss2_weights[2], float *eta_out, float *max_out);
+/* Marking (src/step-50.cc:1084-1090): flags_out[c] = 1 where the indicator of the last gmg_error_indicator call reaches
+ * fraction * max (the reference: 0.6 * linfty_norm, refine_and_coarsen with a single threshold and no coarsening); the
+ * float32 indicators are widened to double for the comparison, as Vector<float> entries are.  *threshold_out = the
+ * printed "Threshold value for refinement". */
+int gmg_mark_cells(gmg_handle h, int32_t n_cells, double fraction, uint8_t *flags_out, double *threshold_out);
+/* SolutionTransfer::interpolate + constraints.set_zero (src/step-50.cc:1110-1119) after a refinement-only step: the
+ * new vector takes the old values at the dofs both meshes share (copy_old[k] -> copy_new[k]); pass by pass (coarse to
+ * fine) every refined cell whose 8 corners are known gives its 19 edge / face / centre points (parent_dofs: 27 new dofs
+ * per refined cell, index t0 + 3 t1 + 9 t2, -1: none) their trilinear values, the first cell in the hand-over order
+ * winning a shared point, sums over the corners in vertex order with unfused arithmetic -- the bits of the sequential
+ * host loop; constrained dofs end at 0.  GMG_EINVAL when a dof is left without a value. */
+int gmg_transfer_solution(gmg_handle h, int32_t n_old, const double *u_old, int32_t n_new, int32_t n_copy,
+                          const int32_t *copy_old, const int32_t *copy_new, int32_t n_pass, const int64_t *pass_ptr,
+                          const int32_t *parent_dofs /*[pass_ptr[n_pass]][27]*/, const uint8_t *constrained /*[n_new]*/,
+                          double *u_new_out);
 /* The O(N^2) pair sums of postprocess_electrostatic_energy (src/step-50.cc:1316-1332) over the atoms of gmg_set_atoms:
  * out[0] = sum_{i<j} q_i q_j / r_ij, out[1] = sum_{i<j} q_i q_j erfc(r_ij / r_c) / r_ij. */
 int gmg_pair_energies(gmg_handle h, double r_c, double out[2]);

@@ -49,11 +49,46 @@ def test_indicator_bit_identical_to_sequential_restatement(refined, residual):
     gp2, gw2 = hostlib.gauss(2)
     eta, mx = g.error_indicator(M.get("topo_face_nb"), M.get("topo_face_kind"), M.get("topo_hang_children"), u, rho, residual,
                                 gp2, gw2)
+    marked, thr_dev = g.mark_cells(nc)
     g.close()
     thr = M.error_indicator(u, rho, nq, residual)
     ref = np.concatenate([M.get("eta", l) for l in range(M.n_levels)])
+    # marking on the device (gmg_mark_cells) = the host's mark_cells: same threshold bits, same flags
+    ref_flags = np.concatenate([M.get("flags", l)[M.get("active_cells", l)] for l in range(M.n_levels)])
+    assert thr_dev == thr
+    assert np.array_equal(marked.astype(bool), ref_flags.astype(bool)) and marked.any() and not marked.all()
     assert ref.dtype == np.float32 and eta.dtype == np.float32
     assert (M.get("topo_face_kind") & 3 == 2).any() and (M.get("topo_face_kind") & 3 == 1).any()  # hanging faces are covered
     assert np.array_equal(eta.view(np.uint32), ref.view(np.uint32))
     # same indicators, same maximum: the threshold 0.6 * max (src/step-50.cc:1084) marks the same cells
     assert mx == ref.max() and abs(thr - 0.6 * float(mx)) <= 1e-12 * thr
+
+
+def test_solution_transfer_bit_identical_to_sequential_restatement():
+    """gmg_transfer_solution (SolutionTransfer::interpolate + set_zero, src/step-50.cc:1110-1119) against ministep's
+    transfer_solution across every refinement step of the 2-atom golden hierarchy: the same doubles, bit for bit
+    (shared edge / face points take the value of the first refined cell, as in the sequential loop)."""
+    P = oracle_cycle(make_prm(cycles=4, bc="Exact", atom="atom_n1_2.data", nq=4), 3)
+    f = P.forest
+    capi = pkg().capi
+    g = capi.Gmg()
+    old = hostlib.Ministep(f.reps, f.lo, f.hi)
+    old.build(matrices=False)
+    rng = np.random.default_rng(5)
+    history = []
+    for step, flags in enumerate(P.flag_history[:3]):
+        new = hostlib.Ministep(f.reps, f.lo, f.hi)
+        for fl in history + [flags]:
+            new.refine(fl)
+        new.build(matrices=False)
+        history.append(flags)
+        u_old = rng.standard_normal(len(old.get("boundary")))
+        old_res = old.n_levels - 1
+        ref = new.transfer_from(old, old_res, u_old)
+        co, cn, pp, pd = new.transfer_tables(old, old_res)
+        assert len(pd) > 0
+        x = g.transfer_solution(u_old, len(ref), co, cn, pp, pd, new.get("constrained"))
+        assert np.array_equal(x.view(np.uint64), ref.view(np.uint64)), step
+        assert np.abs(x).max() > 0
+        old = new
+    g.close()
