@@ -329,7 +329,8 @@ def run_b200(args):
     kid = g.coarse_kernel(capi.GMG_LEVEL, 0)
     kernel = KERNEL_NAMES[kid]
     if world > 1:
-        kernel = "gmg::cg_persistent_dist<512> (distributed coarse-level CG, halo + all-reduce over peer memory inside the kernel)"
+        kernel = ("gmg::cg_persistent_dist<1024> (distributed coarse-level CG: halo rows and all-to-all tagged-word reductions over "
+                  "NVLink peer memory inside the kernel, no grid.sync)")
     vec_mb = 4 * 8 * n_rows0 / 1e6
     l2_resident = fmt == 2 and vec_mb / world < 100
     tr = profile_traffic(kid if world == 1 else "dist", world, n_rows0)
@@ -374,7 +375,7 @@ def run_b200(args):
                 "ms_per_step_hierarchy_already_on_device": ms_e2 / e2e_steps,
                 "includes_hierarchy_hand_over": bool(full_e2e),
                 "what": ("compute_charge_densities + rhs assembly + solve() with host buffers: atoms/cells/CSR matrices/vectors H2D, "
-                         "densities/rhs/solution D2H") if full_e2e else
+                         "rhs/solution D2H") if full_e2e else
                         "compute_charge_densities + rhs assembly + gmg_pcg_solve with host buffers; EXCLUDES the hierarchy "
                         "hand-over (partitioned once at set-up), so compare with N=1's ms_per_step_hierarchy_already_on_device, "
                         "not with N=1's e2e value"},
@@ -387,7 +388,7 @@ def run_b200(args):
             "h2d_bytes_per_step": e2e_dev["h2d"] // e2e_steps, "d2h_bytes_per_step": e2e_dev["d2h"] // e2e_steps,
             "what": "compute_charge_densities + rhs assembly + solve() with host buffers and `Matrix assembly = Device`: "
                     "atoms/cells/cell-dof maps/constraints/patch-level CSR/vectors H2D, system + level-0 matrices assembled on "
-                    "the device (bit-identical CSR), densities/rhs/solution D2H",
+                    "the device (bit-identical CSR), rhs/solution D2H (the densities stay on the device: their consumers run there)",
             "host_assembled_matrices": {k: host_leg[k] for k in ("value", "ms_per_step", "h2d_bytes_per_step",
                                                                  "d2h_bytes_per_step")}})
     # ---- V-cycle time: first (largest) and mean over the solve, from the coarse profile + one direct measurement
@@ -488,6 +489,63 @@ def run_b200(args):
         finally:
             g.set_smoother(capi.SMOOTHER_MC_SSOR, 0.5, 2)
             g.setup()
+        # ---- point Jacobi(0.5) x 2 (north_star smoother (2); the reference's test configuration): no colour launches at all
+        try:
+            g.set_smoother(capi.SMOOTHER_JACOBI, 0.5, 2)
+            g.setup()
+            for _ in range(2):
+                B.step_device()
+            k_j = max(2, min(args.steps, 5))
+            ms_j, outs_j, launches_j, _ = timed(B.step_device, k_j)
+            x_j = B.download_x()
+            line.setdefault("smoothers", {})["Jacobi"] = {
+                "ms_per_step": ms_j / k_j, "value": B.n_dofs * k_j / (ms_j * 1e-3), "steps": k_j,
+                "outer_iterations": outs_j[-1][0], "gpu_launches_per_step": int(launches_j // k_j),
+                "rel_l2_solution_vs_multicolour": float(np.linalg.norm(x_j - x_gpu) / np.linalg.norm(x_gpu)),
+                "role": "damped point Jacobi(0.5) x 2 on every level (Ifpack's, as in the reference's Jacobi goldens)"}
+        except Exception as exc:
+            print(f"bench.py: Jacobi leg failed: {exc}", file=sys.stderr)
+        finally:
+            g.set_smoother(capi.SMOOTHER_MC_SSOR, 0.5, 2)
+            g.setup()
+        # ---- SURVEY 8f N4 (never the headline: a different hierarchy than the reference's): coarse levels below the base
+        # mesh, so the coarse CG runs on (reps / 2^k + 1)^3 dofs; same meshes above the base lattice, same RHS, same solution
+        if world == 1 and not args.coarse_levels:
+            line["coarse_levels_below_base_mesh"] = {}
+            for sm_name, k_lv in (("Jacobi", 3), ("MulticolourSSOR", 3)):
+                B4 = None
+                try:
+                    prm4 = P.lattice.cluster_prm(atom_file, args.atoms_n, cycles=args.cycles, smoother=sm_name, device=local,
+                                                 coarse_levels=k_lv)
+                    B4 = P.hostapi.BenchProblem(prm4)
+                    B4.gmg.set_stream(stream.cuda_stream)
+                    for _ in range(3):
+                        B4.step_device()
+                    k4 = max(2, min(args.steps, 5))
+                    barrier()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    with torch.cuda.stream(stream):
+                        e0.record(stream)
+                        outs4 = [B4.step_device() for _ in range(k4)]
+                        e1.record(stream)
+                    barrier()
+                    ms4 = e0.elapsed_time(e1)
+                    x4 = B4.download_x()
+                    line["coarse_levels_below_base_mesh"]["%s_k%d" % (sm_name, k_lv)] = {
+                        "smoother": sm_name, "coarse_levels": k_lv, "ms_per_step": ms4 / k4,
+                        "value": B4.n_dofs * k4 / (ms4 * 1e-3), "n_dofs_level": B4.level_n,
+                        "outer_iterations": outs4[-1][0], "coarse_iterations": B4.gmg.last_coarse_iterations(),
+                        "same_system_dofs": B4.n_dofs == B.n_dofs,
+                        # (the deeper hierarchy numbers the dofs differently: the norms are what can be compared)
+                        "rel_err_solution_norms_vs_headline": {
+                            "l1": abs(float(np.abs(x4).sum()) - parity["sol_l1"]) / parity["sol_l1"],
+                            "l2": abs(float(np.linalg.norm(x4)) - parity["sol_l2"]) / parity["sol_l2"],
+                            "linf": abs(float(np.abs(x4).max()) - parity["sol_linf"]) / parity["sol_linf"]}}
+                except Exception as exc:
+                    print(f"bench.py: coarse-levels leg ({sm_name}, k = {k_lv}) failed: {exc}", file=sys.stderr)
+                finally:
+                    if B4 is not None:
+                        B4.close()
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], cmpv = cpu_baseline_from(B, pos, q, args, b_gpu, x_gpu)

@@ -1394,7 +1394,8 @@ static int vcycle_down(gmg_context *h, const double *src) {
     Level &C = h->levels[l - 1];
     if (int rc = smooth(h, L, L.sol, L.defect, true)) return rc;
     // t = defect - (A + I) sol
-    if (int rc = spmv<EPI_RESID, DOT_NONE>(h, L.AI, L.sol, L.t, L.defect)) return rc;
+    // (a level without refinement edges has an empty interface matrix: A + I is A, in whichever format A has)
+    if (int rc = spmv<EPI_RESID, DOT_NONE>(h, L.edge_free ? L.A : L.AI, L.sol, L.t, L.defect)) return rc;
     // defect[l-1] += P^T t
     if (int rc = spmv<EPI_ADD, DOT_NONE>(h, C.R, L.t, C.defect)) return rc;
   }
@@ -1972,7 +1973,9 @@ int gmg_setup(gmg_handle h) {
       }
     }
     if (!L.A.valid) return fail(h, GMG_EINVAL, "level matrix missing on level " + std::to_string(l));
-    if (l == 0 && h->compress >= 2 && !L.A.patterned)
+    // row-pattern format: level 0 (coarse CG) and every other large level (with coarse levels below the base mesh the
+    // base lattice is an ordinary smoothed level: its Jacobi / Chebyshev sweeps and residuals then run on pat_spmv)
+    if ((l == 0 || L.n >= 500000) && h->compress >= 2 && !L.A.patterned)
       if ((rc = build_pat(h, L.A))) return rc;
     if (l == 0 && h->compress >= 1 && !L.A.patterned && !L.A.compressed)
       if ((rc = build_csell(h, L.A))) return rc;
@@ -1996,6 +1999,7 @@ int gmg_setup(gmg_handle h) {
           if ((rc = build_sell_host(h, ai, h->drop_tol, L.AI))) return rc;
         }
       }
+      L.edge_free = L.hI.nnz() == 0;
       TraceScope tr_s("    I^T, colours / wavefronts");
       free_sell(L.IT);
       if (!L.hI.empty() && L.hI.nnz() > 0) {

@@ -99,6 +99,7 @@ struct Level {
   int n_fwd = 0, n_bwd = 0, ssor_grid = 0;
   int cluster_blocks = 0;            // > 0: small level, smooth() as one thread-block cluster of this many blocks
   double lambda_max = 0.0;           // Chebyshev
+  bool edge_free = false;             // the interface matrix of the level has no entry (uniform level)
   std::vector<int32_t> user_color;   // optional colouring handed over by the host (gmg_set_level_coloring)
 };
 
