@@ -13,8 +13,18 @@
 //   4. asm_rows_fill: the same column set again + the values, written to the CSR arrays.
 #include "assemble_row.h"
 
+// the cell arrays kept on the device by the last gmg_assemble_rhs call (rhs.cu)
+int gmg_rhs_resident(gmg_context *h, int *n_cells, const double **cell_h, const int **cell_dofs, const double **weights, int *n_q,
+                     const double **rho, int *rho_cells, int *rho_nq);
+
 namespace gmg {
 
+// ncu (profiles/r02_ncu_summary.md): system matrix at 64k atoms -- count<64> 2.35 ms / 872 M warp instructions, fill<64>
+// 5.93 ms / 1794 M, against 0.35 ms / 215 M and 1.44 ms / 544 M for the hanging-node-free level-0 matrix of the same size:
+// three quarters of the instructions are issued by the few warps that hold a row next to a hanging node (a coarse vertex
+// that is a parent of many hanging dofs walks 50-100 incidence entries, each with 8 dofs and their constraint lines).
+// Measured and dropped in round 2: smaller / shared-memory column arrays (32 / 96 / 320 tiers; [32][128] in shared memory),
+// the column set cached between the two passes, batched flag loads -- none moved the two kernels by more than 5 %.
 constexpr int ASM_SMALL = 64;
 constexpr int ASM_LARGE = 320;
 
@@ -125,16 +135,28 @@ static int assemble_matrix_device(gmg_context *h, int n_rows, int64_t n_cells, c
   uint8_t *d_flags = nullptr, *d_cell_hang = nullptr, *d_large = nullptr;
   int64_t *d_hptr = nullptr;
   int *d_err = nullptr;
-  GMG_CUDA(h, arena_alloc(arena, &d_dofs, n_slots));
   GMG_CUDA(h, arena_alloc(arena, &d_flags, n_rows));
   GMG_CUDA(h, arena_alloc(arena, &d_err, 1));
   GMG_CUDA(h, cudaMemsetAsync(d_err, 0, sizeof(int), h->stream));
-  if (int rc = staged_h2d(h, d_dofs, cell_dofs, sizeof(int32_t) * n_slots)) return rc;
-  if (int rc = staged_h2d(h, d_flags, row_flags, sizeof(uint8_t) * n_rows)) return rc;
-  if (cell_h) {
-    GMG_CUDA(h, arena_alloc(arena, &d_h, n_cells));
-    if (int rc = staged_h2d(h, d_h, cell_h, sizeof(double) * n_cells)) return rc;
+  if (cell_dofs) {
+    GMG_CUDA(h, arena_alloc(arena, &d_dofs, n_slots));
+    if (int rc = staged_h2d(h, d_dofs, cell_dofs, sizeof(int32_t) * n_slots)) return rc;
+    if (cell_h) {
+      GMG_CUDA(h, arena_alloc(arena, &d_h, n_cells));
+      if (int rc = staged_h2d(h, d_h, cell_h, sizeof(double) * n_cells)) return rc;
+    }
+  } else {
+    // the cells of the last gmg_assemble_rhs call are still on the device (the same active cells, the same order)
+    int r_cells = 0, n_q = 0, rho_cells = 0, rho_nq = 0;
+    const double *r_h = nullptr, *weights = nullptr, *rho_dev = nullptr;
+    const int *r_dofs = nullptr;
+    if (int rc = gmg_rhs_resident(h, &r_cells, &r_h, &r_dofs, &weights, &n_q, &rho_dev, &rho_cells, &rho_nq)) return rc;
+    if (r_cells != n_cells || !r_dofs || !r_h)
+      return fail(h, GMG_EINVAL, "gmg_assemble_matrix: cell_dofs == NULL needs the cells of a gmg_assemble_rhs call on the same mesh");
+    d_dofs = const_cast<int32_t *>(r_dofs);
+    d_h = const_cast<double *>(r_h);
   }
+  if (int rc = staged_h2d(h, d_flags, row_flags, sizeof(uint8_t) * n_rows)) return rc;
   if (hanging) {
     GMG_CUDA(h, arena_alloc(arena, &d_hptr, (int64_t)n_rows + 1));
     GMG_CUDA(h, arena_alloc(arena, &d_hcol, n_hang));

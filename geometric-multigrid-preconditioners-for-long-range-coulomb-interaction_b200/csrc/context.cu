@@ -1817,7 +1817,7 @@ int gmg_assemble_matrix(gmg_handle h, int which, int level, int32_t n_rows, int6
                         const double *cell_h, double uniform_h, const uint8_t *row_flags, const int64_t *hang_rowptr,
                         const int32_t *hang_col, const double *hang_val, const double *k_ref) {
   if (!h || n_rows < 0 || n_cells < 0 || !k_ref) return GMG_EINVAL;
-  if (n_cells > 0 && !cell_dofs) return GMG_EINVAL;
+  if (n_cells > 0 && !cell_dofs && !(which == GMG_SYSTEM && !cell_h)) return GMG_EINVAL;  // (NULL: the resident RHS cells)
   if (n_rows > 0 && !row_flags) return GMG_EINVAL;
   if (hang_rowptr && hang_rowptr[n_rows] > 0 && (!hang_col || !hang_val)) return GMG_EINVAL;
   gmg::enter(h);

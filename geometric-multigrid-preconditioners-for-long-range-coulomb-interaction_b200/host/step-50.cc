@@ -386,6 +386,7 @@ void LaplaceProblem<dim>::setup_system(const unsigned int &cycle) {
   rhs_constrained.clear();
   hanging_list.clear();
   hanging_list_n = -1;
+  rhs_cells_on_device = nullptr;
   active_cells_cache.reset(new ActiveCells(flatten(*triangulation, *mg_dof_handler, flag_rhs_assembly, base_level())));
   solution.assign(mg_dof_handler->n, 0.0);
   system_rhs.assign(mg_dof_handler->n, 0.0);
@@ -471,6 +472,7 @@ void LaplaceProblem<dim>::assemble_rhs_on_device() {
                              inhom ? &Kref[0][0] : nullptr, inhom ? ghat.data() : nullptr, d.n, d.hang.rowptr.data(),
                              d.hang.col.data(), d.hang.val.data(), constrained.data(), system_rhs.data()),
             "gmg_assemble_rhs");
+  rhs_cells_on_device = (const void *)a.dofs.data();
   if (rec) rec->rhs_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
@@ -530,8 +532,11 @@ void LaplaceProblem<dim>::hand_over_hierarchy() {
       flags.resize(d.n);
       for (int i = 0; i < d.n; ++i) flags[i] = (uint8_t)(d.hanging[i] ? 2 : (d.dirichlet[i] ? 1 : 0));
     }
-    gmg_check(gmg_assemble_matrix(gmg, GMG_SYSTEM, 0, d.n, (int64_t)a.h.size(), a.dofs.data(), a.h.data(), 0.0, flags.data(),
-                                  d.hang.rowptr.data(), d.hang.col.data(), d.hang.val.data(), &Kref[0][0]),
+    // the active cells (dofs, edge lengths) are still on the device from assemble_rhs_on_device() of this cycle
+    const bool resident = rhs_cells_on_device == (const void *)a.dofs.data();
+    gmg_check(gmg_assemble_matrix(gmg, GMG_SYSTEM, 0, d.n, (int64_t)a.h.size(), resident ? nullptr : a.dofs.data(),
+                                  resident ? nullptr : a.h.data(), 0.0, flags.data(), d.hang.rowptr.data(), d.hang.col.data(),
+                                  d.hang.val.data(), &Kref[0][0]),
               "gmg_assemble_matrix");
   } else {
     set(GMG_SYSTEM, 0, system_matrix);

@@ -163,6 +163,7 @@ class LaplaceProblem {
   std::vector<double> rhs_ghat;          // inhomogeneities resolved through the hanging-node lines, per mesh
   std::vector<uint8_t> rhs_constrained;  // constraints.is_constrained(i) as bytes, per mesh
   bool rhs_inhom = false;
+  const void *rhs_cells_on_device = nullptr;  // the cell arrays gmg_assemble_rhs last uploaded (system assembly reuses them)
   std::vector<int> hanging_list;  // hanging dofs, ascending (constraints.distribute), per mesh
   int hanging_list_n = -1;
   std::vector<uint8_t> asm_flags_system, asm_flags_level0;  // row flags of gmg_assemble_matrix, built once per mesh

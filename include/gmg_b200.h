@@ -72,7 +72,9 @@ int gmg_set_matrix(gmg_handle h, int which, int level, int32_t n_rows, int32_t n
  * constraints.distribute_local_to_global into the pattern of make_sparsity_pattern(dof, dsp, constraints, true),
  * :699-701) for which = GMG_SYSTEM, and the level-0 loop of assemble_multigrid (:855-889: boundary / refinement-edge
  * dofs eliminated) for which = GMG_LEVEL, level = 0.  Patch levels (>= 1) are small and stay with gmg_set_matrix.
- *   cell_dofs[n_cells][8]  dofs of the cells in the order of the reference's cell loop (vertex v: bit d = offset along d)
+ *   cell_dofs[n_cells][8]  dofs of the cells in the order of the reference's cell loop (vertex v: bit d = offset along d);
+ *                          which = GMG_SYSTEM: cell_dofs = cell_h = NULL takes the cell arrays the last gmg_assemble_rhs
+ *                          call left on the device (the same active cells in the same order: n_cells must agree)
  *   cell_h[n_cells]        edge length per cell, or NULL: every cell has uniform_h (cell matrix = h * k_ref)
  *   row_flags[n_rows]      bit 0: eliminated row and column (Dirichlet dof, level boundary / refinement-edge dof);
  *                          bit 1: hanging dof, constraint line in the CSR (hang_rowptr[n_rows + 1], hang_col, hang_val;
