@@ -1146,10 +1146,16 @@ static bool window2_plan(gmg_context *h, const Sell &A, int &rows_per_block, int
 static const void *win2_kernel(const gmg_context *h, int &block) {
   if (h->cg_win2_variant == 1) {
     block = 1024;
-    return (const void *)cg_persistent_win2<1024, 24, 2, 0, 6>;
+    return (const void *)cg_persistent_win2<1024, 24, 2, 0, 6, false>;
+  }
+  if (h->cg_win2_variant == 2) {
+    // x += alpha d moved between the publish and the poll of the g.g reduction (hides the reduction, reads d twice):
+    // 39.2 against 39.0 us per iteration on the same box -- no gain, kept for the record
+    block = 512;
+    return (const void *)cg_persistent_win2<512, 8, 6, 24, 6, true>;
   }
   block = 512;
-  return (const void *)cg_persistent_win2<512, 8, 6, 24, 6>;
+  return (const void *)cg_persistent_win2<512, 8, 6, 24, 6, false>;
 }
 
 static int coarse_cg(gmg_context *h, const Sell &A, const double *b, double *x, int max_it, double tol) {

@@ -38,16 +38,15 @@ __device__ __forceinline__ void llg_store(uint64_t *p /*16-byte aligned pair*/, 
 // Sum over all blocks + barrier, every thread contributes `v`.  FENCE: the barrier also orders the blocks' global
 // writes before it against the reads after it (release fence before the publish, acquire fence after the poll).
 // Two block barriers per call: the staging arrays alternate with the parity of the tag (`red`: [2][32], `bc`: [2]).
+// The two halves of ll_grid_sum, for callers that have work to do while the other blocks arrive.
 template <bool FENCE>
-__device__ __forceinline__ double ll_grid_sum(uint64_t *slots, int slot_u64, int nb, double v, uint32_t tag, double *red, double *bc,
-                                              int *bad) {
+__device__ __forceinline__ void ll_publish(uint64_t *slots, int slot_u64, double v, uint32_t tag, double *red) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int par = tag & 1u;
   v = warp_sum(v);
   if (lane == 0) red[par * 32 + w] = v;
   __syncthreads();
-  // (warp 0 has passed a block barrier after every thread's writes: its release fence covers them, and the block
-  // barrier below hands its acquire fence on to every thread, as cooperative groups' grid.sync() does)
+  // (warp 0 has passed a block barrier after every thread's writes: its release fence covers them)
   if (w == 0) {
     const int nw = (blockDim.x + 31) >> 5;
     double r = (lane < nw) ? red[par * 32 + lane] : 0.0;
@@ -56,9 +55,17 @@ __device__ __forceinline__ double ll_grid_sum(uint64_t *slots, int slot_u64, int
       if (FENCE) asm volatile("fence.acq_rel.gpu;" ::: "memory");
       llg_store(slots + (size_t)slot_u64 * blockIdx.x, r, tag);
     }
+  }
+}
+template <bool FENCE>
+__device__ __forceinline__ double ll_await(const uint64_t *slots, int slot_u64, int nb, uint32_t tag, double *bc, int *bad) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int par = tag & 1u;
+  if (w == 0) {
     double s;
     const bool ok = ll_collect_slots<WIN2_MAX_BLOCKS / 32, false>(slots, (size_t)slot_u64, nb, tag, 4000000000LL, s);
     if (lane == 0) {
+      // (the block barrier below hands the acquire fence on to every thread, as cooperative groups' grid.sync() does)
       if (FENCE) asm volatile("fence.acq_rel.gpu;" ::: "memory");
       bc[par] = s;
       if (!ok) *bad = 1;
@@ -66,6 +73,12 @@ __device__ __forceinline__ double ll_grid_sum(uint64_t *slots, int slot_u64, int
   }
   __syncthreads();
   return bc[par];
+}
+template <bool FENCE>
+__device__ __forceinline__ double ll_grid_sum(uint64_t *slots, int slot_u64, int nb, double v, uint32_t tag, double *red, double *bc,
+                                              int *bad) {
+  ll_publish<FENCE>(slots, slot_u64, v, tag, red);
+  return ll_await<FENCE>(slots, slot_u64, nb, tag, bc, bad);
 }
 
 // dynamic shared memory: [4 mbarriers | 2 window stages | diagonal value per pattern id | row index, first entry and
@@ -96,7 +109,7 @@ __host__ __device__ inline Win2Layout win2_layout(int win_elems, int n_pat, int 
 // shared memory and registers only, the direction update moves 32 instead of 40 bytes per row through L2 (these
 // phases run at the L2 slice throughput of the chip, ~43 B / clock / SM, so bytes are what counts).  With 512
 // threads a thread has 128 registers: 24 slices = 48 registers of g for blocks of up to 12288 rows.
-template <int BLOCK, int TW, int SPW, int GV, int DVB>
+template <int BLOCK, int TW, int SPW, int GV, int DVB, bool XSPLIT>
 __global__ void __launch_bounds__(BLOCK, 1)
     cg_persistent_win2(PatView A, const __grid_constant__ DomPat D, const uint32_t *__restrict__ dom_mask, const double *__restrict__ b,
                        double *x, double *g, double *d, double *dt, double *h,
@@ -382,7 +395,31 @@ __global__ void __launch_bounds__(BLOCK, 1)
       }
       if (prof && threadIdx.x == 32) g_cg_block_ns[1][blockIdx.x & 255] += gtime() - tb;
       GMG_PHASE(2)
-      res2 = ll_grid_sum<false>(llB, slot_u64, nb, acc, ++tag, red, bc, &bad);
+      ++tag;
+      ll_publish<false>(llB, slot_u64, acc, tag, red);
+      if (XSPLIT) {
+        // x += alpha d needs alpha only: it runs while the other blocks' partial sums of g.g arrive (the reduction's latency
+        // is hidden behind 24 bytes per row of L2 traffic; d is read once more in the direction update: 40 instead of 32
+        // bytes per row in total, same arithmetic)
+        for (int s0 = s_begin + warp; s0 < s_end; s0 += DVB * WPB) {
+          double dv[DVB], xv[DVB];
+#pragma unroll
+          for (int u = 0; u < DVB; ++u) {
+            const int s = s0 + u * WPB, r = s * 32 + lane;
+            dv[u] = xv[u] = 0.0;
+            if (s < s_end && r < A.n_rows) {
+              dv[u] = (code[(s - s_begin) * 32 + lane] & RC_Z) ? dt[r] : d[r];
+              xv[u] = x[r];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < DVB; ++u) {
+            const int s = s0 + u * WPB, r = s * 32 + lane;
+            if (s < s_end && r < A.n_rows) x[r] = xv[u] + alpha * dv[u];
+          }
+        }
+      }
+      res2 = ll_await<false>(llB, slot_u64, nb, tag, bc, &bad);
       GMG_PHASE(3)
       if (bad) { status = 3; break; }
       res = sqrt(res2);
@@ -390,7 +427,7 @@ __global__ void __launch_bounds__(BLOCK, 1)
       if (it >= max_it) { status = 1; break; }
       const double beta = res2 / gh;
       gh = res2;
-      // ---- x += alpha d ; d = beta d - g -------------------------------------------------------
+      // ---- (x += alpha d ;) d = beta d - g -----------------------------------------------------
       if (prof && threadIdx.x == 32) tb = gtime();
 #pragma unroll
       for (int u0 = 0; u0 < GV; u0 += DVB) {
@@ -404,14 +441,14 @@ __global__ void __launch_bounds__(BLOCK, 1)
           if (s < s_end && r < A.n_rows) {
             z[u] = code[(s - s_begin) * 32 + lane] & RC_Z;
             dv[u] = z[u] ? dt[r] : d[r];
-            xv[u] = x[r];
+            if (!XSPLIT) xv[u] = x[r];
           }
         }
 #pragma unroll
         for (int u = 0; u < DVB; ++u) {
           const int s = s_begin + warp + (u0 + u) * WPB, r = s * 32 + lane;
           if (s < s_end && r < A.n_rows) {
-            x[r] = xv[u] + alpha * dv[u];
+            if (!XSPLIT) x[r] = xv[u] + alpha * dv[u];
             const double dn = beta * dv[u] - greg[u0 + u];
             if (z[u]) dt[r] = dn;  // (d[r] stays 0)
             else d[r] = dn;
@@ -429,7 +466,7 @@ __global__ void __launch_bounds__(BLOCK, 1)
           if (s < s_end && r < A.n_rows) {
             z[u] = code[(s - s_begin) * 32 + lane] & RC_Z;
             dv[u] = z[u] ? dt[r] : d[r];
-            xv[u] = x[r];
+            if (!XSPLIT) xv[u] = x[r];
             gv[u] = g[r];
           }
         }
@@ -437,7 +474,7 @@ __global__ void __launch_bounds__(BLOCK, 1)
         for (int u = 0; u < VB; ++u) {
           const int s = s0 + u * WPB, r = s * 32 + lane;
           if (s < s_end && r < A.n_rows) {
-            x[r] = xv[u] + alpha * dv[u];
+            if (!XSPLIT) x[r] = xv[u] + alpha * dv[u];
             const double dn = beta * dv[u] - gv[u];
             if (z[u]) dt[r] = dn;  // (d[r] stays 0)
             else d[r] = dn;
@@ -451,8 +488,8 @@ __global__ void __launch_bounds__(BLOCK, 1)
       GMG_PHASE(5)
       if (bad) { status = 3; break; }
     }
-    // the x update of the last iteration
-    if (status != 3)
+    // the x update of the last iteration (XSPLIT: already done before the convergence test)
+    if (status != 3 && !XSPLIT)
       for (int s = s_begin + warp; s < s_end; s += WPB) {
         const int r = s * 32 + lane;
         if (r < A.n_rows) {
