@@ -1523,16 +1523,6 @@ static int pcg(gmg_context *h, int precond, double jac_omega, const double *b, d
     GMG_LAUNCH_CHECK(h);
     return GMG_OK;
   };
-  auto check_coarse = [&]() -> int {
-    if (precond != PRECOND_GMG || h->cg_cursor == 0) return GMG_OK;
-    CgResult r;
-    GMG_CUDA(h, gmg::copy_sync(h, &r, h->cg_results + ((h->cg_cursor - 1) % h->cg_ring), sizeof(r), cudaMemcpyDeviceToHost));
-    if (r.status != 0)
-      return fail(h, GMG_ENOCONVERGENCE, "coarse-grid CG: Iterative method reported convergence failure in step " +
-                                             std::to_string(r.iterations) + ". The residual in the last step was " +
-                                             std::to_string(r.res));
-    return GMG_OK;
-  };
   const int rg = reduce_grid(h, n);
   // g = A x - b ; res = ||g||
   if (int rc = spmv<EPI_NRESID, DOT_YY>(h, h->S, x, h->g, b, nullptr, 0.0, &h->scalars->res2)) return rc;
@@ -1553,9 +1543,22 @@ static int pcg(gmg_context *h, int precond, double jac_omega, const double *b, d
     if (int rc = spmv<EPI_ASSIGN, DOT_XY>(h, h->S, h->d, h->hh, nullptr, nullptr, 0.0, &h->scalars->dh)) return rc;
     pcg_update<<<rg, 256, 0, h->stream>>>(n, x, h->g, h->d, h->hh, h->scalars, slot, h->partials, h->counter);
     GMG_LAUNCH_CHECK(h);
-    GMG_CUDA(h, gmg::copy(h, &hs, h->scalars, sizeof(hs), cudaMemcpyDeviceToHost));
+    // one host round trip per iteration: the scalars of the update and the status of the V-cycle's coarse solve together
+    // (into pinned memory: an asynchronous copy to pageable memory is a round trip of its own)
+    CgResult cr{};
+    const bool have_coarse = precond == PRECOND_GMG && h->cg_cursor > 0;
+    static_assert(sizeof(PcgScalars) + sizeof(CgResult) <= 256, "pinned scratch too small");
+    GMG_CUDA(h, gmg::copy(h, h->pin_small, h->scalars, sizeof(hs), cudaMemcpyDeviceToHost));
+    if (have_coarse)
+      GMG_CUDA(h, gmg::copy(h, h->pin_small + sizeof(hs), h->cg_results + ((h->cg_cursor - 1) % h->cg_ring), sizeof(cr),
+                            cudaMemcpyDeviceToHost));
     GMG_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (int rc = check_coarse()) return rc;
+    std::memcpy(&hs, h->pin_small, sizeof(hs));
+    if (have_coarse) std::memcpy(&cr, h->pin_small + sizeof(hs), sizeof(cr));
+    if (have_coarse && cr.status != 0)
+      return fail(h, GMG_ENOCONVERGENCE, "coarse-grid CG: Iterative method reported convergence failure in step " +
+                                             std::to_string(cr.iterations) + ". The residual in the last step was " +
+                                             std::to_string(cr.res));
     res = std::sqrt(hs.res2);
     *res_out = res;
     *iters = it;
@@ -1658,6 +1661,7 @@ int gmg_create(int device, gmg_handle *out) {
   bool ok = dalloc(&h->partials, 3 * h->partials_cap) == cudaSuccess && dalloc(&h->counter, 4) == cudaSuccess &&
             dalloc(&h->scalars, 1) == cudaSuccess && dalloc(&h->cg_results, h->cg_ring) == cudaSuccess &&
             dalloc(&h->cg_ll, WIN2_SLOT_U64_MAX * WIN2_CHANNELS * WIN2_MAX_BLOCKS) == cudaSuccess;
+  if (ok) ok = cudaHostAlloc((void **)&h->pin_small, 256, cudaHostAllocDefault) == cudaSuccess;
   if (ok) {
     cudaMemset(h->cg_ll, 0, sizeof(uint64_t) * WIN2_SLOT_U64_MAX * WIN2_CHANNELS * WIN2_MAX_BLOCKS);
     cudaMemset(h->counter, 0, 4 * sizeof(unsigned int));
@@ -1719,6 +1723,7 @@ int gmg_destroy(gmg_handle h) {
   dfree(h->cg_partials);
   dfree(h->cg_ll);
   dfree(h->ind_eta);
+  if (h->pin_small) cudaFreeHost(h->pin_small);
   dfree(h->cg_results);
   dfree(h->atom_pos);
   dfree(h->atom_q);

@@ -309,6 +309,7 @@ struct gmg_context {
   int cg_win2_variant = 0;     // (GMG_WIN2_VARIANT: vector-phase unrolling under test)
   int cg_win_smem = 0;   // dynamic shared memory the window kernel is currently configured for
   bool is_setup = false;
+  char *pin_small = nullptr;  // 256 bytes of pinned host memory: small D2H results without a staging round trip each
   float *ind_eta = nullptr;  // indicators of the last gmg_error_indicator call (gmg_mark_cells)
   int ind_n = 0;
   float ind_max = 0.0f;
