@@ -131,12 +131,22 @@ __global__ void __launch_bounds__(256) xfer_init(int n, int *stamp, int *owner) 
   }
 }
 __global__ void __launch_bounds__(256) xfer_copy(int n, const int *__restrict__ src, const int *__restrict__ dst,
-                                                 const double *__restrict__ u_old, double *x, int *stamp) {
+                                                 const double *__restrict__ u_old, int n_old, int n_new, double *x, int *stamp,
+                                                 int *bad_index) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) {
+    if (src[k] < 0 || src[k] >= n_old || dst[k] < 0 || dst[k] >= n_new) {
+      *bad_index = 1;
+      return;
+    }
     x[dst[k]] = u_old[src[k]];
     stamp[dst[k]] = -1;
   }
+}
+// the hand-over is untrusted: an index outside [-1, n_new) is reported, never dereferenced
+__global__ void __launch_bounds__(256) xfer_check(int64_t n, const int *__restrict__ pd, int n_new, int *bad_index) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && (pd[i] < -1 || pd[i] >= n_new)) *bad_index = 1;
 }
 // pass l, step 1: a refined cell whose corners are known claims its unknown points (lowest cell index wins)
 __global__ void __launch_bounds__(256) xfer_claim(int64_t p0, int64_t p1, const int *__restrict__ pd, int pass,
@@ -210,16 +220,17 @@ int gmg_transfer_solution(gmg_handle h, int32_t n_old, const double *u_old, int3
   gmg::enter(h);
   const int64_t n_par = pass_ptr[n_pass];
   double *d_old = nullptr, *d_x = nullptr;
-  int *d_src = nullptr, *d_dst = nullptr, *d_pd = nullptr, *d_stamp = nullptr, *d_owner = nullptr, *d_missing = nullptr;
+  int *d_src = nullptr, *d_dst = nullptr, *d_pd = nullptr, *d_stamp = nullptr, *d_owner = nullptr, *d_missing = nullptr, *d_bad = nullptr;
   unsigned char *d_con = nullptr;
   auto cleanup = [&]() {
-    dfree(d_old); dfree(d_x); dfree(d_src); dfree(d_dst); dfree(d_pd); dfree(d_stamp); dfree(d_owner); dfree(d_missing); dfree(d_con);
+    dfree(d_old); dfree(d_x); dfree(d_src); dfree(d_dst); dfree(d_pd); dfree(d_stamp); dfree(d_owner); dfree(d_missing); dfree(d_con); dfree(d_bad);
   };
   cudaError_t e = cudaSuccess;
   if ((e = dalloc(&d_old, n_old)) != cudaSuccess || (e = dalloc(&d_x, n_new)) != cudaSuccess || (e = dalloc(&d_src, n_copy)) != cudaSuccess ||
       (e = dalloc(&d_dst, n_copy)) != cudaSuccess || (e = dalloc(&d_pd, 27 * n_par)) != cudaSuccess ||
       (e = dalloc(&d_stamp, n_new)) != cudaSuccess || (e = dalloc(&d_owner, n_new)) != cudaSuccess ||
-      (e = dalloc(&d_missing, 1)) != cudaSuccess || (e = dalloc(&d_con, n_new)) != cudaSuccess) {
+      (e = dalloc(&d_missing, 1)) != cudaSuccess || (e = dalloc(&d_con, n_new)) != cudaSuccess ||
+      (e = dalloc(&d_bad, 1)) != cudaSuccess) {
     cleanup();
     return gmg::fail(h, GMG_ECUDA, std::string("gmg_transfer_solution: ") + cudaGetErrorString(e));
   }
@@ -232,12 +243,23 @@ int gmg_transfer_solution(gmg_handle h, int32_t n_old, const double *u_old, int3
   }
   cudaMemsetAsync(d_x, 0, sizeof(double) * (size_t)std::max(n_new, 1), h->stream);
   cudaMemsetAsync(d_missing, 0, sizeof(int), h->stream);
+  cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream);
+  if (n_par > 0) {
+    xfer_check<<<cdiv(27 * n_par, 256), 256, 0, h->stream>>>(27 * n_par, d_pd, n_new, d_bad);
+    h->launches++;
+    int bad = 0;
+    e = gmg::copy_sync(h, &bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess || bad) {
+      cleanup();
+      return gmg::fail(h, e != cudaSuccess ? GMG_ECUDA : GMG_EINVAL, "gmg_transfer_solution: a parent_dofs entry is outside [-1, n_new)");
+    }
+  }
   if (n_new > 0) {
     xfer_init<<<cdiv(n_new, 256), 256, 0, h->stream>>>(n_new, d_stamp, d_owner);
     h->launches++;
   }
   if (n_copy > 0) {
-    xfer_copy<<<cdiv(n_copy, 256), 256, 0, h->stream>>>(n_copy, d_src, d_dst, d_old, d_x, d_stamp);
+    xfer_copy<<<cdiv(n_copy, 256), 256, 0, h->stream>>>(n_copy, d_src, d_dst, d_old, n_old, n_new, d_x, d_stamp, d_bad);
     h->launches++;
   }
   for (int l = 0; l < n_pass; ++l) {
@@ -253,12 +275,14 @@ int gmg_transfer_solution(gmg_handle h, int32_t n_old, const double *u_old, int3
     xfer_finish<<<cdiv(n_new, 256), 256, 0, h->stream>>>(n_new, d_con, d_stamp, d_x, d_missing);
     h->launches++;
   }
-  int missing = 0;
+  int missing = 0, bad_copy = 0;
   if ((rc = staged_d2h(h, u_new_out, d_x, sizeof(double) * (size_t)n_new)) == GMG_OK) {
+    gmg::copy(h, &bad_copy, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
     e = gmg::copy_sync(h, &missing, d_missing, sizeof(int), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = gmg::fail(h, GMG_ECUDA, std::string("gmg_transfer_solution: ") + cudaGetErrorString(e));
   }
   cleanup();
+  if (rc == GMG_OK && bad_copy) return gmg::fail(h, GMG_EINVAL, "gmg_transfer_solution: a copy index is out of range");
   if (rc == GMG_OK && missing > 0) return gmg::fail(h, GMG_EINVAL, "solution transfer left a dof without a value");
   return rc;
 }

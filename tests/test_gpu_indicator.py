@@ -92,3 +92,29 @@ def test_solution_transfer_bit_identical_to_sequential_restatement():
         assert np.abs(x).max() > 0
         old = new
     g.close()
+
+
+def test_refinement_entry_points_reject_bad_hand_overs():
+    """Error behaviour of the two new entry points: an index table that points outside the new vector, or marking
+    without indicators on the device, is GMG_EINVAL with a message -- never a wrong answer or an out-of-bounds access."""
+    capi = pkg().capi
+    g = capi.Gmg()
+    with pytest.raises(capi.GmgError):
+        g.mark_cells(10)
+    u_old = np.arange(4, dtype=float)
+    pass_ptr = np.array([0, 1], dtype=np.int64)
+    pd = -np.ones((1, 27), dtype=np.int32)
+    pd[0, 0] = 99  # outside [-1, n_new)
+    with pytest.raises(capi.GmgError):
+        g.transfer_solution(u_old, 4, [0, 1, 2, 3], [0, 1, 2, 3], pass_ptr, pd, np.zeros(4, dtype=np.uint8))
+    with pytest.raises(capi.GmgError):
+        g.transfer_solution(u_old, 4, [0, 1, 2, 7], [0, 1, 2, 3], np.array([0], dtype=np.int64), np.zeros((0, 27), dtype=np.int32),
+                            np.zeros(4, dtype=np.uint8))
+    # a dof nobody provides a value for
+    with pytest.raises(capi.GmgError):
+        g.transfer_solution(u_old, 5, [0, 1, 2, 3], [0, 1, 2, 3], np.array([0], dtype=np.int64), np.zeros((0, 27), dtype=np.int32),
+                            np.zeros(5, dtype=np.uint8))
+    x = g.transfer_solution(u_old, 4, [0, 1, 2, 3], [3, 2, 1, 0], np.array([0], dtype=np.int64), np.zeros((0, 27), dtype=np.int32),
+                            np.array([0, 0, 0, 1], dtype=np.uint8))
+    assert np.array_equal(x, [3.0, 2.0, 1.0, 0.0])  # (constrained dof 3 zeroed: it held u_old[0] = 0 anyway)
+    g.close()
