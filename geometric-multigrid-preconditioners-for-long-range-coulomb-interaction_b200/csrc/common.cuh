@@ -184,6 +184,13 @@ struct PatView {
   const int *rem_ptr;     // the same rows as CSR (rem.n_rows + 1 offsets; window kernel: 4 lanes per row)
   const int *rem_ccol;
   const double *rem_cval;
+  // the same rows once more for the 4-lanes-per-row walk of the window kernel, in the order the lanes load them: groups
+  // of 8 rows, per group [8 entries][32 lanes] (lane = 4 * row-in-group + quarter; lane's i-th entry, column -1 = none):
+  // one coalesced line per load instruction instead of 32 sectors.  rem4_long[group] != 0: a row of the group has more
+  // than 32 entries (walked through the CSR copy)
+  const int *rem4_col;
+  const double *rem4_val;
+  const unsigned char *rem4_long;
 };
 
 // Dominant pattern + window plan of the TMA-staged persistent CG (pattern_win.cuh)

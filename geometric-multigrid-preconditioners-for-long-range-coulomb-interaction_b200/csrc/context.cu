@@ -49,6 +49,9 @@ static void free_sell(Sell &s) {
   dfree(s.rem_ptr);
   dfree(s.rem_ccol);
   dfree(s.rem_cval);
+  dfree(s.rem4_col);
+  dfree(s.rem4_val);
+  dfree(s.rem4_long);
   dfree(s.dom_mask);
   dfree(s.row_code);
   s = Sell{};
@@ -449,6 +452,9 @@ static int build_pat(gmg_context *h, Sell &s) {
     dfree(s.rem_ptr);
     dfree(s.rem_ccol);
     dfree(s.rem_cval);
+    dfree(s.rem4_col);
+    dfree(s.rem4_val);
+    dfree(s.rem4_long);
     dfree(s.dom_mask);
     dfree(s.row_code);
   };
@@ -646,12 +652,23 @@ static int build_pat(gmg_context *h, Sell &s) {
       sell_sub_fill_csr<<<cdiv(n_rem, 256), 256, 0, h->stream>>>(s.v, n_rem, s.rem_rows, s.rem_ptr, s.rem_ccol, s.rem_cval);
       GMG_LAUNCH_CHECK(h);
     }
+    // ... and in the lane order of the window kernel's remainder warps (coalesced loads)
+    const int n_groups = cdiv(n_rem, 8);
+    GMG_CUDA(h, dalloc(&s.rem4_col, (int64_t)n_groups * 256));
+    GMG_CUDA(h, dalloc(&s.rem4_val, (int64_t)n_groups * 256));
+    GMG_CUDA(h, dalloc(&s.rem4_long, n_groups));
+    if (n_groups > 0) {
+      GMG_CUDA(h, cudaMemsetAsync(s.rem4_long, 0, (size_t)n_groups, h->stream));
+      rem4_build<<<cdiv((int64_t)n_groups * 32, 256), 256, 0, h->stream>>>(n_rem, s.rem_ptr, s.rem_ccol, s.rem_cval, s.rem4_col,
+                                                                          s.rem4_val, s.rem4_long);
+      GMG_LAUNCH_CHECK(h);
+    }
   }
   GMG_CUDA(h, cudaStreamSynchronize(h->stream));
   cleanup();
   s.pv = PatView{s.v.n_rows, s.v.n_cols, s.v.n_slices, s.pat,      s.pat_ptr,  s.pat_off, s.pat_val, np + 1, n_ent,
                  SellView{n_rem, s.v.n_cols, rs, s.rem_slice_ptr, s.rem_val, s.rem_col},
-                 s.rem_rows, s.rem_ptr,  s.rem_ccol,   s.rem_cval};
+                 s.rem_rows, s.rem_ptr,  s.rem_ccol,   s.rem_cval, s.rem4_col, s.rem4_val, s.rem4_long};
   s.patterned = true;
   {
     std::vector<int> hoff(n_ent);
@@ -1133,7 +1150,8 @@ static bool window2_plan(gmg_context *h, const Sell &A, int &rows_per_block, int
   for (int i = h->win_global_codes ? 3 : 0; i < 4; ++i) {
     h_smem = tries[i][0];
     code_smem = tries[i][1];
-    lay = win2_layout(A.dom2.win_elems, A.pv.n_pat, rows_per_block, h_smem != 0, code_smem != 0, A.pv.rem.n_rows / h->sm_count + 1);
+    lay = win2_layout(A.dom2.win_elems, A.pv.n_pat, rows_per_block, h_smem != 0, code_smem != 0,
+                      8 * (((A.pv.rem.n_rows + 7) >> 3) / h->sm_count + 1));
     if (lay.total <= smem_cap) return true;
   }
   return false;

@@ -69,6 +69,9 @@ struct Sell {
   int64_t rem_padded = 0;
   int *rem_ptr = nullptr, *rem_ccol = nullptr;  // the remainder rows as CSR
   double *rem_cval = nullptr;
+  int *rem4_col = nullptr;                      // ... and in the lane order of the window kernel (PatView::rem4_*)
+  double *rem4_val = nullptr;
+  unsigned char *rem4_long = nullptr;
   // dominant pattern + TMA window plan for the persistent CG (pattern_win.cuh); dom.len == 0: not available
   DomPat dom{};
   DomPat dom2{};         // the same pattern planned for the tile size of pattern_win2.cuh

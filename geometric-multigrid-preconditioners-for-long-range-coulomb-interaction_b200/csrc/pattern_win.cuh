@@ -242,6 +242,59 @@ __device__ __forceinline__ double rem_row_dot4_at(const PatView &A, int p0, int 
   return acc;
 }
 
+constexpr int REM4_NONE = (int)0x80000000;  // "no entry" in rem4_col (rank-local blocks have negative halo columns)
+// The lane-ordered copy of the remainder rows (PatView::rem4_*): thread (group, lane) writes the up to 8 entries lane
+// `lane` of a remainder warp walks for row 8 * group + lane / 4 -- the quarter `lane & 3` of the row's first 32 entries,
+// split exactly as rem_row_dot4_at splits them.
+__global__ void __launch_bounds__(256) rem4_build(int n_rem, const int *__restrict__ rem_ptr, const int *__restrict__ ccol,
+                                                  const double *__restrict__ cval, int *__restrict__ col4,
+                                                  double *__restrict__ val4, unsigned char *__restrict__ is_long) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int group = (int)(t >> 5), lane = (int)(t & 31);
+  if (group * 8 >= n_rem) return;
+  const int k = group * 8 + (lane >> 2), c = lane & 3;
+  int p0 = 0, len = 0;
+  if (k < n_rem) {
+    p0 = rem_ptr[k];
+    len = rem_ptr[k + 1] - p0;
+  }
+  if (len > 32 && c == 0) is_long[group] = 1;
+  const int n_here = min(len, 32);
+  const int chunk = (n_here + 3) >> 2;
+  const int e0 = p0 + c * chunk;
+  const int cnt = max(min(chunk, n_here - c * chunk), 0);
+  for (int i = 0; i < 8; ++i) {
+    col4[(int64_t)group * 256 + i * 32 + lane] = i < cnt ? ccol[e0 + i] : REM4_NONE;
+    val4[(int64_t)group * 256 + i * 32 + lane] = i < cnt ? cval[e0 + i] : 0.0;
+  }
+}
+// the walk of rem_row_dot4_at on that copy (rows of at most 32 entries): same entries per lane, same chain
+__device__ __forceinline__ double rem_row_dot4_lanes(const PatView &A, int group, const double *__restrict__ x) {
+  const int lane = threadIdx.x & 31, c = lane & 3;
+  const int *cp = A.rem4_col + (int64_t)group * 256 + lane;
+  const double *vp = A.rem4_val + (int64_t)group * 256 + lane;
+  double v[8], xv[8];
+  int col[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    col[i] = __ldg(cp + i * 32);
+    v[i] = __ldg(vp + i * 32);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) xv[i] = col[i] != REM4_NONE ? x[col[i]] : 0.0;
+  double acc = 0.0;
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    if (c == cc) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (col[i] != REM4_NONE) acc = fma(v[i], xv[i], acc);
+    }
+    acc = __shfl_sync(0xffffffffu, acc, (threadIdx.x & 28) | cc);
+  }
+  return acc;
+}
+
 // 1024 threads: warps 0..30 compute, warp 31 is the TMA producer.  A tile is 31 * SPW slices; consumer warp w takes
 // the slices tile + w, tile + w + 31, ... so that each table constant (window offset, value) is loaded once for SPW
 // rows.  Two window stages with full / empty mbarriers; no block-wide barrier inside the SpMV.

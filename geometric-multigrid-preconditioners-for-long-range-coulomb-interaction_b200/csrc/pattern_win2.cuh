@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(BLOCK, 1)
   constexpr int VB = 4;                    // slices per warp and round of the rows whose g lives in global memory
   unsigned long long t_prev = 0;
   const int nb = gridDim.x;
-  const int rem_per_block = A.rem.n_rows / nb + 1;
+  const int n_groups = (A.rem.n_rows + 7) >> 3;  // remainder rows are walked in groups of 8 (PatView::rem4_*)
+  const int rem_per_block = 8 * (n_groups / nb + 1);
   const Win2Layout lay = win2_layout(D.win_elems, A.n_pat, rows_per_block, h_smem != 0, code_smem != 0, rem_per_block);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem);  // [2]
   uint64_t *empty_bar = full + 2;                       // [2]
@@ -144,8 +145,9 @@ __global__ void __launch_bounds__(BLOCK, 1)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int s_begin = (int)(((int64_t)A.n_slices * blockIdx.x) / nb);
   const int s_end = (int)(((int64_t)A.n_slices * (blockIdx.x + 1)) / nb);
-  const int k_begin = (int)(((int64_t)A.rem.n_rows * blockIdx.x) / nb);
-  const int k_end = (int)(((int64_t)A.rem.n_rows * (blockIdx.x + 1)) / nb);
+  const int g_begin = (int)(((int64_t)n_groups * blockIdx.x) / nb);
+  const int g_end = (int)(((int64_t)n_groups * (blockIdx.x + 1)) / nb);
+  const int k_begin = 8 * g_begin, k_end = min(8 * g_end, A.rem.n_rows);
   const int n_tiles = (s_end - s_begin + TILE - 1) / TILE;
   const int n_even = (A.n_rows + 1) & ~1;
   const int s_glob = s_begin + GV * WPB;   // first slice whose g lives in global memory
@@ -249,12 +251,13 @@ __global__ void __launch_bounds__(BLOCK, 1)
       } else if (warp >= TW) {
         // remainder rows (this block's share of ALL of them, not the ones it owns): 8 per warp and round, 4 lanes per
         // row; h goes to global memory, the owner reads it there
-        for (int k0 = (warp - TW) * 8; k0 < k_end - k_begin; k0 += RW * 8) {
-          const int k = k0 + (lane >> 2);
+        for (int gq = g_begin + (warp - TW); gq < g_end; gq += RW) {
+          const int k = (gq - g_begin) * 8 + (lane >> 2);
           const bool on = k < k_end - k_begin;
           const int r = on ? rrow[k] : 0;
           const double dv = (on && (lane & 3) == 0) ? d[r] : 0.0;  // (in flight together with the row's entries)
-          const double aq = rem_row_dot4_at(A, on ? rp0[k] : 0, on ? rlen[k] : 0, lane & 3, d);
+          const double aq = A.rem4_long[gq] ? rem_row_dot4_at(A, on ? rp0[k] : 0, on ? rlen[k] : 0, lane & 3, d)
+                                            : rem_row_dot4_lanes(A, gq, d);
           if (on && (lane & 3) == 0) {
             h[r] = aq;
             acc += dv * aq;
