@@ -1,0 +1,54 @@
+"""GPU runs of the reference's other regression tests through the drop-in `LaplaceProblem` (host class + CUDA library):
+`tests/test_with_optimal_parameters`, `tests_rhs_rc_variation/rc_variation`, `tests_3D/gaussian-charges`.
+Mesh and settings as in tests/test_oracle_reference_tests.py (hyper cube refined 4 times = `Coarse levels below the base
+mesh = 4` on a 16^3 lattice without vacuum; Jacobi(0.5) x 2 smoothing, Kelly marking: the build that wrote the goldens)."""
+import pytest
+
+import hostlib
+from test_oracle_goldens import check_cycle, printed_tol
+from test_oracle_reference_tests import hyper_cube_prm
+
+pytestmark = pytest.mark.gpu
+
+OLD_BUILD = ("subsection Solver input data\n set Smoother = Jacobi\nend\n"
+             "subsection Misc\n set Refinement indicator = Kelly\n set Energy postprocessing atom limit = 0\nend\n")
+
+
+@pytest.mark.parametrize("run,flag", [(0, "true"), (1, "false")])
+def test_with_optimal_parameters_eight_cycles_every_digit(goldens, run, flag):
+    """All 8 adaptive cycles of tests/test_with_optimal_parameters.mpirun=1.output on the device: cells, DoFs per
+    level, starting residuals, Jacobi-smoothed iteration counts 7,7,7,9,9,10,9,9 and solution norms to the printed
+    digits, convergence values to 1e-3 (the tail of the Krylov recurrence follows the summation order)."""
+    gold = goldens["optimal_parameters"][run]
+    text, recs = hostlib.run_problem(hyper_cube_prm(-5, 5, 4, 8, flag=flag, extra=OLD_BUILD))
+    assert len(recs) == 8
+    assert ("Rhs assembly optimization ENABLED" if flag == "true" else "Without rhs assembly optimization") in text
+    for rec, g in zip(recs, gold["cycles"]):
+        check_cycle(rec, g, conv_rel=1e-3)
+    assert "(by level: 8, 27, 125, 729, 4913, 981, 622)" in text
+
+
+def test_rc_variation_rhs_norms(goldens):
+    """tests_rhs_rc_variation: the load vector of 2 atoms on 16^3 cells of [-2.5, 2.5]^3 summed over all atoms (no
+    lists) and through lists with the largest cutoff of the sweep (6.0 r_c ... the printed digits are the same)."""
+    g = goldens["rc_variation"][0]["cycles"][0]
+    for cutoff, flag in ((2.0, "false"), (6.0, "true")):
+        _, recs = hostlib.run_problem(hyper_cube_prm(-2.5, 2.5, 4, 1, cutoff=cutoff, flag=flag, extra=OLD_BUILD))
+        assert recs[0]["n_dofs_level"] == g["n_dofs_level"]
+        assert abs(recs[0]["rhs_l2"] - g["rhs_l2"]) <= printed_tol(g["rhs_l2_digits"])
+        assert abs(recs[0]["rhs_linf"] - g["rhs_linf"]) <= printed_tol(g["rhs_linf_digits"])
+
+
+def test_gaussian_function_without_atoms(goldens):
+    """tests_3D/gaussian-charges.mpirun=1.output: no atom file (`GaussianCharges::RightHandSide`), 8 adaptive cycles;
+    cycle 0 in every printed number (7 iterations, 1.26552e-09), later cycles in cells, DoFs per level and solution
+    norms (see the CPU twin of this test for why not the starting residuals)."""
+    gold = goldens["gaussian_function_3d"][0]["cycles"]
+    text, recs = hostlib.run_problem(hyper_cube_prm(-2.5, 2.5, 4, 8, cutoff=3, atom="", flag="false", extra=OLD_BUILD))
+    assert "Unable to open the file." in text and len(recs) == 8
+    check_cycle(recs[0], gold[0], conv_rel=1e-3)
+    for rec, g in zip(recs, gold):
+        assert rec["n_active_cells"] == g["n_active_cells"]
+        assert rec["n_dofs_level"] == g["n_dofs_level"]
+        for k in ("sol_l1", "sol_l2", "sol_linf"):
+            assert abs(rec[k] - g[k]) <= printed_tol(g[k + "_digits"]) + 1e-7 * abs(g[k]), (g["cycle"], k)
