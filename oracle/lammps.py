@@ -41,4 +41,5 @@ def write(path, pos, q):
         f.write("\nMasses\n\n      1\t\t22.989\n      2 \t35.453\n\nAtoms # full\n\n")
         for i in range(n):
             t = 1 if q[i] > 0 else 2
-            f.write(f"{i + 1} {i + 1} {t} {q[i]:.1f} {pos[i, 0]:.1f} {pos[i, 1]:.1f} {pos[i, 2]:.1f}\n")
+            x, y, z = (repr(float(v)) for v in pos[i])  # shortest text that reads back to the same double
+            f.write(f"{i + 1} {i + 1} {t} {q[i]:.1f} {x} {y} {z}\n")

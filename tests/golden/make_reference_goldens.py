@@ -58,6 +58,17 @@ def parse(relpath):
                 continue
             if cyc is None:
                 continue
+            # tests/cell_data_transfer_test: the atom list every cell hands to its children, printed while the
+            # refinement of this cycle packs the parents' data ("cell with center x y has n values:" + the list)
+            m = re.match(r"cell with center (.+) has (\d+) values:", line)
+            if m:
+                cyc.setdefault("cell_lists", []).append(dict(center=[float(t) for t in m.group(1).split()],
+                                                             n=int(m.group(2)), atoms=None, line=no))
+                continue
+            if cyc.get("cell_lists") and cyc["cell_lists"][-1]["atoms"] is None:
+                cyc["cell_lists"][-1]["atoms"] = [int(t) for t in line.split()]
+                assert len(cyc["cell_lists"][-1]["atoms"]) == cyc["cell_lists"][-1]["n"]
+                continue
             for pat, key, conv in KEYS:
                 m = re.search(pat, line)
                 if m:
@@ -81,6 +92,8 @@ FILES = {
     "gaussian_function_2d": "tests_2D/gaussian-charges.mpirun=1.output",
     "optimal_parameters": "tests/test_with_optimal_parameters.mpirun=1.output",
     "rc_variation": "tests_rhs_rc_variation/rc_variation.mpirun=1.output",
+    "cell_data_transfer": "tests/cell_data_transfer_test.mpirun=1.output",
+    "cell_data_transfer_mpirun3": "tests/cell_data_transfer_test.mpirun=3.output",
     "cluster_ssor_run": "Cluster runs output and postprocessing/SSOR_run.o876223",
     "cluster_ssor_64k": "Cluster runs output and postprocessing/SSOR_64k_atoms.o876224",
     "cluster_without_opti": "Cluster runs output and postprocessing/without_opti.o875054",
@@ -93,6 +106,7 @@ if __name__ == "__main__":
     from oracle import lammps
     import numpy as np
     for src, dst in (("tests/atom_n1_2.data", "atom_n1_2.data"), ("tests/atom_2.data", "atom_2.data"),
+                     ("tests/atom_3.data", "atom_3.data"),
                      ("atom/atom_n1_8.data", "atom_n1_8.data")):
         pos, q, _ = lammps.read(os.path.join(REF, src))
         lammps.write(os.path.join(HERE, dst), pos, q)

@@ -52,3 +52,23 @@ def test_gaussian_function_without_atoms(goldens):
         assert rec["n_dofs_level"] == g["n_dofs_level"]
         for k in ("sol_l1", "sol_l2", "sol_linf"):
             assert abs(rec[k] - g[k]) <= printed_tol(g[k + "_digits"]) + 1e-7 * abs(g[k]), (g["cycle"], k)
+
+
+def test_binning_reproduces_the_cell_data_transfer_lists(goldens):
+    """tests/cell_data_transfer_test.mpirun=1.output (the only golden that prints atom lists) through `gmg_bin_atoms`:
+    the 2D cells become 3D cells in the plane of the atoms (z = 0: the four vertices at z = h are never the nearest), so
+    the device's nearest-vertex test must reproduce the printed lists -- including atom 0, whose distance to a vertex
+    differs from the cutoff in the last bit (0.85 - 0.5 against 3.5 * 0.1)."""
+    import numpy as np
+    from helpers import pkg
+    from test_oracle_reference_tests import cell_data_transfer_case
+    f, pos2, cutoff = cell_data_transfer_case()
+    pos = np.concatenate([pos2, np.zeros((3, 1))], axis=1)
+    g = pkg().capi.Gmg()
+    try:
+        for level, cyc in ((1, goldens["cell_data_transfer"][0]["cycles"][1]),):
+            lo = np.concatenate([f.lo + f.ijk[level] * f.h(level), np.zeros((f.n_cells(level), 1))], axis=1)
+            ptr, idx = g.bin_atoms(lo, np.full(f.n_cells(level), f.h(level)), pos, cutoff)
+            assert [list(idx[ptr[k]:ptr[k + 1]]) for k in range(f.n_cells(level))] == [c["atoms"] for c in cyc["cell_lists"]]
+    finally:
+        g.close()

@@ -10,6 +10,7 @@ hyper cube refined n times, and the atom lists are made on the cells that are ac
 `rhs_assembly_optimization` does (src/step-50.cc:262-293).  The golden files were written by the build that smoothed
 with Jacobi(0.5) x 2 and marked with the Kelly estimator alone (the same build as the cluster logs, DESIGN.md
 section 2): with those two settings every printed digit is reproduced."""
+import numpy as np
 import pytest
 
 from conftest import make_prm
@@ -126,3 +127,53 @@ def test_host_builds_the_same_hyper_cube_hierarchy_as_the_oracle():
         assert np.array_equal(M.get("copy_global", l), d.copy_global[l])
     assert np.array_equal(M.get("dof_xyz").reshape(-1, 3), d.xyz)
     assert np.array_equal(M.get("hanging").astype(bool), d.hanging)
+
+
+def cell_data_transfer_case():
+    """Mesh and atoms of tests/cell_data_transfer_test.prm: hyper_cube(0, 1) in 2D refined once (4 cells), the 3 atoms of
+    tests/atom_3.data, cutoff 3.5 r_c with r_c = 0.1; returns (forest, positions, cutoff)."""
+    import os
+    from conftest import GOLDEN
+    from oracle import lammps
+    from oracle.mesh import Forest
+    pos, q, _ = lammps.read(os.path.join(GOLDEN, "atom_3.data"))
+    assert np.array_equal(pos[:, 2], np.zeros(3)) and list(q) == [1.0, -1.0, 1.0]
+    f = Forest(1, 0.0, 1.0, 2)
+    f.refine_global(1)
+    return f, pos[:, :2], 3.5 * 0.1
+
+
+def literal_lists(f, level, pos, cutoff):
+    """src/step-50.cc:262-293 word for word: a cell lists atom i iff one of its vertices is closer than the cutoff."""
+    verts = f.real_coords(f.vertex_coords(level))  # (cells, 2^dim, dim)
+    ptr, idx = [0], []
+    for c in range(len(verts)):
+        for i in range(len(pos)):
+            if any(np.sqrt(((pos[i] - v) ** 2).sum()) < cutoff for v in verts[c]):
+                idx.append(i)
+        ptr.append(len(idx))
+    return np.array(ptr, dtype=np.int64), np.array(idx, dtype=np.int64)
+
+
+def test_cell_data_transfer_atom_lists(goldens):
+    """tests/cell_data_transfer_test.mpirun=1 / 3.output: the ONLY golden that prints atom lists.  Cycle 1 prints the
+    list of each of the 4 cells of the first mesh (the binning rule, including the atom that sits 0.35 - 2e-17 from a
+    vertex with the cutoff at 0.35 + 3e-17), cycle 2 the lists of their 16 children (every child carries its parent's
+    list, src/step-50.cc:441-449) in the order the cells are visited."""
+    from oracle import rhs
+    f, pos, cutoff = cell_data_transfer_case()
+    lists1 = literal_lists(f, 1, pos, cutoff)
+    f.refine([np.zeros(1, dtype=bool), np.ones(4, dtype=bool)])
+    assert f.n_cells(2) == 16
+    lists = rhs.inherit_lists(f, lists1, base_level=1)
+    for key in ("cell_data_transfer", "cell_data_transfer_mpirun3"):
+        cyc = goldens[key][0]["cycles"]
+        assert goldens[key][0]["n_atoms"] == 3
+        for level, c in ((1, cyc[1]), (2, cyc[2])):
+            ptr, idx = lists[level]
+            centres = f.lo + (f.ijk[level] + 0.5) * f.h(level)
+            assert len(c["cell_lists"]) == f.n_cells(level)
+            mine = {tuple(centres[k]): list(idx[ptr[k]:ptr[k + 1]]) for k in range(f.n_cells(level))}
+            assert mine == {tuple(gl["center"]): gl["atoms"] for gl in c["cell_lists"]}, (key, level)
+            if key == "cell_data_transfer":  # one rank: also the visiting order (parent by parent, children in z-order)
+                assert [tuple(gl["center"]) for gl in c["cell_lists"]] == list(mine)
