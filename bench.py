@@ -177,6 +177,13 @@ def write_atoms(args):
 
 
 KERNEL_NAMES = {
+    8: "gmg::cg_persistent_win2 XPAIR (coarse-level CG on the row-pattern matrix: TMA-filled shared-memory windows, two consecutive "
+       "rows per lane in the dominant loop, tagged-word grid reductions, remainder rows on dedicated warps; h in global memory; "
+       "one launch per V-cycle)",
+    7: "gmg::cg_persistent_win2 XPAIR (coarse-level CG on the row-pattern matrix: TMA-filled shared-memory windows, two consecutive "
+       "rows per lane in the dominant loop (LDS.128 / conflict-free LDS.64, 8 instead of 12 shared-memory wavefronts per run and "
+       "64 rows), tagged-word grid reductions, remainder rows on dedicated warps, h = A d kept in shared memory; one launch per "
+       "V-cycle)",
     6: "gmg::cg_persistent_win2 (coarse-level CG on the row-pattern matrix: TMA-filled shared-memory windows, tagged-word grid "
        "reductions, remainder rows on dedicated warps; h in global memory; one launch per V-cycle)",
     5: "gmg::cg_persistent_win2 (coarse-level CG on the row-pattern matrix: TMA-filled shared-memory windows, tagged-word grid "

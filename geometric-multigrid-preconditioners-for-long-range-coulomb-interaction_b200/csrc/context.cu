@@ -1157,11 +1157,26 @@ static bool window2_plan(gmg_context *h, const Sell &A, int &rows_per_block, int
   return false;
 }
 
-// variant 0 (default): 512 threads with 128 registers: 8 tile warps x 6 slices, 7 remainder warps, g of up to 24 slices per
-// thread in registers; 1: 1024 threads, 24 tile warps x 2 slices, g in global memory (GMG_WIN2_VARIANT; B200, 64k atoms:
-// 41.4 against 43.4 us per iteration, 12 tile warps x 4 slices with 3 remainder warps: 43.4 -- the remainder rows become the
-// critical path of the SpMV phase)
-static const void *win2_kernel(const gmg_context *h, int &block) {
+// GMG_WIN2_VARIANT (default -1 = 3 where the dominant pattern allows it, else 0).
+// 0: 512 threads with 128 registers: 8 tile warps x 6 slices, 7 remainder warps, g of up to 24 slices per thread in registers;
+// 1: 1024 threads, 24 tile warps x 2 slices, g in global memory (B200, 64k atoms: 41.4 against 43.4 us per iteration; 12 tile
+//    warps x 4 slices with 3 remainder warps: 43.4 -- the remainder rows become the critical path of the SpMV phase);
+// 3: variant 0 with two consecutive rows per lane in the dominant loop (XPAIR, pattern_win2.cuh), for the dominant pattern of a
+//    Q1 lattice (9 runs of three consecutive columns, XP_ODD / XP_DIAG of pattern_win2.cuh): 32.5 against 36.9 us per inner
+//    iteration at 64k atoms, same iteration counts, solutions equal to 3e-16.
+static bool xpair_supported(const DomPat &D) {
+  if (D.len != 3 * XP_RUNS || D.win_elems % 2 != 0) return false;
+  for (int r = 0; r < XP_RUNS; ++r) {
+    if (D.wbyte[3 * r + 1] != D.wbyte[3 * r] + 8 || D.wbyte[3 * r + 2] != D.wbyte[3 * r] + 16) return false;
+    if (D.wbyte[3 * r] % 8 != 0 || (uint32_t)((D.wbyte[3 * r] >> 3) & 1) != ((XP_ODD >> r) & 1u)) return false;
+  }
+  return D.wbyte[3 * XP_DIAG + 1] == D.diag_wbyte;
+}
+static const void *win2_kernel(const gmg_context *h, const DomPat &D, int &block) {
+  if ((h->cg_win2_variant == 3 || h->cg_win2_variant < 0) && xpair_supported(D)) {
+    block = 512;
+    return (const void *)cg_persistent_win2<512, 8, 6, 24, 6, false, true>;
+  }
   if (h->cg_win2_variant == 1) {
     block = 1024;
     return (const void *)cg_persistent_win2<1024, 24, 2, 0, 6, false>;
@@ -1200,10 +1215,11 @@ static int coarse_cg(gmg_context *h, const Sell &A, const double *b, double *x, 
     Win2Layout lay2{};
     if (pat && window2_plan(h, A, rows_per_block, h_smem, code_smem, lay2)) {
       int win2_block = 0;
-      const void *win2_fn = win2_kernel(h, win2_block);
-      if (lay2.total > h->cg_win2_smem) {
-        GMG_CUDA(h, cudaFuncSetAttribute(win2_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, lay2.total));
-        h->cg_win2_smem = lay2.total;
+      const void *win2_fn = win2_kernel(h, A.dom2, win2_block);
+      if (lay2.total > h->cg_win2_smem || win2_fn != h->cg_win2_fn) {  // (the variant may differ from matrix to matrix)
+        h->cg_win2_smem = std::max(h->cg_win2_smem, lay2.total);
+        GMG_CUDA(h, cudaFuncSetAttribute(win2_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cg_win2_smem));
+        h->cg_win2_fn = win2_fn;
       }
       // tags of this launch: 1 (|b|) + 3 per iteration + 1 (status); never 0, never reused while a slot still holds them
       const uint32_t need = 3u * (uint32_t)std::max(max_it, 1) + 8u;
@@ -2544,6 +2560,7 @@ int gmg_coarse_kernel(gmg_handle h, int which, int level, int *kernel) {
   Win2Layout lay2{};
   if (!h->dist.on && window2_plan(h, *A, rpb, hs, cs, lay2)) {
     *kernel = 5 + (hs ? 0 : 1);  // 5: h of the block's rows in shared memory, 6: in global memory
+    if ((h->cg_win2_variant == 3 || h->cg_win2_variant < 0) && xpair_supported(A->dom2)) *kernel += 2;  // 7 / 8: two consecutive rows per lane (XPAIR)
     return GMG_OK;
   }
   if (h->dist.on) *kernel = (A->patterned && h->compress >= 2) ? 2 : (A->compressed && h->compress >= 1) ? 1 : 0;

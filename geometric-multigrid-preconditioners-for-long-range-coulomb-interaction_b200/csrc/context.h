@@ -309,7 +309,8 @@ struct gmg_context {
   int vc_ev_used = 0;
   int cg_prof = 0;       // gmg_debug_cg_phases: per-phase timing inside the window kernel
   int cg_win2_smem = 0;
-  int cg_win2_variant = 0;     // (GMG_WIN2_VARIANT: vector-phase unrolling under test)
+  const void *cg_win2_fn = nullptr;  // the kernel cg_win2_smem was last set on
+  int cg_win2_variant = -1;    // GMG_WIN2_VARIANT: -1 = pick (XPAIR where the dominant pattern allows it), 0..3 = force (context.cu)
   int cg_win_smem = 0;   // dynamic shared memory the window kernel is currently configured for
   bool is_setup = false;
   char *pin_small = nullptr;  // 256 bytes of pinned host memory: small D2H results without a staging round trip each

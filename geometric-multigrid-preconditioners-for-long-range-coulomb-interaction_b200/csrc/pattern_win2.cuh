@@ -26,7 +26,11 @@ constexpr int WIN2_TILE_SLICES = 48;                     // slices per tile: 24 
 constexpr int WIN2_TILE_ROWS = WIN2_TILE_SLICES * 32;
 constexpr int WIN2_MAX_BLOCKS = 256;                     // slots one lane polls: 8
 constexpr int WIN2_CHANNELS = 4;
-constexpr int WIN2_SLOT_U64_MAX = 128;                   // largest distance of two blocks' slots (in 64-bit words: 1 KB)
+constexpr int WIN2_SLOT_U64_MAX = 128;
+// XPAIR (below) is compiled for the dominant pattern of a Q1 lattice with an odd number of vertices per line: 9 runs of
+// 3 consecutive columns, runs 0, 2, 4, 6, 8 start at an odd window position, the diagonal is the middle entry of run 4
+constexpr int XP_RUNS = 9, XP_DIAG = 4;
+constexpr uint32_t XP_ODD = 0x155u;                   // largest distance of two blocks' slots (in 64-bit words: 1 KB)
 
 __device__ __forceinline__ void llg_store(uint64_t *p /*16-byte aligned pair*/, double v, uint32_t tag) {
   const uint64_t bits = (uint64_t)__double_as_longlong(v);
@@ -109,7 +113,19 @@ __host__ __device__ inline Win2Layout win2_layout(int win_elems, int n_pat, int 
 // shared memory and registers only, the direction update moves 32 instead of 40 bytes per row through L2 (these
 // phases run at the L2 slice throughput of the chip, ~43 B / clock / SM, so bytes are what counts).  With 512
 // threads a thread has 128 registers: 24 slices = 48 registers of g for blocks of up to 12288 rows.
-template <int BLOCK, int TW, int SPW, int GV, int DVB, bool XSPLIT>
+//
+// XPAIR: a lane of a tile warp owns TWO CONSECUTIVE rows (a warp walks chunks of 64 consecutive rows) instead of one row
+// of each of SPW slices.  The dominant pattern of a first-touch-numbered Q1 lattice is 9 runs of 3 consecutive columns;
+// the two rows of a lane need 4 consecutive operands per run instead of 2 x 3, so the dominant loop -- which runs at
+// the shared-memory bandwidth -- reads 8 instead of 12 wavefronts per run and 64 rows:
+//   run starts at an even column: 2 x LDS.128 (lane stride 16 bytes: conflict-free);
+//   odd column: LDS.128 for the two middle operands + 2 x LDS.64 for the outer ones, where lanes 0-7 of every group of
+//   16 read the left operand while lanes 8-15 read the right one (and the other way round in the second load): the 16
+//   lanes of a phase then touch 16 different 8-byte slots of a 128-byte line (with every lane reading the same
+//   operand, lanes L and L + 8 would collide), and a select puts the two values in place.
+// Every row still sums its entries in entry order from 0.0 (bit-identical rows); the partial sums of d.h are
+// grouped differently (as they are between the other kernels).  xpair_supported() (host) checks the run structure.
+template <int BLOCK, int TW, int SPW, int GV, int DVB, bool XSPLIT, bool XPAIR = false>
 __global__ void __launch_bounds__(BLOCK, 1)
     cg_persistent_win2(PatView A, const __grid_constant__ DomPat D, const uint32_t *__restrict__ dom_mask, const double *__restrict__ b,
                        double *x, double *g, double *d, double *dt, double *h,
@@ -251,6 +267,7 @@ __global__ void __launch_bounds__(BLOCK, 1)
       } else if (warp >= TW) {
         // remainder rows (this block's share of ALL of them, not the ones it owns): 8 per warp and round, 4 lanes per
         // row; h goes to global memory, the owner reads it there
+        const unsigned long long tr = prof ? gtime() : 0ull;
         for (int gq = g_begin + (warp - TW); gq < g_end; gq += RW) {
           const int k = (gq - g_begin) * 8 + (lane >> 2);
           const bool on = k < k_end - k_begin;
@@ -262,6 +279,133 @@ __global__ void __launch_bounds__(BLOCK, 1)
             h[r] = aq;
             acc += dv * aq;
           }
+        }
+        if (prof && blockIdx.x == prof - 1 && threadIdx.x == TW * 32) g_cg_phase_ns[13] += gtime() - tr;  // (first remainder warp)
+      } else if constexpr (XPAIR) {
+        constexpr int PC = SPW / 2;   // chunks of 64 consecutive rows per warp and tile
+        static_assert(SPW % 2 == 0, "XPAIR walks pairs of slices");
+        const bool hi8 = (lane & 8) != 0;
+        for (int t = 0; t < n_tiles; ++t, ++tc) {
+          const int tile0 = s_begin + t * TILE;
+          const uint32_t st = tc & 1u, use = tc >> 1;
+          // chunk j of this warp: slices tile0 + 2 (j TW + warp) and the next one; the lane's rows are 2 lane, 2 lane + 1 of it
+          uint32_t rc[PC][2];
+          bool any_dom = false, any_general = false;
+#pragma unroll
+          for (int j = 0; j < PC; ++j) {
+            const int s = tile0 + 2 * (j * TW + warp) + (lane >> 4);
+            const uint32_t two = (s < s_end) ? *reinterpret_cast<const uint32_t *>(code + (s - s_begin) * 32 + 2 * (lane & 15))
+                                             : (RC_EMPTY | (RC_EMPTY << 16));
+            rc[j][0] = two & 0xffffu;
+            rc[j][1] = two >> 16;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              any_dom = any_dom || (rc[j][m] & RC_DOM);
+              any_general = any_general || !(rc[j][m] & (RC_DOM | RC_EMPTY | RC_DIAG));
+            }
+          }
+          any_dom = __any_sync(0xffffffffu, any_dom);
+          any_general = __any_sync(0xffffffffu, any_general);
+          double dtv[PC][2];
+#pragma unroll
+          for (int j = 0; j < PC; ++j)
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              dtv[j][m] = 0.0;
+              if (!(rc[j][m] & RC_DOM) && (rc[j][m] & RC_Z)) dtv[j][m] = dt[(tile0 + 2 * (j * TW + warp)) * 32 + 2 * lane + m];
+            }
+          GMG_PHASE(8)
+          if (!mbar_wait(full + st, use & 1u)) pipeline_ok = false;
+          GMG_PHASE(9)
+          // byte address of the lane's first row of chunk 0 in the window; chunk j is j * TW * 64 rows further
+          const char *w = reinterpret_cast<const char *>(win + st * D.win_elems + warp * 64 + 2 * lane);
+          const char *wp = w + (hi8 ? 24 : 0), *wq = w + (hi8 ? 0 : 24);
+          double ad[PC][2], dr[PC][2];
+#pragma unroll
+          for (int j = 0; j < PC; ++j) ad[j][0] = ad[j][1] = dr[j][0] = dr[j][1] = 0.0;
+          if (any_dom) {
+            // run r of chunk j is loaded right after run r - 1 of that chunk has been consumed: its registers are free
+            // then, and the loads have the arithmetic of the other chunks to arrive (the parity of every run is a
+            // compile-time constant: no branches, the whole loop is one basic block)
+            double v[PC][4];
+            auto load_run = [&](int r, int j) {
+              const int wb = D.wbyte[3 * r];
+              if ((XP_ODD >> r) & 1u) {
+                const double2 mid = *reinterpret_cast<const double2 *>(w + wb + 8 + j * (TW * 64 * 8));
+                const double p = *reinterpret_cast<const double *>(wp + wb + j * (TW * 64 * 8));
+                const double q = *reinterpret_cast<const double *>(wq + wb + j * (TW * 64 * 8));
+                v[j][0] = hi8 ? q : p;
+                v[j][1] = mid.x;
+                v[j][2] = mid.y;
+                v[j][3] = hi8 ? p : q;
+              } else {
+                const double2 a2 = *reinterpret_cast<const double2 *>(w + wb + j * (TW * 64 * 8));
+                const double2 b2 = *reinterpret_cast<const double2 *>(w + wb + 16 + j * (TW * 64 * 8));
+                v[j][0] = a2.x;
+                v[j][1] = a2.y;
+                v[j][2] = b2.x;
+                v[j][3] = b2.y;
+              }
+            };
+#pragma unroll
+            for (int j = 0; j < PC; ++j) load_run(0, j);
+#pragma unroll
+            for (int r = 0; r < XP_RUNS; ++r) {
+#pragma unroll
+              for (int j = 0; j < PC; ++j) {
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                  ad[j][m] = fma(D.val[3 * r], v[j][m], ad[j][m]);
+                  ad[j][m] = fma(D.val[3 * r + 1], v[j][m + 1], ad[j][m]);
+                  ad[j][m] = fma(D.val[3 * r + 2], v[j][m + 2], ad[j][m]);
+                }
+                if (r == XP_DIAG) {  // the run around the diagonal: d of the lane's own rows
+                  dr[j][0] = v[j][1];
+                  dr[j][1] = v[j][2];
+                }
+                if (r + 1 < XP_RUNS) load_run(r + 1, j);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < PC; ++j) {
+              dr[j][0] = *reinterpret_cast<const double *>(w + D.diag_wbyte + j * (TW * 64 * 8));
+              dr[j][1] = *reinterpret_cast<const double *>(w + D.diag_wbyte + 8 + j * (TW * 64 * 8));
+            }
+          }
+          // this warp is done with the stage: hand it back to the producer
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty_bar + st)) : "memory");
+          GMG_PHASE(10)
+#pragma unroll
+          for (int j = 0; j < PC; ++j) {
+            const int li = (tile0 + 2 * (j * TW + warp) - s_begin) * 32 + 2 * lane;  // local index of the lane's first row
+            const int r0 = (tile0 + 2 * (j * TW + warp)) * 32 + 2 * lane;
+            // (measured: branches on the row codes, as here, beat a branch-free version of this epilogue that fetches
+            // diagval for every row and selects -- 32.5 against 33.3 us per inner iteration at 64k atoms)
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              const uint32_t c = rc[j][m];
+              const bool general = !(c & (RC_DOM | RC_EMPTY | RC_DIAG));
+              const bool z = !(c & RC_DOM) && (c & RC_Z);
+              if (z) dr[j][m] = dtv[j][m];
+              if (c & RC_DIAG) ad[j][m] = fma(diagval[c & RC_ID], dr[j][m], 0.0);
+              if (any_general) {  // (a dominant-compatible row with a dominant column outside the matrix: a handful at most)
+                const double ag = pat_row_dot_lanes<false>(T, general ? (c & RC_ID) : empty_id, d + r0 + m, z, dr[j][m]);
+                if (general) ad[j][m] = ag;
+              }
+              if (!(c & RC_EMPTY)) acc += dr[j][m] * ad[j][m];
+            }
+            // (h of a remainder row is written by the warp that walks it -- to global memory, which is where hloc points
+            // when h does not fit in shared memory: never store over it)
+            const bool e0 = rc[j][0] & RC_EMPTY, e1 = rc[j][1] & RC_EMPTY;
+            if (!e0 && !e1) *reinterpret_cast<double2 *>(hloc + li) = make_double2(ad[j][0], ad[j][1]);
+            else {
+              if (!e0) hloc[li] = ad[j][0];
+              if (!e1) hloc[li + 1] = ad[j][1];
+            }
+          }
+          GMG_PHASE(11)
         }
       } else {
         for (int t = 0; t < n_tiles; ++t, ++tc) {

@@ -108,6 +108,32 @@ def test_compressed_coarse_matrix_is_lossless(capi, lattice8):
     assert out[2][3]["cg_iter_bytes"] < 0.35 * out[0][3]["cg_iter_bytes"]  # ~ the 88 n bytes of the vectors
 
 
+def test_window_kernel_with_two_rows_per_lane_is_the_default_and_changes_nothing(capi, lattice8, goldens, monkeypatch):
+    """The coarse-grid CG's window kernel walks the dominant pattern of a Q1 lattice with two consecutive rows per lane
+    (XPAIR, csrc/pattern_win2.cuh: kernel ids 7 / 8) unless GMG_WIN2_VARIANT forces the one-row-per-lane loop (5 / 6): the
+    rows are summed in the same entry order, so both take the cluster log's 97 iterations to the same residual and
+    solution."""
+    P = lattice8
+    gold = goldens["cluster_ssor_run"][0]["cycles"][0]
+    out = {}
+    for variant in (None, "0", "3"):
+        if variant is None:
+            monkeypatch.delenv("GMG_WIN2_VARIANT", raising=False)
+        else:
+            monkeypatch.setenv("GMG_WIN2_VARIANT", variant)
+        g = capi.Gmg()
+        hand_over(P, g)
+        kid = g.coarse_kernel(capi.GMG_LEVEL, 0)
+        assert kid in ((5, 6) if variant == "0" else (7, 8)), (variant, kid)
+        out[variant] = g.cg_solve(capi.GMG_LEVEL, 0, P.b, 1000, 1e-10)
+        g.close()
+    for variant in (None, "3"):
+        assert out[variant][1] == out["0"][1] == gold["its"] == 97
+        assert abs(out[variant][2] - out["0"][2]) <= 1e-9 * out["0"][2]
+        assert rel_l2(out[variant][0], out["0"][0]) < 1e-13
+    assert abs(out[None][2] - gold["conv"]) <= 1e-5 * gold["conv"]
+
+
 @pytest.mark.parametrize("kind", ["jacobi", "lex_ssor"])
 def test_smoother_steps_match_oracle(capi, P3, kind):
     from oracle import solver
