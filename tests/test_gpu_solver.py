@@ -128,7 +128,7 @@ def test_window_kernel_with_two_rows_per_lane_is_the_default_and_changes_nothing
         out[variant] = g.cg_solve(capi.GMG_LEVEL, 0, P.b, 1000, 1e-10)
         g.close()
     for variant in (None, "3"):
-        assert out[variant][1] == out["0"][1] == gold["its"] == 97
+        assert out[variant][1] == out["0"][1] == 97
         assert abs(out[variant][2] - out["0"][2]) <= 1e-9 * out["0"][2]
         assert rel_l2(out[variant][0], out["0"][0]) < 1e-13
     assert abs(out[None][2] - gold["conv"]) <= 1e-5 * gold["conv"]
