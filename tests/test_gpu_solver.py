@@ -112,26 +112,28 @@ def test_window_kernel_with_two_rows_per_lane_is_the_default_and_changes_nothing
     """The coarse-grid CG's window kernel walks the dominant pattern of a Q1 lattice with two consecutive rows per lane
     (XPAIR, csrc/pattern_win2.cuh: kernel ids 7 / 8) unless GMG_WIN2_VARIANT forces the one-row-per-lane loop (5 / 6): the
     rows are summed in the same entry order, so both take the cluster log's 97 iterations to the same residual and
-    solution."""
+    solution.  "global": the layout of levels too large for shared memory (h and the row codes in global memory: ids 6 / 8)."""
     P = lattice8
     gold = goldens["cluster_ssor_run"][0]["cycles"][0]
     out = {}
-    for variant in (None, "0", "3"):
+    for variant, layout in ((None, "smem"), ("0", "smem"), ("3", "smem"), (None, "global"), ("0", "global")):
         if variant is None:
             monkeypatch.delenv("GMG_WIN2_VARIANT", raising=False)
         else:
             monkeypatch.setenv("GMG_WIN2_VARIANT", variant)
+        monkeypatch.setenv("GMG_WIN_GLOBAL_CODES", "1" if layout == "global" else "0")
         g = capi.Gmg()
         hand_over(P, g)
         kid = g.coarse_kernel(capi.GMG_LEVEL, 0)
-        assert kid in ((5, 6) if variant == "0" else (7, 8)), (variant, kid)
-        out[variant] = g.cg_solve(capi.GMG_LEVEL, 0, P.b, 1000, 1e-10)
+        assert kid == (5 if variant == "0" else 7) + (1 if layout == "global" else 0), (variant, layout, kid)
+        out[variant, layout] = g.cg_solve(capi.GMG_LEVEL, 0, P.b, 1000, 1e-10)
         g.close()
-    for variant in (None, "3"):
-        assert out[variant][1] == out["0"][1] == 97
-        assert abs(out[variant][2] - out["0"][2]) <= 1e-9 * out["0"][2]
-        assert rel_l2(out[variant][0], out["0"][0]) < 1e-13
-    assert abs(out[None][2] - gold["conv"]) <= 1e-5 * gold["conv"]
+    ref = out["0", "smem"]
+    for key, (x, its, res) in out.items():
+        assert its == ref[1] == 97, key
+        assert abs(res - ref[2]) <= 1e-9 * ref[2], key
+        assert rel_l2(x, ref[0]) < 1e-13, key
+    assert abs(out[None, "smem"][2] - gold["conv"]) <= 1e-5 * gold["conv"]
 
 
 @pytest.mark.parametrize("kind", ["jacobi", "lex_ssor"])
