@@ -64,6 +64,9 @@ void ParameterReader::declare_parameters() {
   prm.declare_entry("Refinement indicator", "KellyAndResidual", Patterns::Selection("KellyAndResidual | Kelly"),
                     "KellyAndResidual = the shipped source (src/step-50.cc:1040-1081); Kelly = the older build that "
                     "produced the cluster logs (marks with the Kelly estimator alone)");
+  prm.declare_entry("Initial guess", "Transferred", Patterns::Selection("Transferred | Zero"),
+                    "Transferred = the shipped source: the solve of a refined mesh starts from the interpolated solution "
+                    "(src/step-50.cc:1095-1121); Zero = the older build behind the step-16 / tests_2D / tests_3D goldens");
   prm.declare_entry("Energy postprocessing atom limit", "300", Patterns::Integer(),
                     "postprocess_electrostatic_energy runs only below this atom count (reference: 300)");
   prm.declare_entry("Energy norm error atom limit", "0", Patterns::Integer(),
@@ -168,6 +171,7 @@ LaplaceProblem<dim>::LaplaceProblem(
     energy_atom_limit = (unsigned int)prm.get_integer("Energy postprocessing atom limit");
     energy_norm_atom_limit = (unsigned int)prm.get_integer("Energy norm error atom limit");
     indicator_with_residual = prm.get("Refinement indicator") == "KellyAndResidual";
+    zero_initial_guess = prm.get("Initial guess") == "Zero";
     prm.leave_subsection();
   } catch (const ExcParameter &) {
     prm.leave_subsection();
@@ -736,6 +740,10 @@ void LaplaceProblem<dim>::refine_grid(const unsigned int &cycle) {
   const std::vector<double> previous_solution = distributed_solution;
   triangulation->refine(refine_flags);
   setup_system(cycle);
+  if (zero_initial_guess) {  // `Initial guess = Zero`
+    solution.assign(mg_dof_handler->n, 0.0);
+    return;
+  }
   // SolutionTransfer::interpolate + set_zero on the device (gmg_transfer_solution): the host provides the index tables
   // (which old dof is which new dof, the 27 dofs of every refined cell), the values never pass through host arithmetic
   const TransferTables T = transfer_tables(old_res, *old_dofs, *triangulation, *mg_dof_handler);

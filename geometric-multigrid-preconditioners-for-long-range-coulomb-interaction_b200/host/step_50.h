@@ -154,6 +154,7 @@ class LaplaceProblem {
   unsigned int energy_atom_limit = 300;
   unsigned int energy_norm_atom_limit = 0;  // 0: always (reference source)
   bool indicator_with_residual = true;  // false: Kelly part only (the build behind the cluster logs)
+  bool zero_initial_guess = false;      // true: every cycle's solve starts from 0 (the build behind the step-16 goldens)
   // Matrix assembly = Device: the system matrix and the level-0 matrix are assembled on the GPU from the cell -> dof
   // maps (gmg_assemble_matrix: the same CSR, bit for bit) instead of on the host; patch levels stay on the host
   bool device_assembly = false;

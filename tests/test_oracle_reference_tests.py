@@ -67,20 +67,38 @@ def test_rc_variation_rhs_norms(goldens):
 @pytest.mark.parametrize("key,dim", [("gaussian_function_3d", 3), ("gaussian_function_2d", 2)])
 def test_gaussian_function_without_atoms(goldens, key, dim):
     """tests_3D / tests_2D gaussian-charges.mpirun=1.output: no atom file, the right-hand side is
-    GaussianCharges::RightHandSide (include/step_50.h:321-329); 8 adaptive cycles.  Cycle 0: every printed number
-    (7 / 6 Jacobi iterations).  Later cycles: cells, DoFs per level and solution norms (that older build started
-    the later solves from another initial guess: its starting residuals are not the shipped source's)."""
+    GaussianCharges::RightHandSide (include/step_50.h:321-329); 8 adaptive cycles, every printed number of every cycle
+    (iteration counts 7,7,9,9,9,9,10,10 in 3D, 6,6,7,7,8,8,8,8 in 2D).  The build behind these files started the solve
+    of every cycle from zero (its starting residual of cycle 1 is || b ||, not the residual of an interpolated
+    solution): `initial_guess="zero"`; with the shipped source's transferred guess the meshes and solution norms are the
+    same and the starting residuals smaller."""
     gold = goldens[key][0]["cycles"]
     assert len(gold) == 8
-    P = problem.from_prm_string(hyper_cube_prm(-2.5, 2.5, 4, 8, cutoff=3, atom="", dim=dim), smoother="jacobi",
-                                indicator="kelly")
-    recs = P.run()
-    check_cycle(recs[0], gold[0])
+    prm = hyper_cube_prm(-2.5, 2.5, 4, 8, cutoff=3, atom="", dim=dim)
+    recs = problem.from_prm_string(prm, smoother="jacobi", indicator="kelly", initial_guess="zero").run()
     for rec, g in zip(recs, gold):
-        assert rec["n_active_cells"] == g["n_active_cells"]
-        assert rec["n_dofs_level"] == g["n_dofs_level"]
-        for k in ("sol_l1", "sol_l2", "sol_linf"):
-            assert abs(rec[k] - g[k]) <= printed_tol(g[k + "_digits"]) + 1e-7 * abs(g[k]), (g["cycle"], k)
+        check_cycle(rec, g, conv_rel=1e-4)
+    if dim == 2:
+        shipped = problem.from_prm_string(prm, smoother="jacobi", indicator="kelly").run()
+        for rec, old, g in zip(shipped, recs, gold):
+            assert rec["n_dofs_level"] == g["n_dofs_level"]
+            assert abs(rec["sol_l2"] - g["sol_l2"]) <= printed_tol(g["sol_l2_digits"]) + 1e-7 * g["sol_l2"]
+            assert rec["cycle"] == 0 or rec["start"] < old["start"]
+
+
+@pytest.mark.parametrize("key,dim", [("step16_3d", 3), ("step16_2d", 2)])
+def test_step16_all_adaptive_cycles(goldens, key, dim):
+    """tests_3D / tests_2D step-16.mpirun=1.output: all 5 adaptive cycles of the Step16 problem (coefficient jump,
+    f = 10) -- cells, DoFs per level, starting residuals, iteration counts 8,11,10,14,14 / 7,10,11,13,13, convergence
+    values, solution norms -- with the settings of the build that wrote them (Jacobi smoothing, Kelly marking, zero
+    initial guess).  test_oracle_goldens.py pins cycle 0 with the defaults."""
+    gold = goldens[key][0]["cycles"]
+    assert len(gold) == 5
+    P = problem.from_prm_string(make_prm("Step16", dim=dim, nref=4, cycles=5, atom="x"), smoother="jacobi",
+                                indicator="kelly", initial_guess="zero")
+    recs = P.run()
+    for rec, g in zip(recs, gold):
+        check_cycle(rec, g, conv_rel=1e-4)
 
 
 @pytest.mark.parametrize("key", ["gaussian_charges_mpirun3", "gaussian_charges_mpirun7"])
