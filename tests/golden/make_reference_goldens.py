@@ -87,6 +87,7 @@ FILES = {
     "gaussian_charges_mpirun3": "tests/gaussian-charges.mpirun=3.output",
     "gaussian_charges_mpirun7": "tests/gaussian-charges.mpirun=7.output",
     "step16_3d": "tests_3D/step-16.mpirun=1.output",
+    "step16_with_atoms": "tests/step-16.mpirun=1.output",
     "step16_2d": "tests_2D/step-16.mpirun=1.output",
     "gaussian_function_3d": "tests_3D/gaussian-charges.mpirun=1.output",
     "gaussian_function_2d": "tests_2D/gaussian-charges.mpirun=1.output",

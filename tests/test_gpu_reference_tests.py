@@ -64,6 +64,18 @@ def test_step16_all_adaptive_cycles(goldens):
         check_cycle(rec, g, conv_rel=1e-3)
 
 
+def test_step16_mesh_with_atom_right_hand_side(goldens):
+    """tests/step-16.mpirun=1.output through `LaplaceProblem`: the Step16 problem with the Gaussian charge density of two
+    atoms as right-hand side (no lists), all 5 adaptive cycles (8,10,11,10,14 iterations)."""
+    from conftest import make_prm
+    gold = goldens["step16_with_atoms"][0]["cycles"]
+    text, recs = hostlib.run_problem(make_prm("Step16", nref=4, cycles=5, atom="atom_2.data", flag="false", cutoff=3,
+                                              extra=OLD_BUILD + ZERO_GUESS))
+    assert "Number of atoms: 2" in text and len(recs) == 5
+    for rec, g in zip(recs, gold):
+        check_cycle(rec, g, conv_rel=1e-3)
+
+
 def test_binning_reproduces_the_cell_data_transfer_lists(goldens):
     """tests/cell_data_transfer_test.mpirun=1.output (the only golden that prints atom lists) through `gmg_bin_atoms`:
     the 2D cells become 3D cells in the plane of the atoms (z = 0: the four vertices at z = h are never the nearest), so

@@ -101,6 +101,20 @@ def test_step16_all_adaptive_cycles(goldens, key, dim):
         check_cycle(rec, g, conv_rel=1e-4)
 
 
+def test_step16_mesh_with_atom_right_hand_side(goldens):
+    """tests/step-16.mpirun=1.output: `Problem = Step16` (unit cube refined 4 times, coefficient jump, homogeneous BC) run
+    WITH an atom file, so the right-hand side is the Gaussian charge density of the 2 atoms of tests/atom_2.data summed
+    over all atoms (that build had no atom lists): every printed number of all 5 adaptive cycles (8,10,11,10,14
+    iterations; Jacobi smoothing, Kelly marking, zero initial guess)."""
+    gold = goldens["step16_with_atoms"][0]
+    assert gold["n_atoms"] == 2 and len(gold["cycles"]) == 5
+    P = problem.from_prm_string(make_prm("Step16", nref=4, cycles=5, atom="atom_2.data", flag="false", cutoff=3),
+                                smoother="jacobi", indicator="kelly", initial_guess="zero")
+    recs = P.run(energy_gate=0)
+    for rec, g in zip(recs, gold["cycles"]):
+        check_cycle(rec, g, conv_rel=1e-4)
+
+
 @pytest.mark.parametrize("key", ["gaussian_charges_mpirun3", "gaussian_charges_mpirun7"])
 def test_rank_independent_numbers_of_the_parallel_goldens(goldens, key):
     """tests/gaussian-charges.mpirun=3 / 7.output against the 1-rank file the oracle reproduces digit by digit
