@@ -209,3 +209,15 @@ def test_cell_data_transfer_atom_lists(goldens):
             assert mine == {tuple(gl["center"]): gl["atoms"] for gl in c["cell_lists"]}, (key, level)
             if key == "cell_data_transfer":  # one rank: also the visiting order (parent by parent, children in z-order)
                 assert [tuple(gl["center"]) for gl in c["cell_lists"]] == list(mine)
+
+
+def test_multi_rank_goldens_covered_by_the_one_rank_reproduction(goldens):
+    """The 3- and 7-rank outputs of the Jacobi-smoothed reference tests carry, line by line, the numbers of their
+    1-rank outputs (checked when the goldens were transcribed, tests/golden/make_reference_goldens.py): reproducing the
+    1-rank files digit by digit -- the tests above and in test_oracle_goldens.py -- reproduces these 16 files as well."""
+    same = set(goldens["same_numbers_as_one_rank"])
+    for stem in ("tests_3D/step-16", "tests_2D/step-16", "tests_3D/gaussian-charges", "tests_2D/gaussian-charges",
+                 "tests/step-16", "tests/test_with_optimal_parameters"):
+        assert {"%s.mpirun=%d.output" % (stem, r) for r in (3, 7)} <= same
+    assert "tests_rhs_rc_variation/rc_variation.mpirun=3.output" in same
+    assert len(same) == 16
