@@ -26,11 +26,11 @@ constexpr int WIN2_TILE_SLICES = 48;                     // slices per tile: 24 
 constexpr int WIN2_TILE_ROWS = WIN2_TILE_SLICES * 32;
 constexpr int WIN2_MAX_BLOCKS = 256;                     // slots one lane polls: 8
 constexpr int WIN2_CHANNELS = 4;
-constexpr int WIN2_SLOT_U64_MAX = 128;
+constexpr int WIN2_SLOT_U64_MAX = 128;                   // largest distance of two blocks' slots (in 64-bit words: 1 KB)
 // XPAIR (below) is compiled for the dominant pattern of a Q1 lattice with an odd number of vertices per line: 9 runs of
 // 3 consecutive columns, runs 0, 2, 4, 6, 8 start at an odd window position, the diagonal is the middle entry of run 4
 constexpr int XP_RUNS = 9, XP_DIAG = 4;
-constexpr uint32_t XP_ODD = 0x155u;                   // largest distance of two blocks' slots (in 64-bit words: 1 KB)
+constexpr uint32_t XP_ODD = 0x155u;
 
 __device__ __forceinline__ void llg_store(uint64_t *p /*16-byte aligned pair*/, double v, uint32_t tag) {
   const uint64_t bits = (uint64_t)__double_as_longlong(v);
@@ -116,13 +116,17 @@ __host__ __device__ inline Win2Layout win2_layout(int win_elems, int n_pat, int 
 //
 // XPAIR: a lane of a tile warp owns TWO CONSECUTIVE rows (a warp walks chunks of 64 consecutive rows) instead of one row
 // of each of SPW slices.  The dominant pattern of a first-touch-numbered Q1 lattice is 9 runs of 3 consecutive columns;
-// the two rows of a lane need 4 consecutive operands per run instead of 2 x 3, so the dominant loop -- which runs at
-// the shared-memory bandwidth -- reads 8 instead of 12 wavefronts per run and 64 rows:
+// the two rows of a lane need 4 consecutive operands per run instead of 2 x 3, so the dominant loop reads 8 instead of
+// 12 shared-memory wavefronts per run and 64 rows:
 //   run starts at an even column: 2 x LDS.128 (lane stride 16 bytes: conflict-free);
 //   odd column: LDS.128 for the two middle operands + 2 x LDS.64 for the outer ones, where lanes 0-7 of every group of
 //   16 read the left operand while lanes 8-15 read the right one (and the other way round in the second load): the 16
 //   lanes of a phase then touch 16 different 8-byte slots of a 128-byte line (with every lane reading the same
 //   operand, lanes L and L + 8 would collide), and a select puts the two values in place.
+// Fewer wavefronts alone bought nothing (B200, 64k atoms: 12.5 -> 11.5 us for the loop): with 8 tile warps the loop is
+// bound by the latency of "loads, wait, dependent DFMAs" per run.  What made it 6.8 us: the run parities are
+// compile-time constants (XP_ODD: the loop is one basic block) and run r + 1 of a chunk is loaded right after run r of
+// that chunk has been consumed, into the same registers, while the other chunks' DFMAs issue.
 // Every row still sums its entries in entry order from 0.0 (bit-identical rows); the partial sums of d.h are
 // grouped differently (as they are between the other kernels).  xpair_supported() (host) checks the run structure.
 template <int BLOCK, int TW, int SPW, int GV, int DVB, bool XSPLIT, bool XPAIR = false>
