@@ -178,7 +178,9 @@ int gmg_debug_vcycle_profile(gmg_handle h, int enable, double out_ms[4]);
 int gmg_debug_cg_blocks(gmg_handle h, double out_ns[768]);
 /* Which persistent CG kernel gmg_cg_solve / the coarse solve runs on this matrix: 0 plain SELL, 1 CSELL,
  * 2 row patterns with L1 gathers (also the multi-GPU kernel), 3 row patterns with TMA-filled shared-memory windows,
- * 4 the same with the row codes read from global memory (more than ~35 k rows per SM). */
+ * 4 the same with the row codes read from global memory (more than ~35 k rows per SM); 5 / 6 the second-generation
+ * window kernel (tagged-word grid reductions, g in registers) with h = A d of a block's rows in shared / global memory,
+ * 7 / 8 the same with two consecutive rows per lane in the dominant loop (the default on Q1 lattices). */
 int gmg_coarse_kernel(gmg_handle h, int which, int level, int *kernel);
 /* accumulated device time (ms, CUDA events on the handle's stream) and launch count of the
  * persistent coarse-CG kernel since the last reset; inner iterations summed in *iters. */
